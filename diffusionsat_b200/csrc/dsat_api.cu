@@ -1,0 +1,844 @@
+// libdsat.so: context, buffers, launch orchestration and the C ABI of include/dsat.h.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dsat.h"
+#include "dsat_common.cuh"
+#include "dsat_gemm_simt.cuh"
+#include "dsat_message.cuh"
+#include "dsat_norm_head.cuh"
+#ifdef DSAT_WITH_TCGEN05
+#include "dsat_gemm_tc.cuh"
+#endif
+
+using namespace dsat;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t count = 0;
+    cudaError_t alloc(size_t n) {
+        release();
+        count = n;
+        if (n == 0) return cudaSuccess;
+        return cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; count = 0;
+    }
+    cudaError_t upload(const T* host, size_t n, cudaStream_t s) {
+        return cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+struct PackedLayer {          // one launched linear op
+    DevBuf<float> w, b;
+#ifdef DSAT_WITH_TCGEN05
+    DevBuf<__nv_bfloat16> w_bf16;   // [N, K] K-major copy for the tensor-core path
+#endif
+    int K = 0, N = 0;
+};
+
+enum OpId { OP_V1 = 0, OP_Q2, OP_L2, OP_L3, OP_C1, OP_C2, OP_U1, OP_U2, OP_U3, OP_O1, OP_O2, OP_COUNT };
+
+}  // namespace
+
+struct dsat_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    long long launches = 0;
+    int precision = DSAT_F32;
+
+    // model
+    bool has_model = false;
+    int F = 0, Q = 0, HQ = 0, HL = 0, HC = 0, HU = 0, HO = 0;
+    PackedLayer ops[OP_COUNT];
+
+    // graph
+    bool has_graph = false;
+    int n = 0, m = 0, nnz = 0, n_graphs = 0, chains = 0, group_graphs = 0, n_groups = 0, total_graphs = 0;
+    int words = 0;
+    long long Nt = 0, Mt = 0;
+    DevBuf<int> cl_rowptr, cl_lit, lit_rowptr, lit_clause, var_seg, clause_seg;
+    DevBuf<float> deg_w, vdeg_w, rev_w;
+
+    // activations
+    bool has_buffers = false;
+    DevBuf<float> VROW, CROW, H1, H2, QS, LIT, CH, COUT, U1, U2, UOUT, SPRE, O1, LOGITS, OUT;
+    DevBuf<float2> X;
+    DevBuf<int> labels, done, steps_taken, rounds_run, graph_sat, graph_map, latch_step, sat_now;
+    DevBuf<float> loss_sum, graph_loss;
+    DevBuf<unsigned char> BITS, LAST, LATCH, FINAL, is_sat, sat_any;
+    DevBuf<unsigned long long> packed;
+    // injected noise staging
+    DevBuf<float> inj_normals, inj_uniforms, inj_noisy;
+    DevBuf<int> inj_labels;
+
+    int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
+    int ldc() const { return F + 2 * Q; }
+    int ldh1() const { return HQ + HL; }
+};
+
+#define CK_CUDA(ctx, expr)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);           \
+            return DSAT_ERR_CUDA;                                                       \
+        }                                                                               \
+    } while (0)
+
+#define CK_ARG(ctx, cond, msg)                                                          \
+    do {                                                                                \
+        if (!(cond)) { (ctx)->err = (msg); return DSAT_ERR_ARG; }                       \
+    } while (0)
+
+#define LAUNCHED(ctx)                                                                   \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        CK_CUDA(ctx, cudaGetLastError());                                               \
+    } while (0)
+
+namespace {
+
+UnitGraphDev graph_view(const dsat_ctx* c) {
+    UnitGraphDev g;
+    g.n = c->n; g.m = c->m; g.nnz = c->nnz; g.n_graphs = c->n_graphs;
+    g.cl_rowptr = c->cl_rowptr.p; g.cl_lit = c->cl_lit.p;
+    g.lit_rowptr = c->lit_rowptr.p; g.lit_clause = c->lit_clause.p;
+    g.var_seg = c->var_seg.p; g.clause_seg = c->clause_seg.p;
+    g.deg_w = c->deg_w.p; g.vdeg_w = c->vdeg_w.p; g.rev_w = c->rev_w.p;
+    return g;
+}
+
+int ensure_buffers(dsat_ctx* c) {
+    if (c->has_buffers) return DSAT_OK;
+    if (!c->has_model || !c->has_graph) { c->err = "set the model and the graph first"; return DSAT_ERR_STATE; }
+    const size_t Nt = (size_t)c->Nt, Mt = (size_t)c->Mt;
+    CK_CUDA(c, c->VROW.alloc(Nt * c->ldv()));
+    CK_CUDA(c, c->CROW.alloc(Mt * c->ldc()));
+    CK_CUDA(c, c->H1.alloc(Nt * c->ldh1()));
+    CK_CUDA(c, c->H2.alloc(Nt * c->HL));
+    CK_CUDA(c, c->QS.alloc(Nt * 3 * c->Q));
+    CK_CUDA(c, c->LIT.alloc(Nt * 2 * c->Q));
+    CK_CUDA(c, c->CH.alloc(Mt * c->HC));
+    CK_CUDA(c, c->COUT.alloc(Mt * (c->Q + c->F)));
+    CK_CUDA(c, c->U1.alloc(Nt * c->HU));
+    CK_CUDA(c, c->U2.alloc(Nt * c->HU));
+    CK_CUDA(c, c->UOUT.alloc(Nt * c->F));
+    CK_CUDA(c, c->SPRE.alloc(Nt * c->F));
+    CK_CUDA(c, c->O1.alloc(Nt * c->HO));
+    CK_CUDA(c, c->LOGITS.alloc(Nt * DSAT_LOGIT_PAD));
+    CK_CUDA(c, c->OUT.alloc(Nt));
+    CK_CUDA(c, c->X.alloc(Nt + 1));
+    CK_CUDA(c, c->labels.alloc(Nt));
+    CK_CUDA(c, c->BITS.alloc(Nt));
+    CK_CUDA(c, c->LAST.alloc(Nt));
+    CK_CUDA(c, c->LATCH.alloc(Nt));
+    CK_CUDA(c, c->FINAL.alloc(Nt));
+    const size_t G = (size_t)c->total_graphs, NG = (size_t)c->n_groups;
+    CK_CUDA(c, c->done.alloc(NG));
+    CK_CUDA(c, c->steps_taken.alloc(NG));
+    CK_CUDA(c, c->rounds_run.alloc(NG));
+    CK_CUDA(c, c->loss_sum.alloc(NG));
+    CK_CUDA(c, c->graph_sat.alloc(G));
+    CK_CUDA(c, c->graph_map.alloc(G));
+    CK_CUDA(c, c->graph_loss.alloc(G));
+    CK_CUDA(c, c->latch_step.alloc(G));
+    CK_CUDA(c, c->sat_now.alloc(G));
+    CK_CUDA(c, c->is_sat.alloc(G));
+    CK_CUDA(c, c->sat_any.alloc(G));
+    CK_CUDA(c, c->packed.alloc(G * c->words));
+    // padded columns must be zero forever: clear everything once
+    CK_CUDA(c, cudaMemsetAsync(c->VROW.p, 0, c->VROW.count * sizeof(float), c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->CROW.p, 0, c->CROW.count * sizeof(float), c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->OUT.p, 0, c->OUT.count * sizeof(float), c->stream));
+    c->has_buffers = true;
+    return DSAT_OK;
+}
+
+void release_buffers(dsat_ctx* c) {
+    c->VROW.release(); c->CROW.release(); c->H1.release(); c->H2.release(); c->QS.release(); c->LIT.release();
+    c->CH.release(); c->COUT.release(); c->U1.release(); c->U2.release(); c->UOUT.release(); c->SPRE.release();
+    c->O1.release(); c->LOGITS.release(); c->OUT.release(); c->X.release(); c->labels.release();
+    c->BITS.release(); c->LAST.release(); c->LATCH.release(); c->FINAL.release();
+    c->done.release(); c->steps_taken.release(); c->rounds_run.release(); c->loss_sum.release();
+    c->graph_sat.release(); c->graph_map.release(); c->graph_loss.release(); c->latch_step.release();
+    c->sat_now.release(); c->is_sat.release(); c->sat_any.release(); c->packed.release();
+    c->inj_normals.release(); c->inj_uniforms.release(); c->inj_noisy.release(); c->inj_labels.release();
+    c->has_buffers = false;
+}
+
+// ---------------------------------------------------------------------------- launch helpers
+int run_linear(dsat_ctx* c, int op, const float* A, int lda, float* Y, int ldy, long long rows, int epi) {
+    LinearOp l;
+    l.A = A; l.lda = lda; l.W = c->ops[op].w.p; l.ldw = c->ops[op].N; l.bias = c->ops[op].b.p;
+    l.Y = Y; l.ldy = ldy; l.rows = (int)rows; l.K = c->ops[op].K; l.N = c->ops[op].N; l.epi = epi; l.qmaps = c->Q;
+    CK_CUDA(c, launch_sgemm(l, c->stream));
+    c->launches++;
+    return DSAT_OK;
+}
+
+template <typename KernelLauncher>
+int dispatch_width(dsat_ctx* c, int width, KernelLauncher&& fn) {
+    switch (width) {
+        case 64: fn(std::integral_constant<int, 2>()); break;
+        case 128: fn(std::integral_constant<int, 4>()); break;
+        case 256: fn(std::integral_constant<int, 8>()); break;
+        default: c->err = "feature width must be 64, 128 or 256"; return DSAT_ERR_UNSUPPORTED;
+    }
+    return DSAT_OK;
+}
+
+struct LossScalars { float t, ts, norm_plus; };
+
+// host-side fp32 scalars of train_loss (reference model/query_sat.py:41-42,48-53)
+float kl_host(float pa, float pb) {
+    float qa = 1.0f - pa;
+    float t1 = pa == 0.f ? 0.f : pa * (logf(pa) - logf(pb));
+    float t2 = qa == 0.f ? 0.f : qa * (log1pf(-pa) - log1pf(-pb));
+    return t1 + t2;
+}
+LossScalars loss_scalars(float noise_scale) {
+    LossScalars s;
+    s.t = powf(noise_scale, 0.5f);
+    s.ts = fminf(s.t + 0.01f, 1.0f);
+    float pa = 0.0f * (1.0f - s.ts) + s.ts / 2.0f;      // distribution_at_time(0, ts)
+    float pb = 0.0f * (1.0f - 1.0f) + 1.0f / 2.0f;      // distribution_at_time(0, 1)
+    s.norm_plus = kl_host(pa, pb) + 1e-4f;
+    return s;
+}
+
+int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const float* uniforms_dev,
+               const int* labels_dev, bool use_x, NoiseSource ns) {
+    const long long Nt = c->Nt;
+    const int threads = 256;
+    step_begin_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
+        Nt, noise_scale, use_x ? c->X.p : nullptr, noisy_dev, uniforms_dev, labels_dev, c->labels.p,
+        c->VROW.p, c->ldv(), c->F, ns);
+    LAUNCHED(c);
+    {   // variables_state = ones, clauses_state = ones (reference model/query_sat.py:141,148)
+        long long tot = Nt * (c->F / 4);
+        fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+            c->VROW.p, c->ldv(), Nt, c->F / 4, 1.0f);
+        LAUNCHED(c);
+        tot = c->Mt * (c->F / 4);
+        fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+            c->CROW.p, c->ldc(), c->Mt, c->F / 4, 1.0f);
+        LAUNCHED(c);
+    }
+    CK_CUDA(c, cudaMemsetAsync(c->done.p, 0, c->done.count * sizeof(int), c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->steps_taken.p, 0xff, c->steps_taken.count * sizeof(int), c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->rounds_run.p, 0, c->rounds_run.count * sizeof(int), c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->loss_sum.p, 0, c->loss_sum.count * sizeof(float), c->stream));
+    return DSAT_OK;
+}
+
+// One message-passing round (reference model/query_sat.py:225-348).
+int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, LossScalars ls) {
+    const long long Nt = c->Nt, Mt = c->Mt;
+    const int F = c->F, Q = c->Q, ldv = c->ldv(), ldc = c->ldc(), ldh1 = c->ldh1();
+    const UnitGraphDev g = graph_view(c);
+    int rc;
+    {
+        const int threads = 256;
+        round_noise_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
+            Nt, normals_dev, c->VROW.p, ldv, F, ns, (unsigned)round);
+        LAUNCHED(c);
+    }
+    // v1 -> [hidden of variables_query | first hidden of lit_query]            (:240, :252)
+    if ((rc = run_linear(c, OP_V1, c->VROW.p, ldv, c->H1.p, ldh1, Nt, EPI_LRELU))) return rc;
+    // query (+ softplus pair)                                                   (:240)
+    if ((rc = run_linear(c, OP_Q2, c->H1.p, ldh1, c->QS.p, 3 * Q, Nt, EPI_QUERY))) return rc;
+    // lit_query layers 2, 3                                                     (:252)
+    if ((rc = run_linear(c, OP_L2, c->H1.p + c->HQ, ldh1, c->H2.p, c->HL, Nt, EPI_LRELU))) return rc;
+    if ((rc = run_linear(c, OP_L3, c->H2.p, c->HL, c->LIT.p, 2 * Q, Nt, EPI_LINEAR))) return rc;
+    // clause side gather: clause_messages and 4*clauses_loss                    (:241, :248, :255-256)
+    rc = dispatch_width(c, Q, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        clause_gather_kernel<V><<<gather_grid(Mt, c->sm_count), GATHER_WARPS * 32, 0, c->stream>>>(
+            g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
+    });
+    if (rc) return rc;
+    LAUNCHED(c);
+    // clause_update MLP                                                          (:258-261)
+    if ((rc = run_linear(c, OP_C1, c->CROW.p, ldc, c->CH.p, c->HC, Mt, EPI_LRELU))) return rc;
+    if ((rc = run_linear(c, OP_C2, c->CH.p, c->HC, c->COUT.p, Q + F, Mt, EPI_LINEAR))) return rc;
+    // literal side gather (reads the OLD clause state's neighbours only through cl4/COUT)   (:245-246, :269-273)
+    rc = dispatch_width(c, Q, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        literal_gather_kernel<V><<<gather_grid(Nt, c->sm_count), GATHER_WARPS * 32, 0, c->stream>>>(
+            g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
+    });
+    if (rc) return rc;
+    LAUNCHED(c);
+    // clause PairNorm + residual + carry                                        (:263-266, :348)
+    rc = dispatch_width(c, F, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
+        pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->clause_seg.p, c->n_graphs, c->m, c->total_graphs,
+                                                         c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
+    });
+    if (rc) return rc;
+    LAUNCHED(c);
+    // update_gate MLP                                                            (:277-278)
+    if ((rc = run_linear(c, OP_U1, c->VROW.p, ldv, c->U1.p, c->HU, Nt, EPI_LRELU))) return rc;
+    if ((rc = run_linear(c, OP_U2, c->U1.p, c->HU, c->U2.p, c->HU, Nt, EPI_LRELU))) return rc;
+    if ((rc = run_linear(c, OP_U3, c->U2.p, c->HU, c->UOUT.p, F, Nt, EPI_LINEAR))) return rc;
+    // variables PairNorm + residual + carry                                     (:279-280, :347)
+    rc = dispatch_width(c, F, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
+        pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->var_seg.p, c->n_graphs, c->n, c->total_graphs,
+                                                         c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
+    });
+    if (rc) return rc;
+    LAUNCHED(c);
+    // variables_output MLP                                                       (:283)
+    if ((rc = run_linear(c, OP_O1, c->SPRE.p, F, c->O1.p, c->HO, Nt, EPI_LRELU))) return rc;
+    if ((rc = run_linear(c, OP_O2, c->O1.p, c->HO, c->LOGITS.p, DSAT_LOGIT_PAD, Nt, EPI_LINEAR))) return rc;
+    // logit map selection, SAT check, early exit                                 (:289-338)
+    head_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->group_graphs, c->LOGITS.p,
+                                                         DSAT_LOGIT_PAD, c->labels.p, ls.t, ls.ts, ls.norm_plus,
+                                                         c->done.p, c->OUT.p, c->BITS.p, c->graph_sat.p,
+                                                         c->graph_loss.p, c->graph_map.p);
+    LAUNCHED(c);
+    group_finalize_kernel<<<(c->n_groups + 127) / 128, 128, 0, c->stream>>>(
+        c->n_groups, c->group_graphs, c->total_graphs, round, c->graph_sat.p, c->graph_loss.p, c->done.p,
+        c->steps_taken.p, c->loss_sum.p, c->rounds_run.p);
+    LAUNCHED(c);
+    return DSAT_OK;
+}
+
+int pack_weights(dsat_ctx* c, const float* const* kernels, const float* const* biases, const int* in_dims,
+                 const int* out_dims) {
+    // reference layer order: query0 query1 lit0 lit1 lit2 clause0 clause1 upd0 upd1 upd2 out0 out1
+    const int F = c->F, Q = c->Q, A = DSAT_AUX_PAD;
+    const int hq = out_dims[0], hl = out_dims[2], hc = out_dims[5], hu = out_dims[7], ho = out_dims[10];
+    c->HQ = pad16(hq); c->HL = pad16(hl); c->HC = pad16(hc); c->HU = pad16(hu); c->HO = pad16(ho);
+
+    auto upload = [&](int op, int K, int N, const std::vector<float>& w, const std::vector<float>& b) -> int {
+        c->ops[op].K = K; c->ops[op].N = N;
+        CK_CUDA(c, c->ops[op].w.alloc((size_t)K * N));
+        CK_CUDA(c, c->ops[op].b.alloc((size_t)N));
+        CK_CUDA(c, cudaMemcpy(c->ops[op].w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK_CUDA(c, cudaMemcpy(c->ops[op].b.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return DSAT_OK;
+    };
+    // copy a [rows, cols] block of a reference kernel (leading dim src_ld) into a packed matrix
+    auto blit = [](std::vector<float>& dst, int dst_ld, int dst_r, int dst_c, const float* src, int src_ld,
+                   int src_r, int rows, int cols) {
+        for (int r = 0; r < rows; ++r)
+            memcpy(&dst[(size_t)(dst_r + r) * dst_ld + dst_c], src + (size_t)(src_r + r) * src_ld, cols * sizeof(float));
+    };
+    auto plain = [&](int op, int layer, int Kp, int Np) -> int {
+        std::vector<float> w((size_t)Kp * Np, 0.f), b(Np, 0.f);
+        blit(w, Np, 0, 0, kernels[layer], out_dims[layer], 0, in_dims[layer], out_dims[layer]);
+        memcpy(b.data(), biases[layer], out_dims[layer] * sizeof(float));
+        return upload(op, Kp, Np, w, b);
+    };
+    int rc;
+    {   // OP_V1: rows [variables F | aux 9 (+7 zero)], cols [query hidden | lit hidden]
+        const int K = F + A, N = c->HQ + c->HL;
+        std::vector<float> w((size_t)K * N, 0.f), b(N, 0.f);
+        blit(w, N, 0, 0, kernels[0], hq, 0, F + 9, hq);
+        blit(w, N, 0, c->HQ, kernels[2], hl, 0, F + 9, hl);
+        memcpy(b.data(), biases[0], hq * sizeof(float));
+        memcpy(b.data() + c->HQ, biases[2], hl * sizeof(float));
+        if ((rc = upload(OP_V1, K, N, w, b))) return rc;
+    }
+    if ((rc = plain(OP_Q2, 1, c->HQ, Q))) return rc;
+    if ((rc = plain(OP_L2, 3, c->HL, c->HL))) return rc;
+    if ((rc = plain(OP_L3, 4, c->HL, 2 * Q))) return rc;
+    if ((rc = plain(OP_C1, 5, F + 2 * Q, c->HC))) return rc;
+    if ((rc = plain(OP_C2, 6, c->HC, Q + F))) return rc;
+    {   // OP_U1: reference rows [grad Q | variables F | aux 9 | loss_pos Q | loss_neg Q]
+        //        packed rows    [variables F | aux 16 | grad Q | loss_pos Q | loss_neg Q]
+        const int K = F + A + 3 * Q, N = c->HU;
+        std::vector<float> w((size_t)K * N, 0.f), b(N, 0.f);
+        blit(w, N, 0, 0, kernels[7], hu, Q, F + 9, hu);
+        blit(w, N, F + A, 0, kernels[7], hu, 0, Q, hu);
+        blit(w, N, F + A + Q, 0, kernels[7], hu, Q + F + 9, 2 * Q, hu);
+        memcpy(b.data(), biases[7], hu * sizeof(float));
+        if ((rc = upload(OP_U1, K, N, w, b))) return rc;
+    }
+    if ((rc = plain(OP_U2, 8, c->HU, c->HU))) return rc;
+    if ((rc = plain(OP_U3, 9, c->HU, F))) return rc;
+    if ((rc = plain(OP_O1, 10, F, c->HO))) return rc;
+    if ((rc = plain(OP_O2, 11, c->HO, DSAT_LOGIT_PAD))) return rc;
+    return DSAT_OK;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+int dsat_version(void) { return 1; }
+
+int dsat_create(int device, dsat_ctx** out) {
+    if (!out) return DSAT_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return DSAT_ERR_CUDA;
+    dsat_ctx* c = new dsat_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
+    c->stream = c->own_stream;
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return DSAT_OK;
+}
+
+void dsat_destroy(dsat_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    release_buffers(c);
+    for (auto& op : c->ops) {
+        op.w.release(); op.b.release();
+#ifdef DSAT_WITH_TCGEN05
+        op.w_bf16.release();
+#endif
+    }
+    c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
+    c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* dsat_last_error(const dsat_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int dsat_set_stream(dsat_ctx* c, void* s) {
+    if (!c) return DSAT_ERR_ARG;
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+    return DSAT_OK;
+}
+
+int dsat_synchronize(dsat_ctx* c) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DSAT_OK;
+}
+
+int dsat_timer_begin(dsat_ctx* c) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    CK_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    return DSAT_OK;
+}
+
+int dsat_timer_end(dsat_ctx* c, float* ms) {
+    if (!c || !ms) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    CK_CUDA(c, cudaEventSynchronize(c->ev1));
+    CK_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return DSAT_OK;
+}
+
+long long dsat_launch_count(const dsat_ctx* c) { return c ? c->launches : 0; }
+
+int dsat_set_precision(dsat_ctx* c, int dtype) {
+    if (!c) return DSAT_ERR_ARG;
+    if (dtype == DSAT_F32) { c->precision = dtype; return DSAT_OK; }
+#ifdef DSAT_WITH_TCGEN05
+    if (dtype == DSAT_BF16) { c->precision = dtype; return DSAT_OK; }
+#endif
+    c->err = "precision not available in this build";
+    return DSAT_ERR_UNSUPPORTED;
+}
+
+int dsat_set_model(dsat_ctx* c, int n_layers, const float* const* kernels, const float* const* biases,
+                   const int* in_dims, const int* out_dims) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, n_layers == 12 && kernels && biases && in_dims && out_dims, "dsat_set_model: expected 12 layers");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    const int F = in_dims[10], Q = out_dims[1];
+    CK_ARG(c, (F == 64 || F == 128 || F == 256) && (Q == 64 || Q == 128 || Q == 256),
+           "feature_maps and query_maps must be 64, 128 or 256");
+    const int v1 = F + 9;
+    bool ok = in_dims[0] == v1 && in_dims[1] == out_dims[0] && in_dims[2] == v1 && in_dims[3] == out_dims[2] &&
+              in_dims[4] == out_dims[3] && out_dims[4] == 2 * Q && in_dims[5] == F + 2 * Q &&
+              in_dims[6] == out_dims[5] && out_dims[6] == F + Q && in_dims[7] == Q + v1 + 2 * Q &&
+              in_dims[8] == out_dims[7] && in_dims[9] == out_dims[8] && out_dims[9] == F &&
+              in_dims[11] == out_dims[10] && out_dims[11] == DSAT_LOGIT_MAPS;
+    CK_ARG(c, ok, "dsat_set_model: layer dimensions do not form the QuerySAT MLPs");
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->has_buffers && (c->F != F || c->Q != Q)) release_buffers(c);
+    c->F = F; c->Q = Q;
+    int rc = pack_weights(c, kernels, biases, in_dims, out_dims);
+    if (rc) return rc;
+#ifdef DSAT_WITH_TCGEN05
+    if ((rc = tc_pack_weights(c))) return rc;
+#endif
+    c->has_model = true;
+    return DSAT_OK;
+}
+
+int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_t* cl_rowptr, const int32_t* cl_lit,
+                   const int32_t* lit_rowptr, const int32_t* lit_clause, int n_graphs, const int32_t* var_seg,
+                   const int32_t* clause_seg, int n_chains, int group_graphs) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, n_vars > 0 && n_clauses >= 0 && nnz >= 0 && n_graphs > 0 && n_chains > 0, "dsat_set_graph: bad sizes");
+    CK_ARG(c, cl_rowptr && lit_rowptr && var_seg && clause_seg && (nnz == 0 || (cl_lit && lit_clause)),
+           "dsat_set_graph: null index array");
+    CK_ARG(c, cl_rowptr[0] == 0 && cl_rowptr[n_clauses] == nnz && lit_rowptr[0] == 0 && lit_rowptr[2 * n_vars] == nnz,
+           "dsat_set_graph: row pointers do not cover nnz");
+    CK_ARG(c, var_seg[0] == 0 && var_seg[n_graphs] == n_vars && clause_seg[0] == 0 && clause_seg[n_graphs] == n_clauses,
+           "dsat_set_graph: graph segments do not cover the unit");
+    for (int e = 0; e < nnz; ++e) {
+        CK_ARG(c, cl_lit[e] >= 0 && cl_lit[e] < 2 * n_vars, "dsat_set_graph: literal code out of range");
+        CK_ARG(c, lit_clause[e] >= 0 && lit_clause[e] < n_clauses, "dsat_set_graph: clause id out of range");
+    }
+    int max_graph_vars = 0;
+    for (int g = 0; g < n_graphs; ++g) {
+        CK_ARG(c, var_seg[g + 1] > var_seg[g] && clause_seg[g + 1] >= clause_seg[g], "dsat_set_graph: empty or unordered graph segment");
+        if (var_seg[g + 1] - var_seg[g] > max_graph_vars) max_graph_vars = var_seg[g + 1] - var_seg[g];
+    }
+    CK_CUDA(c, cudaSetDevice(c->device));
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    release_buffers(c);
+    c->n = n_vars; c->m = n_clauses; c->nnz = nnz; c->n_graphs = n_graphs; c->chains = n_chains;
+    c->total_graphs = n_graphs * n_chains;
+    c->group_graphs = group_graphs > 0 ? group_graphs : c->total_graphs;
+    c->n_groups = ceil_div(c->total_graphs, c->group_graphs);
+    c->Nt = (long long)n_chains * n_vars;
+    c->Mt = (long long)n_chains * n_clauses;
+    c->words = ceil_div(max_graph_vars, 64);
+    CK_ARG(c, c->Nt < (1ll << 31) - 256 && c->Mt < (1ll << 31) - 256,
+           "dsat_set_graph: too many rows for one context; use fewer chains per context");
+
+    std::vector<float> deg_w(2 * n_vars), vdeg_w(n_vars), rev_w(n_clauses > 0 ? n_clauses : 1);
+    for (int l = 0; l < 2 * n_vars; ++l) {
+        float d = (float)(lit_rowptr[l + 1] - lit_rowptr[l]);
+        deg_w[l] = 1.0f / sqrtf(fmaxf(d, 1.0f));
+    }
+    for (int v = 0; v < n_vars; ++v) {
+        float d = (float)(lit_rowptr[2 * v + 2] - lit_rowptr[2 * v]);
+        vdeg_w[v] = 1.0f / sqrtf(fmaxf(d, 1.0f));
+    }
+    for (int j = 0; j < n_clauses; ++j) {
+        float d = (float)(cl_rowptr[j + 1] - cl_rowptr[j]);
+        rev_w[j] = 1.0f / sqrtf(fmaxf(d, 1.0f));
+    }
+    auto up_i = [&](DevBuf<int>& b, const int32_t* h, size_t cnt) -> cudaError_t {
+        cudaError_t e = b.alloc(cnt > 0 ? cnt : 1);
+        if (e != cudaSuccess || cnt == 0) return e;
+        return cudaMemcpy(b.p, h, cnt * sizeof(int), cudaMemcpyHostToDevice);
+    };
+    auto up_f = [&](DevBuf<float>& b, const std::vector<float>& h) -> cudaError_t {
+        cudaError_t e = b.alloc(h.size());
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+    };
+    CK_CUDA(c, up_i(c->cl_rowptr, cl_rowptr, n_clauses + 1));
+    CK_CUDA(c, up_i(c->cl_lit, cl_lit, nnz));
+    CK_CUDA(c, up_i(c->lit_rowptr, lit_rowptr, 2 * n_vars + 1));
+    CK_CUDA(c, up_i(c->lit_clause, lit_clause, nnz));
+    CK_CUDA(c, up_i(c->var_seg, var_seg, n_graphs + 1));
+    CK_CUDA(c, up_i(c->clause_seg, clause_seg, n_graphs + 1));
+    CK_CUDA(c, up_f(c->deg_w, deg_w));
+    CK_CUDA(c, up_f(c->vdeg_w, vdeg_w));
+    CK_CUDA(c, up_f(c->rev_w, rev_w));
+    c->has_graph = true;
+    return DSAT_OK;
+}
+
+int dsat_words_per_graph(const dsat_ctx* c) { return c ? c->words : 0; }
+
+// ----------------------------------------------------------------------------------- model call
+int dsat_model_call(dsat_ctx* c, float noise_scale, const float* noisy_num, const int32_t* labels,
+                    const float* normals, int rounds, uint64_t seed, uint64_t chain_offset, float* prediction_out,
+                    int32_t* steps_taken, float* loss) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, noisy_num && prediction_out && rounds >= 0, "dsat_model_call: null buffer or negative rounds");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    const size_t Nt = (size_t)c->Nt;
+    CK_CUDA(c, c->inj_noisy.alloc(Nt * 2));
+    CK_CUDA(c, c->inj_noisy.upload(noisy_num, Nt * 2, c->stream));
+    if (labels) {
+        CK_CUDA(c, c->inj_labels.alloc(Nt));
+        CK_CUDA(c, c->inj_labels.upload(labels, Nt, c->stream));
+    }
+    if (normals && rounds > 0) {
+        CK_CUDA(c, c->inj_normals.alloc(Nt * 4 * rounds));
+        CK_CUDA(c, c->inj_normals.upload(normals, Nt * 4 * rounds, c->stream));
+    }
+    NoiseSource ns{seed, chain_offset * (uint64_t)c->n, 0u};
+    if ((rc = begin_call(c, noise_scale, c->inj_noisy.p, nullptr, labels ? c->inj_labels.p : nullptr, false, ns))) return rc;
+    const LossScalars ls = loss_scalars(noise_scale);
+    for (int r = 0; r < rounds; ++r)
+        if ((rc = run_round(c, r, normals ? c->inj_normals.p + (size_t)r * Nt * 4 : nullptr, ns, ls))) return rc;
+    CK_CUDA(c, cudaMemcpyAsync(prediction_out, c->OUT.p, Nt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<float> lsum(c->n_groups);
+    std::vector<int> rrun(c->n_groups);
+    if (steps_taken)
+        CK_CUDA(c, cudaMemcpyAsync(steps_taken, c->steps_taken.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK_CUDA(c, cudaMemcpyAsync(lsum.data(), c->loss_sum.p, c->n_groups * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK_CUDA(c, cudaMemcpyAsync(rrun.data(), c->rounds_run.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (loss)
+        for (int g = 0; g < c->n_groups; ++g) loss[g] = rrun[g] > 0 ? lsum[g] / (float)rrun[g] : 0.f;
+    return DSAT_OK;
+}
+
+// --------------------------------------------------------------------------------------- sampler
+static int sample_enqueue_impl(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t chain_offset,
+                               const float* uniforms_dev, const int* labels_dev, const float* normals_dev) {
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    const long long Nt = c->Nt;
+    const UnitGraphDev g = graph_view(c);
+    {   // x = 0.5 (reference DiffusionSampler.py:86)
+        const long long rows4 = (2 * Nt + 3) / 4;      // X is allocated with one spare float2
+        fill_cols_kernel<<<(unsigned)((rows4 + 255) / 256), 256, 0, c->stream>>>(
+            reinterpret_cast<float*>(c->X.p), 4, rows4, 1, 0.5f);
+        LAUNCHED(c);
+    }
+    CK_CUDA(c, cudaMemsetAsync(c->latch_step.p, 0xff, c->latch_step.count * sizeof(int), c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->sat_any.p, 0, c->sat_any.count, c->stream));
+    for (int t = 0; t < n_steps; ++t) {
+        const double ns_d = 1.0 - (double)t / (double)n_steps;       // Python float (:106)
+        const float noise_scale = (float)ns_d;
+        NoiseSource ns{seed, chain_offset * (uint64_t)c->n, (unsigned)t};
+        if ((rc = begin_call(c, noise_scale, nullptr, uniforms_dev ? uniforms_dev + (size_t)t * Nt : nullptr,
+                             labels_dev ? labels_dev + (size_t)t * Nt : nullptr, true, ns)))
+            return rc;
+        const LossScalars ls = loss_scalars(noise_scale);
+        for (int r = 0; r < n_rounds; ++r) {
+            const float* nrm = normals_dev ? normals_dev + ((size_t)t * n_rounds + r) * Nt * 4 : nullptr;
+            if ((rc = run_round(c, r, nrm, ns, ls))) return rc;
+        }
+        // posterior scalars (reference DiffusionSampler.py:30-33): pow in fp32, max() in Python floats
+        PosteriorScalars ps;
+        const float t1 = powf(noise_scale, 0.5f);
+        const double t_prev = ns_d - 1.0 / (double)n_steps;
+        const float t2 = powf((float)(t_prev > 0.0 ? t_prev : 0.0), 0.5f);
+        const float alpha = (1.0f - t1) / (1.0f - t2);
+        ps.t1 = t1;
+        ps.one_minus_alpha = 1.0f - alpha;
+        step_end_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->OUT.p, c->X.p, ps, t,
+                                                                 c->LAST.p, c->LATCH.p, c->latch_step.p, c->sat_now.p);
+        LAUNCHED(c);
+    }
+    pack_assignments_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->words, c->LAST.p, c->LATCH.p,
+                                                                     c->latch_step.p, c->packed.p, c->is_sat.p, c->FINAL.p);
+    LAUNCHED(c);
+    return DSAT_OK;
+}
+
+int dsat_sample_enqueue(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t chain_offset) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, n_steps > 0 && n_rounds >= 0, "dsat_sample: bad step or round count");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    return sample_enqueue_impl(c, n_steps, n_rounds, seed, chain_offset, nullptr, nullptr, nullptr);
+}
+
+int dsat_sample_fetch(dsat_ctx* c, uint64_t* packed, uint8_t* is_sat, int32_t* latch_step, uint8_t* sat_any_step) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, c->has_buffers, "dsat_sample_fetch: nothing was sampled");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    const size_t G = (size_t)c->total_graphs;
+    if (packed)
+        CK_CUDA(c, cudaMemcpyAsync(packed, c->packed.p, G * c->words * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    if (is_sat) CK_CUDA(c, cudaMemcpyAsync(is_sat, c->is_sat.p, G, cudaMemcpyDeviceToHost, c->stream));
+    if (latch_step)
+        CK_CUDA(c, cudaMemcpyAsync(latch_step, c->latch_step.p, G * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (sat_any_step) {
+        // cum_accuracy of diffusion(): a graph counts once any step's rounded prediction satisfied it,
+        // which is exactly "latched" (reference DiffusionSampler.py:119-130,154-170)
+        std::vector<int> ls(G);
+        CK_CUDA(c, cudaMemcpy(ls.data(), c->latch_step.p, G * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < G; ++i) sat_any_step[i] = ls[i] >= 0;
+    }
+    return DSAT_OK;
+}
+
+int dsat_sample(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t chain_offset, const float* uniforms,
+                const int32_t* labels, const float* normals, uint64_t* packed, uint8_t* is_sat, int32_t* latch_step,
+                uint8_t* sat_any_step) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, n_steps > 0 && n_rounds >= 0, "dsat_sample: bad step or round count");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    const size_t Nt = (size_t)c->Nt;
+    if (uniforms) {
+        CK_CUDA(c, c->inj_uniforms.alloc(Nt * n_steps));
+        CK_CUDA(c, c->inj_uniforms.upload(uniforms, Nt * n_steps, c->stream));
+    }
+    if (labels) {
+        CK_CUDA(c, c->inj_labels.alloc(Nt * n_steps));
+        CK_CUDA(c, c->inj_labels.upload(labels, Nt * n_steps, c->stream));
+    }
+    if (normals && n_rounds > 0) {
+        CK_CUDA(c, c->inj_normals.alloc(Nt * 4 * n_rounds * n_steps));
+        CK_CUDA(c, c->inj_normals.upload(normals, Nt * 4 * n_rounds * n_steps, c->stream));
+    }
+    rc = sample_enqueue_impl(c, n_steps, n_rounds, seed, chain_offset, uniforms ? c->inj_uniforms.p : nullptr,
+                             labels ? c->inj_labels.p : nullptr, (normals && n_rounds > 0) ? c->inj_normals.p : nullptr);
+    if (rc) return rc;
+    return dsat_sample_fetch(c, packed, is_sat, latch_step, sat_any_step);
+}
+
+// ------------------------------------------------------------------------------------------ SpMM
+int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int feat, int dtype, int chains) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, c->has_graph, "dsat_spmm: graph not set");
+    CK_ARG(c, x_dev && y_dev && chains > 0 && (direction == 0 || direction == 1), "dsat_spmm: bad argument");
+    CK_ARG(c, dtype == DSAT_F32 || dtype == DSAT_BF16, "dsat_spmm: dtype must be f32 or bf16");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    const int* rowptr = direction == 0 ? c->cl_rowptr.p : c->lit_rowptr.p;
+    const int* colidx = direction == 0 ? c->cl_lit.p : c->lit_clause.p;
+    const float* scale = direction == 0 ? c->rev_w.p : c->deg_w.p;
+    const int rows_out = direction == 0 ? c->m : 2 * c->n;
+    const int rows_in = direction == 0 ? 2 * c->n : c->m;
+    const int grid = gather_grid((long long)chains * rows_out, c->sm_count);
+    int rc = dispatch_width(c, feat, [&](auto v) {
+        constexpr int V = decltype(v)::value;
+        if (dtype == DSAT_BF16)
+            spmm_segment_sum_kernel<V, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowptr, colidx, scale, rows_out,
+                                                                                         rows_in, chains, x_dev, y_dev);
+        else
+            spmm_segment_sum_kernel<V, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowptr, colidx, scale, rows_out,
+                                                                                          rows_in, chains, x_dev, y_dev);
+    });
+    if (rc) return rc;
+    LAUNCHED(c);
+    return DSAT_OK;
+}
+
+// ----------------------------------------------------------------------------------------- debug
+static int debug_buffer(dsat_ctx* c, int id, float** p, long long* rows, int* ld) {
+    const long long Nt = c->Nt, Mt = c->Mt;
+    switch (id) {
+        case DSAT_BUF_VROW: *p = c->VROW.p; *rows = Nt; *ld = c->ldv(); break;
+        case DSAT_BUF_CROW: *p = c->CROW.p; *rows = Mt; *ld = c->ldc(); break;
+        case DSAT_BUF_H1: *p = c->H1.p; *rows = Nt; *ld = c->ldh1(); break;
+        case DSAT_BUF_H2: *p = c->H2.p; *rows = Nt; *ld = c->HL; break;
+        case DSAT_BUF_QS: *p = c->QS.p; *rows = Nt; *ld = 3 * c->Q; break;
+        case DSAT_BUF_LIT: *p = c->LIT.p; *rows = Nt; *ld = 2 * c->Q; break;
+        case DSAT_BUF_CH: *p = c->CH.p; *rows = Mt; *ld = c->HC; break;
+        case DSAT_BUF_COUT: *p = c->COUT.p; *rows = Mt; *ld = c->Q + c->F; break;
+        case DSAT_BUF_U1: *p = c->U1.p; *rows = Nt; *ld = c->HU; break;
+        case DSAT_BUF_U2: *p = c->U2.p; *rows = Nt; *ld = c->HU; break;
+        case DSAT_BUF_UOUT: *p = c->UOUT.p; *rows = Nt; *ld = c->F; break;
+        case DSAT_BUF_SPRE: *p = c->SPRE.p; *rows = Nt; *ld = c->F; break;
+        case DSAT_BUF_O1: *p = c->O1.p; *rows = Nt; *ld = c->HO; break;
+        case DSAT_BUF_LOGITS: *p = c->LOGITS.p; *rows = Nt; *ld = DSAT_LOGIT_PAD; break;
+        case DSAT_BUF_OUT: *p = c->OUT.p; *rows = Nt; *ld = 1; break;
+        case DSAT_BUF_X: *p = reinterpret_cast<float*>(c->X.p); *rows = Nt; *ld = 2; break;
+        default: c->err = "unknown buffer id"; return DSAT_ERR_ARG;
+    }
+    return DSAT_OK;
+}
+
+int dsat_debug_dims(const dsat_ctx* cc, int buffer, long long* rows, int* ld) {
+    dsat_ctx* c = const_cast<dsat_ctx*>(cc);
+    if (!c || !rows || !ld) return DSAT_ERR_ARG;
+    CK_ARG(c, c->has_model && c->has_graph, "set the model and the graph first");
+    float* p;
+    return debug_buffer(c, buffer, &p, rows, ld);
+}
+
+int dsat_debug_read(dsat_ctx* c, int buffer, float* host_out, long long count) {
+    if (!c || !host_out) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    float* p; long long rows; int ld;
+    if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
+    CK_ARG(c, count == rows * ld, "dsat_debug_read: count must be rows*ld");
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    CK_CUDA(c, cudaMemcpy(host_out, p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+    return DSAT_OK;
+}
+
+int dsat_debug_write(dsat_ctx* c, int buffer, const float* host_in, long long count) {
+    if (!c || !host_in) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    float* p; long long rows; int ld;
+    if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
+    CK_ARG(c, count == rows * ld, "dsat_debug_write: count must be rows*ld");
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    CK_CUDA(c, cudaMemcpy(p, host_in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    return DSAT_OK;
+}
+
+int dsat_debug_begin(dsat_ctx* c, float noise_scale, const float* noisy_num, const int32_t* labels) {
+    if (!c || !noisy_num) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    const size_t Nt = (size_t)c->Nt;
+    CK_CUDA(c, c->inj_noisy.alloc(Nt * 2));
+    CK_CUDA(c, c->inj_noisy.upload(noisy_num, Nt * 2, c->stream));
+    if (labels) {
+        CK_CUDA(c, c->inj_labels.alloc(Nt));
+        CK_CUDA(c, c->inj_labels.upload(labels, Nt, c->stream));
+    }
+    NoiseSource ns{0ull, 0ull, 0u};
+    if ((rc = begin_call(c, noise_scale, c->inj_noisy.p, nullptr, labels ? c->inj_labels.p : nullptr, false, ns))) return rc;
+    // dsat_debug_round re-reads the noise scale from aux column 6 of row 0
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DSAT_OK;
+}
+
+int dsat_debug_round(dsat_ctx* c, int round, const float* normals) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    const size_t Nt = (size_t)c->Nt;
+    if (normals) {
+        CK_CUDA(c, c->inj_normals.alloc(Nt * 4));
+        CK_CUDA(c, c->inj_normals.upload(normals, Nt * 4, c->stream));
+    }
+    float noise_scale = 0.f;
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    CK_CUDA(c, cudaMemcpy(&noise_scale, c->VROW.p + c->F + 6, sizeof(float), cudaMemcpyDeviceToHost));
+    NoiseSource ns{0ull, 0ull, 0u};
+    rc = run_round(c, round, normals ? c->inj_normals.p : nullptr, ns, loss_scalars(noise_scale));
+    if (rc) return rc;
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DSAT_OK;
+}
+
+int dsat_debug_groups(dsat_ctx* c, int32_t* done, int32_t* steps_taken, float* loss_sum, int32_t* graph_sat,
+                      int32_t* graph_map) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, c->has_buffers, "no buffers yet");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (done) CK_CUDA(c, cudaMemcpy(done, c->done.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
+    if (steps_taken) CK_CUDA(c, cudaMemcpy(steps_taken, c->steps_taken.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
+    if (loss_sum) CK_CUDA(c, cudaMemcpy(loss_sum, c->loss_sum.p, c->n_groups * sizeof(float), cudaMemcpyDeviceToHost));
+    if (graph_sat) CK_CUDA(c, cudaMemcpy(graph_sat, c->graph_sat.p, c->total_graphs * sizeof(int), cudaMemcpyDeviceToHost));
+    if (graph_map) CK_CUDA(c, cudaMemcpy(graph_map, c->graph_map.p, c->total_graphs * sizeof(int), cudaMemcpyDeviceToHost));
+    return DSAT_OK;
+}
+
+}  // extern "C"

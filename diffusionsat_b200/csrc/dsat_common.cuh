@@ -1,0 +1,170 @@
+// Shared device helpers for the DiffusionSAT sampling kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define DSAT_AUX_PAD 16      // aux columns of v1 (9 used: normal4, noisy2, noise_scale, denoised2)
+#define DSAT_LOGIT_MAPS 8    // reference model/query_sat.py:99
+#define DSAT_LOGIT_PAD 16
+
+namespace dsat {
+
+__host__ __device__ inline int pad16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------- math
+// softplus with the usual large-argument guard (log1p(exp(x)) otherwise); reference
+// loss/sat.py:132 uses tf.nn.softplus.
+__device__ __forceinline__ float softplus_f(float x) {
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// tf.round(tf.sigmoid(z)) as a bit: half-to-even makes sigma == 0.5 round to 0
+// (reference utils/sat.py:119, satuniformity/DiffusionSampler.py:154).
+__device__ __forceinline__ int sigmoid_bit(float z) { return sigmoid_f(z) > 0.5f ? 1 : 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------- per-lane row vectors
+// A feature row of width W = 32*V floats is spread over a warp: lane l owns, for V >= 4, the
+// float4 chunks at columns c*128 + 4*l (c < V/4); for V == 2 the float2 at column 2*l.
+template <int V> struct LaneVec { float v[V]; };
+
+template <int V>
+__device__ __forceinline__ LaneVec<V> lane_load(const float* __restrict__ row, int lane) {
+    LaneVec<V> r;
+    if constexpr (V == 2) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(row) + lane);
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(row + c * 128) + lane);
+            r.v[4 * c + 0] = t.x; r.v[4 * c + 1] = t.y; r.v[4 * c + 2] = t.z; r.v[4 * c + 3] = t.w;
+        }
+    }
+    return r;
+}
+
+// plain (coherent) load for buffers written earlier in the same kernel
+template <int V>
+__device__ __forceinline__ LaneVec<V> lane_load_rw(const float* row, int lane) {
+    LaneVec<V> r;
+    if constexpr (V == 2) {
+        float2 t = reinterpret_cast<const float2*>(row)[lane];
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c) {
+            float4 t = reinterpret_cast<const float4*>(row + c * 128)[lane];
+            r.v[4 * c + 0] = t.x; r.v[4 * c + 1] = t.y; r.v[4 * c + 2] = t.z; r.v[4 * c + 3] = t.w;
+        }
+    }
+    return r;
+}
+
+template <int V>
+__device__ __forceinline__ void lane_store(float* __restrict__ row, int lane, const LaneVec<V>& r) {
+    if constexpr (V == 2) {
+        reinterpret_cast<float2*>(row)[lane] = make_float2(r.v[0], r.v[1]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c)
+            reinterpret_cast<float4*>(row + c * 128)[lane] =
+                make_float4(r.v[4 * c + 0], r.v[4 * c + 1], r.v[4 * c + 2], r.v[4 * c + 3]);
+    }
+}
+
+// bf16 rows: lane owns the same columns as in the fp32 layout (8-byte loads for V == 4)
+template <int V>
+__device__ __forceinline__ LaneVec<V> lane_load_bf16(const __nv_bfloat16* __restrict__ row, int lane) {
+    LaneVec<V> r;
+    if constexpr (V == 2) {
+        __nv_bfloat162 t = reinterpret_cast<const __nv_bfloat162*>(row)[lane];
+        r.v[0] = __low2float(t); r.v[1] = __high2float(t);
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c) {
+            uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + c * 128) + lane);
+            __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+            __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+            r.v[4 * c + 0] = __low2float(a); r.v[4 * c + 1] = __high2float(a);
+            r.v[4 * c + 2] = __low2float(b); r.v[4 * c + 3] = __high2float(b);
+        }
+    }
+    return r;
+}
+
+template <int V>
+__device__ __forceinline__ void lane_store_bf16(__nv_bfloat16* __restrict__ row, int lane, const LaneVec<V>& r) {
+    if constexpr (V == 2) {
+        reinterpret_cast<__nv_bfloat162*>(row)[lane] = __floats2bfloat162_rn(r.v[0], r.v[1]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(r.v[4 * c + 0], r.v[4 * c + 1]);
+            __nv_bfloat162 b = __floats2bfloat162_rn(r.v[4 * c + 2], r.v[4 * c + 3]);
+            uint2 raw;
+            raw.x = *reinterpret_cast<uint32_t*>(&a);
+            raw.y = *reinterpret_cast<uint32_t*>(&b);
+            reinterpret_cast<uint2*>(row + c * 128)[lane] = raw;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- Philox
+// Philox4x32-10 counter-based generator; the same function is restated in numpy in
+// diffusionsat_b200/philox.py so that host-side tests can inject identical noise.
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ inline Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// 23 random mantissa bits -> [0,1)
+__host__ __device__ inline float u32_to_unit_float(uint32_t x) {
+    uint32_t bits = (x & 0x7fffffu) | 0x3f800000u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(bits) - 1.0f;
+#else
+    float f; memcpy(&f, &bits, 4); return f - 1.0f;
+#endif
+}
+
+enum PhiloxStream : uint32_t { STREAM_NORMAL = 0, STREAM_UNIFORM = 1, STREAM_LABEL = 2 };
+
+// counter = (element lo, element hi, step<<16 | round, stream); key = seed
+__device__ __forceinline__ Philox4 noise_draw(uint64_t seed, uint64_t element, uint32_t step, uint32_t round,
+                                              uint32_t stream) {
+    return philox4x32_10((uint32_t)element, (uint32_t)(element >> 32), (step << 16) | round, stream,
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    float u1 = fmaxf(u32_to_unit_float(a), 1.0e-7f);
+    float ang = 6.283185307179586f * u32_to_unit_float(b);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(ang, &s, &c);
+    n0 = s * rad; n1 = c * rad;
+}
+
+}  // namespace dsat

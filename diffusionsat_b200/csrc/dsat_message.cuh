@@ -1,0 +1,224 @@
+// Message passing over the clause-literal graph: segment-sum SpMM kernels that share ONE adjacency
+// (the unit graph's CSR/CSC) across all chains.  Rows of chain c live at offset c*rows_per_chain, so
+// the index arrays are read once per warp and stay in L1/L2 for every chain.
+//
+// One warp produces one output row; lane l owns the columns described in dsat_common.cuh (float4 per
+// lane at width 128).  Gathered rows are 512-byte contiguous (width 128, fp32): one fully coalesced
+// request per edge, and the edge loop is unrolled so that several requests are in flight per warp.
+//
+//   clause_gather  : reference model/query_sat.py:241 (loss/sat.py:132-135) and :255-256
+//   literal_gather : reference model/query_sat.py:245-246 (closed form of the GradientTape) and :269-273
+//   spmm_*         : the same segment-sum cores on caller buffers (roofline sweeps)
+#pragma once
+#include "dsat_common.cuh"
+
+namespace dsat {
+
+struct UnitGraphDev {
+    int n, m, nnz, n_graphs;            // unit sizes
+    const int* cl_rowptr;               // [m+1]
+    const int* cl_lit;                  // [nnz] literal codes 2*var+sign
+    const int* lit_rowptr;              // [2n+1]
+    const int* lit_clause;              // [nnz]
+    const int* var_seg;                 // [n_graphs+1]
+    const int* clause_seg;              // [n_graphs+1]
+    const float* deg_w;                 // [2n]  rsqrt(max(deg(lit),1))
+    const float* vdeg_w;                // [n]   rsqrt(max(deg(+v)+deg(-v),1))   (the reference's factor 4 is carried by cl4)
+    const float* rev_w;                 // [m]   rsqrt(max(|clause|,1))
+};
+
+constexpr int GATHER_WARPS = 8;
+
+// ------------------------------------------------------------------------------ clause side
+// For clause j of chain c:
+//   cmsg[j] = rev_w[j] * sum_{lit in j} LIT[var(lit)][sign(lit)*Q : +Q]
+//   cl4[j]  = 4 * exp(-sum_{lit in j} SP[var(lit)][sign(lit)*Q : +Q])        SP = softplus(+-query)
+// LIT rows have leading dimension ld_lit (2Q used), SP rows ld_sp with the pair starting at column sp_off.
+// Output goes to OUT[(c*m + j)*ld_out + out_off : +2Q] = [cmsg | cl4].
+template <int V>
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+clause_gather_kernel(UnitGraphDev g, int chains,
+                     const float* __restrict__ LIT, int ld_lit,
+                     const float* __restrict__ SP, int ld_sp, int sp_off,
+                     float* __restrict__ OUT, int ld_out, int out_off) {
+    constexpr int Q = 32 * V;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)chains * g.m;
+    const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * GATHER_WARPS;
+    for (long long w = warp0; w < total; w += stride) {
+        const int c = (int)(w / g.m), j = (int)(w % g.m);
+        const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
+        const size_t vbase = (size_t)c * g.n;
+        LaneVec<V> acc_l, acc_s;
+#pragma unroll
+        for (int i = 0; i < V; ++i) { acc_l.v[i] = 0.f; acc_s.v[i] = 0.f; }
+        int e = e0;
+        for (; e + 3 <= e1; e += 3) {   // 3-SAT fast path: three edges in flight
+            int c0 = __ldg(g.cl_lit + e), c1 = __ldg(g.cl_lit + e + 1), c2 = __ldg(g.cl_lit + e + 2);
+            const size_t r0 = vbase + (c0 >> 1), r1 = vbase + (c1 >> 1), r2 = vbase + (c2 >> 1);
+            LaneVec<V> l0 = lane_load<V>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
+            LaneVec<V> l1 = lane_load<V>(LIT + r1 * ld_lit + (c1 & 1) * Q, lane);
+            LaneVec<V> l2 = lane_load<V>(LIT + r2 * ld_lit + (c2 & 1) * Q, lane);
+            LaneVec<V> s0 = lane_load<V>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
+            LaneVec<V> s1 = lane_load<V>(SP + r1 * ld_sp + sp_off + (c1 & 1) * Q, lane);
+            LaneVec<V> s2 = lane_load<V>(SP + r2 * ld_sp + sp_off + (c2 & 1) * Q, lane);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                acc_l.v[i] = ((acc_l.v[i] + l0.v[i]) + l1.v[i]) + l2.v[i];
+                acc_s.v[i] = ((acc_s.v[i] + s0.v[i]) + s1.v[i]) + s2.v[i];
+            }
+        }
+        for (; e < e1; ++e) {
+            int c0 = __ldg(g.cl_lit + e);
+            const size_t r0 = vbase + (c0 >> 1);
+            LaneVec<V> l0 = lane_load<V>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
+            LaneVec<V> s0 = lane_load<V>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
+#pragma unroll
+            for (int i = 0; i < V; ++i) { acc_l.v[i] += l0.v[i]; acc_s.v[i] += s0.v[i]; }
+        }
+        const float rw = __ldg(g.rev_w + j);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            acc_l.v[i] *= rw;
+            acc_s.v[i] = 4.0f * expf(-acc_s.v[i]);
+        }
+        float* dst = OUT + ((size_t)c * g.m + j) * ld_out + out_off;
+        lane_store<V>(dst, lane, acc_l);
+        lane_store<V>(dst + Q, lane, acc_s);
+    }
+}
+
+// ----------------------------------------------------------------------------- literal side
+// For variable v of chain c (pos = literal code 2v, neg = 2v+1):
+//   S4+- = sum_{clauses j containing +-v} cl4[j]            (cl4 = 4*clauses_loss)
+//   g[v] = (-sigma(q)*S4+ + sigma(-q)*S4-) * vdeg_w[v]      == variables_grad of reference :245-246
+//   vloss+-[v] = deg_w[+-v] * sum_{j containing +-v} MSG[j] == variables_loss_pos/neg of reference :269-273
+// CL4 rows: ld_cl, column cl_off; MSG rows: ld_msg, column 0; QRY rows: ld_q (query in columns [0,Q)).
+// Output OUT[(c*n+v)*ld_out + out_off : +3Q] = [g | vloss+ | vloss-].
+template <int V>
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+literal_gather_kernel(UnitGraphDev g, int chains,
+                      const float* __restrict__ CL4, int ld_cl, int cl_off,
+                      const float* __restrict__ MSG, int ld_msg,
+                      const float* __restrict__ QRY, int ld_q,
+                      float* __restrict__ OUT, int ld_out, int out_off) {
+    constexpr int Q = 32 * V;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)chains * g.n;
+    const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * GATHER_WARPS;
+    for (long long w = warp0; w < total; w += stride) {
+        const int c = (int)(w / g.n), v = (int)(w % g.n);
+        const size_t cbase = (size_t)c * g.m;
+        LaneVec<V> s4[2], ms[2];
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) { s4[sgn].v[i] = 0.f; ms[sgn].v[i] = 0.f; }
+            const int code = 2 * v + sgn;
+            const int e0 = __ldg(g.lit_rowptr + code), e1 = __ldg(g.lit_rowptr + code + 1);
+            int e = e0;
+            for (; e + 2 <= e1; e += 2) {
+                const size_t j0 = cbase + __ldg(g.lit_clause + e), j1 = cbase + __ldg(g.lit_clause + e + 1);
+                LaneVec<V> a0 = lane_load<V>(CL4 + j0 * ld_cl + cl_off, lane);
+                LaneVec<V> a1 = lane_load<V>(CL4 + j1 * ld_cl + cl_off, lane);
+                LaneVec<V> b0 = lane_load<V>(MSG + j0 * ld_msg, lane);
+                LaneVec<V> b1 = lane_load<V>(MSG + j1 * ld_msg, lane);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    s4[sgn].v[i] = (s4[sgn].v[i] + a0.v[i]) + a1.v[i];
+                    ms[sgn].v[i] = (ms[sgn].v[i] + b0.v[i]) + b1.v[i];
+                }
+            }
+            for (; e < e1; ++e) {
+                const size_t j0 = cbase + __ldg(g.lit_clause + e);
+                LaneVec<V> a0 = lane_load<V>(CL4 + j0 * ld_cl + cl_off, lane);
+                LaneVec<V> b0 = lane_load<V>(MSG + j0 * ld_msg, lane);
+#pragma unroll
+                for (int i = 0; i < V; ++i) { s4[sgn].v[i] += a0.v[i]; ms[sgn].v[i] += b0.v[i]; }
+            }
+        }
+        const size_t row = (size_t)c * g.n + v;
+        LaneVec<V> q = lane_load<V>(QRY + row * ld_q, lane);
+        const float vw = __ldg(g.vdeg_w + v);
+        const float dwp = __ldg(g.deg_w + 2 * v), dwn = __ldg(g.deg_w + 2 * v + 1);
+        LaneVec<V> grad;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const float sg = sigmoid_f(q.v[i]), sgn_ = sigmoid_f(-q.v[i]);
+            grad.v[i] = (-sg * s4[0].v[i] + sgn_ * s4[1].v[i]) * vw;
+            ms[0].v[i] *= dwp;
+            ms[1].v[i] *= dwn;
+        }
+        float* dst = OUT + row * ld_out + out_off;
+        lane_store<V>(dst, lane, grad);
+        lane_store<V>(dst + Q, lane, ms[0]);
+        lane_store<V>(dst + 2 * Q, lane, ms[1]);
+    }
+}
+
+// --------------------------------------------------------------------- standalone segment sums
+// Y[c, r, :] = scale[r] * sum_{e in row r} X[c, col(e), :]   on caller buffers, fp32 or bf16 storage.
+// dir 0: clause <- literal (X rows are literal codes: [2n, F] per chain, i.e. the [n, 2F] layout);
+// dir 1: literal <- clause (X rows are clauses: [m, F] per chain).
+template <int V, bool BF16>
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+spmm_segment_sum_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                        const float* __restrict__ scale, int rows_out, int rows_in, int chains,
+                        const void* __restrict__ Xv, void* __restrict__ Yv) {
+    constexpr int F = 32 * V;
+    const int lane = threadIdx.x & 31;
+    const long long total = (long long)chains * rows_out;
+    const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * GATHER_WARPS;
+    for (long long w = warp0; w < total; w += stride) {
+        const int c = (int)(w / rows_out), r = (int)(w % rows_out);
+        const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
+        const size_t xbase = (size_t)c * rows_in;
+        LaneVec<V> acc;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
+        int e = e0;
+        for (; e + 4 <= e1; e += 4) {
+            size_t i0 = xbase + __ldg(colidx + e), i1 = xbase + __ldg(colidx + e + 1);
+            size_t i2 = xbase + __ldg(colidx + e + 2), i3 = xbase + __ldg(colidx + e + 3);
+            LaneVec<V> x0, x1, x2, x3;
+            if constexpr (BF16) {
+                const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(Xv);
+                x0 = lane_load_bf16<V>(X + i0 * F, lane); x1 = lane_load_bf16<V>(X + i1 * F, lane);
+                x2 = lane_load_bf16<V>(X + i2 * F, lane); x3 = lane_load_bf16<V>(X + i3 * F, lane);
+            } else {
+                const float* X = reinterpret_cast<const float*>(Xv);
+                x0 = lane_load<V>(X + i0 * F, lane); x1 = lane_load<V>(X + i1 * F, lane);
+                x2 = lane_load<V>(X + i2 * F, lane); x3 = lane_load<V>(X + i3 * F, lane);
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc.v[i] = (((acc.v[i] + x0.v[i]) + x1.v[i]) + x2.v[i]) + x3.v[i];
+        }
+        for (; e < e1; ++e) {
+            size_t i0 = xbase + __ldg(colidx + e);
+            LaneVec<V> x0;
+            if constexpr (BF16) x0 = lane_load_bf16<V>(reinterpret_cast<const __nv_bfloat16*>(Xv) + i0 * F, lane);
+            else x0 = lane_load<V>(reinterpret_cast<const float*>(Xv) + i0 * F, lane);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc.v[i] += x0.v[i];
+        }
+        const float s = __ldg(scale + r);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] *= s;
+        const size_t yrow = (size_t)c * rows_out + r;
+        if constexpr (BF16) lane_store_bf16<V>(reinterpret_cast<__nv_bfloat16*>(Yv) + yrow * F, lane, acc);
+        else lane_store<V>(reinterpret_cast<float*>(Yv) + yrow * F, lane, acc);
+    }
+}
+
+inline int gather_grid(long long total_rows, int sm_count) {
+    // grid-stride kernels: a multiple of the SM count (8 resident CTAs of 256 threads per SM, 4 waves)
+    long long blocks = (total_rows + GATHER_WARPS - 1) / GATHER_WARPS;
+    const long long cap = (long long)sm_count * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace dsat

@@ -1,0 +1,326 @@
+// PairNorm + residual/carry, the logit-map head with the per-graph SAT check, the batch early-exit
+// bookkeeping, and the per-denoising-step kernels (randomized rounding, posterior, first-SAT latch,
+// bit packing).  All of them treat a graph (= one chain of one formula) as the unit of work: graph
+// `gid` is formula `gid % n_graphs` of chain `gid / n_graphs`, its nodes are contiguous rows.
+#pragma once
+#include "dsat_common.cuh"
+#include "dsat_message.cuh"
+
+namespace dsat {
+
+template <int V>
+__device__ __forceinline__ int lane_col(int lane, int i) {
+    if constexpr (V == 2) return lane * 2 + i;
+    else return (i >> 2) * 128 + lane * 4 + (i & 3);
+}
+
+// ------------------------------------------------------------------------------------ PairNorm
+// reference layers/normalization.py:43-71 with graph_norm = membership/count (model/query_sat.py:206-211):
+//   x -= sum_{nodes of the graph} x * (1/count)      per feature
+//   x *= rsqrt(mean_f(x^2) + 1e-6)                   per node
+// fused with the caller's  new = x*0.25 + 0.1*old  (model/query_sat.py:265-266, 279-280) and with the
+// end-of-round  s = s*0.2 + s*0.8  (:347-348).  PRE (optional) receives the state before that carry:
+// it is what variables_output reads (:283).
+template <int V>
+__global__ void __launch_bounds__(256)
+pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
+                const float* __restrict__ SRC, int ld_src, int src_off,
+                float* __restrict__ STATE, int ld_state,
+                float* __restrict__ PRE, int ld_pre) {
+    constexpr int F = 32 * V;
+    __shared__ float red[8][F];
+    __shared__ float mean_s[F];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
+        const int chain = gid / n_graphs_unit, lg = gid % n_graphs_unit;
+        const size_t base = (size_t)chain * rows_per_chain;
+        const size_t r0 = base + __ldg(seg + lg), r1 = base + __ldg(seg + lg + 1);
+        const float wgt = 1.0f / (float)(r1 - r0);
+        LaneVec<V> sum;
+#pragma unroll
+        for (int i = 0; i < V; ++i) sum.v[i] = 0.f;
+        for (size_t r = r0 + warp; r < r1; r += 8) {
+            LaneVec<V> x = lane_load<V>(SRC + r * ld_src + src_off, lane);
+#pragma unroll
+            for (int i = 0; i < V; ++i) sum.v[i] += x.v[i] * wgt;
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) red[warp][lane_col<V>(lane, i)] = sum.v[i];
+        __syncthreads();
+        for (int col = tid; col < F; col += 256) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w][col];
+            mean_s[col] = s;
+        }
+        __syncthreads();
+        LaneVec<V> mean;
+#pragma unroll
+        for (int i = 0; i < V; ++i) mean.v[i] = mean_s[lane_col<V>(lane, i)];
+        for (size_t r = r0 + warp; r < r1; r += 8) {
+            LaneVec<V> x = lane_load<V>(SRC + r * ld_src + src_off, lane);
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < V; ++i) { x.v[i] -= mean.v[i]; ss += x.v[i] * x.v[i]; }
+            ss = warp_sum(ss);
+            const float inv = rsqrtf(ss / (float)F + 1.0e-6f);
+            float* srow = STATE + r * ld_state;
+            LaneVec<V> old = lane_load_rw<V>(srow, lane);
+            LaneVec<V> nw, carried;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                nw.v[i] = __fadd_rn(__fmul_rn(x.v[i] * inv, 0.25f), __fmul_rn(0.1f, old.v[i]));
+                carried.v[i] = __fadd_rn(__fmul_rn(nw.v[i], 0.2f), __fmul_rn(nw.v[i], 0.8f));
+            }
+            if (PRE) lane_store<V>(PRE + r * ld_pre, lane, nw);
+            lane_store<V>(srow, lane, carried);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------- head
+// KL(Bernoulli(pa) || Bernoulli(pb)), probabilities as parameters (TFP's registered Bernoulli KL,
+// external): pa*(log pa - log pb) + (1-pa)*(log1p(-pa) - log1p(-pb)), 0*inf := 0.
+__device__ __forceinline__ float bernoulli_kl(float pa, float pb) {
+    const float qa = 1.0f - pa;
+    const float t1 = pa == 0.f ? 0.f : pa * (logf(pa) - logf(pb));
+    const float t2 = qa == 0.f ? 0.f : qa * (log1pf(-pa) - log1pf(-pb));
+    return t1 + t2;
+}
+
+__device__ __forceinline__ int graph_clauses_unsat(const UnitGraphDev& g, int lg, size_t rowbase,
+                                                   const unsigned char* bits, int tid, int nthreads) {
+    int unsat = 0;
+    const int c0 = __ldg(g.clause_seg + lg), c1 = __ldg(g.clause_seg + lg + 1);
+    for (int j = c0 + tid; j < c1; j += nthreads) {
+        const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
+        int sat = 0;
+        for (int e = e0; e < e1; ++e) {
+            const int code = __ldg(g.cl_lit + e);
+            sat |= ((int)bits[rowbase + (code >> 1)] != (code & 1));   // literal true: bit 1 for +v, bit 0 for -v
+        }
+        unsat |= !sat;
+    }
+    return unsat;
+}
+
+// Logit-map selection (reference model/query_sat.py:289-292,317-320,328-329 with train_loss :40-53)
+// and is_batch_sat's per-clause test (utils/sat.py:118-124), one CTA per graph.  Graphs whose
+// early-exit group already finished are skipped: their OUT keeps the logits of the round that broke.
+__global__ void __launch_bounds__(128)
+head_kernel(UnitGraphDev g, int total_graphs, int group_graphs,
+            const float* __restrict__ LOGITS, int ld_logits, const int* __restrict__ labels,
+            float t, float ts, float norm_plus,
+            const int* __restrict__ done, float* __restrict__ OUT, unsigned char* BITS,
+            int* __restrict__ graph_sat, float* __restrict__ graph_loss, int* __restrict__ graph_map) {
+    __shared__ float red[4][DSAT_LOGIT_MAPS];
+    __shared__ int best_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = blockIdx.x;
+    if (gid >= total_graphs) return;
+    if (done[gid / group_graphs]) return;
+    const int chain = gid / g.n_graphs, lg = gid % g.n_graphs;
+    const int v0 = __ldg(g.var_seg + lg), v1 = __ldg(g.var_seg + lg + 1);
+    const size_t rowbase = (size_t)chain * g.n;
+    const float wgt = 1.0f / (float)(v1 - v0);
+
+    float part[DSAT_LOGIT_MAPS];
+#pragma unroll
+    for (int k = 0; k < DSAT_LOGIT_MAPS; ++k) part[k] = 0.f;
+    for (int v = v0 + tid; v < v1; v += 128) {
+        const size_t row = rowbase + v;
+        const float y = (float)__ldg(labels + row);
+        const float pa = y * (1.0f - ts) + ts / 2.0f;
+        const float4 za = __ldg(reinterpret_cast<const float4*>(LOGITS + row * ld_logits));
+        const float4 zb = __ldg(reinterpret_cast<const float4*>(LOGITS + row * ld_logits + 4));
+        const float z[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+#pragma unroll
+        for (int k = 0; k < DSAT_LOGIT_MAPS; ++k) {
+            const float pb = sigmoid_f(z[k]) * (1.0f - t) + t / 2.0f;
+            part[k] += (bernoulli_kl(pa, pb) / norm_plus) * wgt;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < DSAT_LOGIT_MAPS; ++k) {
+        const float s = warp_sum(part[k]);
+        if (lane == 0) red[warp][k] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float tot[DSAT_LOGIT_MAPS];
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < DSAT_LOGIT_MAPS; ++k) {
+            tot[k] = (red[0][k] + red[1][k]) + (red[2][k] + red[3][k]);
+            if (tot[k] < tot[best]) best = k;           // ties keep the lowest index (tf.argmin)
+        }
+        // sum(sort_desc(loss) * [1,4,9,...,64]); the caller divides by 204 (model/query_sat.py:311-313)
+        for (int a = 1; a < DSAT_LOGIT_MAPS; ++a) {
+            float key = tot[a]; int b = a - 1;
+            while (b >= 0 && tot[b] < key) { tot[b + 1] = tot[b]; --b; }
+            tot[b + 1] = key;
+        }
+        float acc = 0.f;
+        for (int k = 0; k < DSAT_LOGIT_MAPS; ++k) acc += tot[k] * (float)((k + 1) * (k + 1));
+        graph_loss[gid] = acc;
+        graph_map[gid] = best;
+        best_s = best;
+    }
+    __syncthreads();
+    const int best = best_s;
+    for (int v = v0 + tid; v < v1; v += 128) {
+        const size_t row = rowbase + v;
+        const float z = __ldg(LOGITS + row * ld_logits + best);
+        OUT[row] = z;
+        BITS[row] = (unsigned char)sigmoid_bit(z);
+    }
+    __syncthreads();
+    const int unsat = __syncthreads_or(graph_clauses_unsat(g, lg, rowbase, BITS, tid, 128));
+    if (tid == 0) graph_sat[gid] = !unsat;
+}
+
+// Batch-global early exit (reference model/query_sat.py:330-338): a group (= one reference batch of
+// graphs) stops at the first round in which every one of its graphs is satisfied.  Also accumulates
+// the scalar loss of :311-315,323.
+__global__ void group_finalize_kernel(int n_groups, int group_graphs, int total_graphs, int round,
+                                      const int* __restrict__ graph_sat, const float* __restrict__ graph_loss,
+                                      int* done, int* steps_taken, float* loss_sum, int* rounds_run) {
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= n_groups || done[grp]) return;
+    const int g0 = grp * group_graphs;
+    const int g1 = min(g0 + group_graphs, total_graphs);
+    int all = 1;
+    float ls = 0.f;
+    for (int gi = g0; gi < g1; ++gi) { all &= graph_sat[gi]; ls += graph_loss[gi]; }
+    loss_sum[grp] += ls / 204.0f;
+    rounds_run[grp] += 1;
+    steps_taken[grp] = round;
+    if (all) done[grp] = 1;
+}
+
+// ------------------------------------------------------------------------------ per-step kernels
+struct NoiseSource {
+    unsigned long long seed;
+    unsigned long long element_offset;   // global index of local row 0 (global_chain0 * n_unit)
+    unsigned int step;
+};
+
+// Model-call start: aux columns [normal4 | noisy2 | noise_scale | 0 0 | pad], state = ones, labels.
+// If `uniforms_or_null`/X are given this is also the randomized rounding of the denoising step
+// (reference model/query_sat.py:55-60, DiffusionSampler.py:107-109): r = floor(x0 + U), x = [r, 1-r].
+__global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X,
+                                  const float* __restrict__ noisy_in,      // [n_rows,2] explicit noisy_num or null
+                                  const float* __restrict__ uniforms_in,   // [n_rows] or null -> Philox
+                                  const int* __restrict__ labels_in,       // [n_rows] or null -> Philox
+                                  int* __restrict__ labels,
+                                  float* __restrict__ VROW, int ld, int aux_off, NoiseSource ns) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    float a, b;
+    if (noisy_in) {
+        a = noisy_in[2 * r]; b = noisy_in[2 * r + 1];
+    } else {
+        const float u = uniforms_in ? uniforms_in[r]
+                                    : u32_to_unit_float(noise_draw(ns.seed, ns.element_offset + r, ns.step, 0, STREAM_UNIFORM).x);
+        a = floorf(X[r].x + u);
+        b = 1.0f - a;
+    }
+    if (X) X[r] = make_float2(a, b);
+    float* aux = VROW + (size_t)r * ld + aux_off;
+    reinterpret_cast<float4*>(aux)[1] = make_float4(a, b, noise_scale, 0.f);
+    reinterpret_cast<float4*>(aux)[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(aux)[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    labels[r] = labels_in ? labels_in[r]
+                          : (int)(noise_draw(ns.seed, ns.element_offset + r, ns.step, 0, STREAM_LABEL).x & 1u);
+}
+
+// Fresh N(0,1)[.,4] every round (reference model/query_sat.py:239).
+__global__ void round_noise_kernel(long long n_rows, const float* __restrict__ normals_in /*[n_rows,4] or null*/,
+                                   float* __restrict__ VROW, int ld, int aux_off, NoiseSource ns, unsigned int round) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    float4 nrm;
+    if (normals_in) {
+        nrm = __ldg(reinterpret_cast<const float4*>(normals_in) + r);
+    } else {
+        Philox4 p = noise_draw(ns.seed, ns.element_offset + r, ns.step, round, STREAM_NORMAL);
+        box_muller(p.x, p.y, nrm.x, nrm.y);
+        box_muller(p.z, p.w, nrm.z, nrm.w);
+    }
+    reinterpret_cast<float4*>(VROW + (size_t)r * ld + aux_off)[0] = nrm;
+}
+
+__global__ void fill_cols_kernel(float* __restrict__ dst, int ld, long long rows, int cols4, float value) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols4) return;
+    const long long r = i / cols4; const int c = (int)(i % cols4);
+    reinterpret_cast<float4*>(dst + (size_t)r * ld)[c] = make_float4(value, value, value, value);
+}
+
+// End of a denoising step, one CTA per graph: p = sigmoid(prediction); posterior
+// q(x_{t-1} | x_t, x0_hat) (reference DiffusionSampler.py:29-37,127-129, written exactly as there:
+// x_hat uses t1); xx = round(p); first-SAT latch (:154-170).
+struct PosteriorScalars { float t1, one_minus_alpha; };
+
+__global__ void __launch_bounds__(128)
+step_end_kernel(UnitGraphDev g, int total_graphs, const float* __restrict__ OUT, float2* X,
+                PosteriorScalars ps, int step, unsigned char* LAST, unsigned char* LATCH,
+                int* __restrict__ latch_step, int* __restrict__ sat_now) {
+    const int tid = threadIdx.x;
+    const int gid = blockIdx.x;
+    if (gid >= total_graphs) return;
+    const int chain = gid / g.n_graphs, lg = gid % g.n_graphs;
+    const int v0 = __ldg(g.var_seg + lg), v1 = __ldg(g.var_seg + lg + 1);
+    const size_t rowbase = (size_t)chain * g.n;
+    const float t1 = ps.t1, oma = ps.one_minus_alpha;
+    for (int v = v0 + tid; v < v1; v += 128) {
+        const size_t row = rowbase + v;
+        const float p = sigmoid_f(OUT[row]);
+        const float2 x = X[row];
+        const float h0 = (1.0f - p) * (1.0f - t1) + t1 / 2.0f;      // distribution_at_time(x0, t1)
+        const float h1 = p * (1.0f - t1) + t1 / 2.0f;
+        const float u0 = (x.x * (1.0f - oma) + oma / 2.0f) * h0;     // distribution_at_time(x, 1-alpha_t) * x_new
+        const float u1 = (x.y * (1.0f - oma) + oma / 2.0f) * h1;
+        const float s = (u0 + u1) + 1.0e-8f;
+        X[row] = make_float2(u0 / s, u1 / s);
+        LAST[row] = (unsigned char)(p > 0.5f ? 1 : 0);
+    }
+    __syncthreads();
+    const int unsat = __syncthreads_or(graph_clauses_unsat(g, lg, rowbase, LAST, tid, 128));
+    if (tid == 0) sat_now[gid] = !unsat;
+    if (!unsat && latch_step[gid] < 0) {
+        for (int v = v0 + tid; v < v1; v += 128) LATCH[rowbase + v] = LAST[rowbase + v];
+        __syncthreads();
+        if (tid == 0) latch_step[gid] = step;
+    }
+}
+
+// Final assignment of a graph = latched bits if any, else the last step's (reference :182-185);
+// packed little-endian into 64-bit words, x1 = bit 0 (utils/VariableAssignment.py:63-69).
+__global__ void __launch_bounds__(128)
+pack_assignments_kernel(UnitGraphDev g, int total_graphs, int words_per_graph,
+                        const unsigned char* LAST, const unsigned char* LATCH, const int* __restrict__ latch_step,
+                        unsigned long long* __restrict__ packed, unsigned char* __restrict__ is_sat,
+                        unsigned char* FINAL) {
+    const int tid = threadIdx.x;
+    const int gid = blockIdx.x;
+    if (gid >= total_graphs) return;
+    const int chain = gid / g.n_graphs, lg = gid % g.n_graphs;
+    const int v0 = __ldg(g.var_seg + lg), v1 = __ldg(g.var_seg + lg + 1);
+    const size_t rowbase = (size_t)chain * g.n;
+    const unsigned char* src = latch_step[gid] >= 0 ? LATCH : LAST;
+    for (int v = v0 + tid; v < v1; v += 128) FINAL[rowbase + v] = src[rowbase + v];
+    for (int w = tid; w < words_per_graph; w += 128) {
+        unsigned long long word = 0ull;
+        const int b0 = v0 + w * 64;
+        for (int i = 0; i < 64 && b0 + i < v1; ++i)
+            word |= (unsigned long long)(src[rowbase + b0 + i] & 1) << i;
+        packed[(size_t)gid * words_per_graph + w] = word;
+    }
+    __syncthreads();
+    const int unsat = __syncthreads_or(graph_clauses_unsat(g, lg, rowbase, FINAL, tid, 128));
+    if (tid == 0) is_sat[gid] = (unsigned char)(!unsat);
+}
+
+}  // namespace dsat
