@@ -1,0 +1,44 @@
+"""CPU tests of the C-ABI library: it builds, loads, exports every symbol include/dsat.h declares,
+and fails loudly (no fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dsat.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dsat_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(dsat_lib):
+    from diffusionsat_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(_lib.library_path())
+    for name in declared:
+        assert hasattr(raw, name), "libdsat.so does not export %s" % name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared       # the ctypes binding covers the whole header
+    assert dsat_lib.dsat_version() >= 1
+
+
+def test_no_cpu_fallback_without_gpu(dsat_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from diffusionsat_b200 import _lib
+    with pytest.raises(_lib.DsatError, match="no CPU fallback"):
+        _lib.Context(0)
+
+
+def test_product_code_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "diffusionsat_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", text, flags=re.M), f

@@ -1,0 +1,150 @@
+"""CPU tests: host-side mirrors and the oracle against golden vectors produced by the reference's own
+pure-Python modules (tests/golden/make_golden.py) and the known answers in the reference's tests."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from diffusionsat_b200 import graph as G
+from diffusionsat_b200 import synth
+from diffusionsat_b200.dimacs import DimacsFile
+from diffusionsat_b200.variable_assignment import VariableAssignment
+from oracle import querysat_oracle as O
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "host_golden.json")))
+
+
+@pytest.mark.parametrize("case", GOLD["dimacs_parse"], ids=lambda c: repr(c["text"][:18]))
+def test_dimacs_parser_matches_reference(case):
+    df = DimacsFile()
+    if "error" in case:
+        with pytest.raises(Exception) as info:
+            df.load_from_string(case["text"])
+        assert type(info.value).__name__ == case["error"]
+        return
+    df.load_from_string(case["text"])
+    assert df.number_of_vars() == case["n_vars"]
+    assert df.clauses() == case["clauses"]
+    assert {str(k): v for k, v in df.b_values.items()} == case["b_values"]
+    assert str(df) == case["str"]
+
+
+@pytest.mark.parametrize("case", GOLD["reduce_clauses"], ids=lambda c: str(len(c["clauses"])))
+def test_reduce_clauses_matches_reference(case):
+    df = DimacsFile(clauses=[list(c) for c in case["clauses"]])
+    df.reduce_clauses()
+    assert sorted(df.clauses(), key=lambda c: (len(c), c)) == case["reduced_sorted"]
+    assert [len(c) for c in df.clauses()] == case["lengths"]          # sorted by length, as the reference
+
+
+def test_reduce_clauses_reference_known_answers():
+    # reference utils/test_DimacsFile.py:3-21
+    for clauses, want in (([[1, 2], [1, 2], [3]], [[3], [1, 2]]), ([[1, 2, 3], [1, 2], [3]], [[3], [1, 2]]),
+                          ([[1, 2, -3], [1, -2], [1]], [[1]])):
+        df = DimacsFile(clauses=clauses)
+        df.reduce_clauses()
+        assert df.clauses() == want
+
+
+@pytest.mark.parametrize("case", GOLD["variable_assignment"], ids=lambda c: str(c["n"]))
+def test_variable_assignment_matches_reference(case):
+    a = VariableAssignment(clauses=case["clauses"]) if case["clauses"] else VariableAssignment(case["n"], [])
+    a.assign_all_from_bit_list(case["bits"])
+    assert str(int(a)) == case["int"]
+    assert a.satisfiable() == case["sat"]
+    assert str(a) == case["str"]
+    assert a.as_int_list() == case["int_list"]
+    b = VariableAssignment(case["n"], [])
+    b.assign_all_from_int(int(case["int"]))
+    assert b.values() == a.values()
+    # the oracle's restatements of the same two functions
+    assert str(O.encode_assignment(case["bits"])) == case["int"]
+    assert O._satisfiable_py([bool(x) for x in case["bits"]], case["clauses"]) == case["sat"]
+
+
+def test_variable_assignment_known_answer():
+    a = VariableAssignment(3, [])
+    a.assign_all_from_int_list([1, 2, 3])
+    assert int(a) == 7                                   # reference utils/VariableAssignment.py:109-112
+
+
+@pytest.mark.parametrize("case", GOLD["adj_indices"], ids=lambda c: str(c["n"]))
+def test_adjacency_indices_match_reference(case):
+    pos, neg = G.compute_adj_indices(case["clauses"])
+    assert pos == case["pos"] and neg == case["neg"]
+    # CSR/CSC built for the kernels hold exactly the same multiset of (literal, clause) pairs
+    unit = G.build_unit_graph(case["n"], case["clauses"])
+    want = sorted([(2 * v, c) for v, c in case["pos"]] + [(2 * v + 1, c) for v, c in case["neg"]])
+    csr = sorted((int(unit.cl_lit[e]), j) for j in range(unit.n_clauses)
+                 for e in range(unit.cl_rowptr[j], unit.cl_rowptr[j + 1]))
+    csc = sorted((l, int(unit.lit_clause[e])) for l in range(2 * unit.n_vars)
+                 for e in range(unit.lit_rowptr[l], unit.lit_rowptr[l + 1]))
+    assert csr == want and csc == want
+    # reference-layout COO regenerated from the unit graph (one chain) equals the reference's lists
+    coo, shape = unit.reference_coo(1)
+    n = case["n"]
+    assert shape == (2 * n, len(case["clauses"]))
+    assert coo.tolist() == [list(p) for p in case["pos"]] + [[v + n, c] for v, c in case["neg"]]
+    # inside a clause the literals are ordered by the reference literal row (sign*n + var)
+    for j in range(unit.n_clauses):
+        codes = unit.cl_lit[unit.cl_rowptr[j]:unit.cl_rowptr[j + 1]]
+        rows = (codes & 1) * n + (codes >> 1)
+        assert np.all(np.diff(rows) >= 0)
+    for l in range(2 * n):
+        assert np.all(np.diff(unit.lit_clause[unit.lit_rowptr[l]:unit.lit_rowptr[l + 1]]) >= 0)
+
+
+def test_oracle_graph_layout_matches_reference_indices():
+    case = GOLD["adj_indices"][0]
+    n, clauses = case["n"], case["clauses"]
+    g = O.OracleGraph.copies(n, clauses, 3)
+    off_pos = [(v + c * n, j + c * len(clauses)) for c in range(3) for v, j in case["pos"]]
+    off_neg = [(v + c * n + 3 * n, j + c * len(clauses)) for c in range(3) for v, j in case["neg"]]
+    got = list(zip(g.lit_row.tolist(), g.clause.tolist()))
+    assert got == off_pos + off_neg                       # all positives, then all negatives (SatSpecifics.py:24-35)
+    unit = G.build_unit_graph(n, clauses)
+    coo, shape = unit.reference_coo(3)
+    assert coo.tolist() == [list(p) for p in got] and shape == (6 * n, 3 * len(clauses))
+
+
+@pytest.mark.parametrize("case", GOLD["chi_square"], ids=lambda c: str(len(c["observed"])))
+def test_chi_square_matches_reference(case, capsys):
+    from diffusionsat_b200.uniformity import chi_square_likelihood
+    p = chi_square_likelihood({int(k): v for k, v in case["observed"].items()},
+                              {int(k): v for k, v in case["expected"].items()})
+    assert p == pytest.approx(case["p"], rel=1e-12, abs=1e-300)
+
+
+def test_solution_count_known_answer():
+    # reference utils/test_AllSolutions.py:6,18 : 14 models
+    assert len(synth.enumerate_solutions(5, [[-1, 2], [1, -2], [-3, 4, 5]])) == 14
+
+
+def test_degree_weights_and_batch_rule():
+    n, clauses = synth.random_3sat(30, seed=0)
+    assert len(clauses) == 133                           # int(4.258 n + 58.26 n^(-2/3)), data/CNFGen.py:42-43
+    unit = G.build_unit_graph(n, clauses)
+    deg = unit.lit_degree()
+    assert deg.sum() == 399
+    np.testing.assert_allclose(unit.degree_weight(), 1 / np.sqrt(np.maximum(deg, 1)), rtol=1e-7)
+    np.testing.assert_allclose(unit.var_degree_weight(), 4 / np.sqrt(np.maximum(deg[0::2] + deg[1::2], 1)), rtol=1e-7)
+    np.testing.assert_allclose(unit.rev_degree_weight(), 1 / np.sqrt(3.0), rtol=1e-7)
+    assert G.chains_per_reference_batch(30, 133) == 103  # floor(20000 / (2n+m)), SURVEY.md section 8
+    assert G.chains_per_reference_batch(100, 430) == 31
+    assert G.chains_per_reference_batch(250, 1065) == 12
+    assert G.chains_per_reference_batch(20000, 1) == 1   # the first formula always fits (data/dimac.py:281)
+
+
+def test_union_graph_and_reference_coo_roundtrip():
+    formulas = [synth.random_ksat_mixed(int(n), int(m), seed=s) for s, (n, m) in enumerate([(5, 9), (3, 4), (8, 20)])]
+    union = G.build_union_graph(formulas)
+    assert union.n_graphs == 3 and union.var_seg.tolist() == [0, 5, 8, 16] and union.clause_seg.tolist() == [0, 9, 13, 33]
+    coo, shape = union.reference_coo(1)
+    vg = np.repeat(np.arange(3), [5, 3, 8])
+    cg = np.repeat(np.arange(3), [9, 4, 20])
+    back = G.unit_graph_from_reference_coo(coo, shape, vg, cg)
+    for name in ("cl_rowptr", "cl_lit", "lit_rowptr", "lit_clause", "var_seg", "clause_seg"):
+        np.testing.assert_array_equal(getattr(back, name), getattr(union, name))
+    og = O.OracleGraph.from_formulas(formulas)
+    assert list(zip(og.lit_row.tolist(), og.clause.tolist())) == [tuple(p) for p in coo.tolist()]

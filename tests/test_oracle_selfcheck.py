@@ -1,0 +1,106 @@
+"""CPU tests that validate the oracle against itself where the reference offers no golden vectors
+(SURVEY.md section 8c): autograd vs closed-form gradient, dense matrix vs segment sums, a batch of
+copies vs independent runs, literal-negation equivariance, posterior normalisation."""
+import numpy as np
+import torch
+
+from diffusionsat_b200 import synth
+from oracle import querysat_oracle as O
+from tests import helpers as H
+
+
+def _setup(n_vars=12, chains=3, rounds=3, seed=0, dtype=torch.float64):
+    _, clauses = synth.random_3sat(n_vars, seed=seed)
+    wts = H.make_weights(seed=3)
+    n_rows = n_vars * chains
+    noise = H.noise_for(n_rows, rounds, seed)
+    noisy = O.randomized_rounding(torch.full((n_rows, 2), 0.5), torch.from_numpy(noise["uniform"])).numpy()
+    return n_vars, clauses, wts, noise, noisy
+
+
+def test_closed_form_gradient_equals_autograd():
+    n_vars, clauses, wts, noise, noisy = _setup()
+    graph = O.OracleGraph.copies(n_vars, clauses, 3)
+    w = O.weights_to_torch(wts, torch.float64)
+    args = (graph, w, 0.7, torch.from_numpy(noisy), torch.from_numpy(noise["labels"].astype(np.int64)),
+            torch.from_numpy(noise["normals"]), 3)
+    a = O.model_loop(*args, dtype=torch.float64)
+    b = O.model_loop(*args, dtype=torch.float64, use_autograd=True)
+    assert torch.allclose(a[0], b[0], rtol=1e-12, atol=1e-13)
+    assert torch.allclose(a[3], b[3], rtol=1e-12, atol=1e-13)
+
+
+def test_segment_sums_equal_dense_adjacency():
+    n_vars, clauses = synth.random_ksat_mixed(9, 30, seed=5)
+    graph = O.OracleGraph.copies(n_vars, clauses, 2)
+    dense = torch.zeros(2 * graph.n_vars, graph.n_clauses, dtype=torch.float64)
+    for r, c in zip(graph.lit_row.tolist(), graph.clause.tolist()):
+        dense[r, c] += 1                                   # duplicates count (Appendix A.2)
+    x_c = torch.randn(graph.n_clauses, 7, dtype=torch.float64)
+    x_l = torch.randn(2 * graph.n_vars, 7, dtype=torch.float64)
+    assert torch.allclose(graph.lit_from_clause(x_c), dense @ x_c)
+    assert torch.allclose(graph.clause_from_lit(x_l), dense.t() @ x_l)
+
+
+def test_batch_of_copies_equals_independent_runs():
+    n_vars, clauses, wts, noise, noisy = _setup(n_vars=10, chains=3, rounds=2)
+    w = O.weights_to_torch(wts, torch.float64)
+    big = O.OracleGraph.copies(n_vars, clauses, 3)
+    labels = torch.from_numpy(noise["labels"].astype(np.int64))
+    full = O.model_loop(big, w, 0.3, torch.from_numpy(noisy), labels, torch.from_numpy(noise["normals"]), 2,
+                        dtype=torch.float64)
+    one = O.OracleGraph.copies(n_vars, clauses, 1)
+    for c in range(3):
+        rows = slice(c * n_vars, (c + 1) * n_vars)
+        part = O.model_loop(one, w, 0.3, torch.from_numpy(noisy[rows]), labels[rows],
+                            torch.from_numpy(noise["normals"][:, rows]), 2, dtype=torch.float64)
+        assert torch.allclose(full[3][rows], part[3], rtol=1e-10, atol=1e-12)     # per-graph ops only
+
+
+def test_clause_loss_is_unsat_probability_and_negation_flips_it():
+    n_vars, clauses = 6, [[1, -2, 3], [-4, 5], [6]]
+    graph = O.OracleGraph.copies(n_vars, clauses, 1)
+    q = torch.randn(n_vars, 4, dtype=torch.float64)
+    loss = O.softplus_loss_adj(q, graph)
+    p_true = torch.sigmoid(q)
+    want = torch.stack([(1 - p_true[0]) * p_true[1] * (1 - p_true[2]), p_true[3] * (1 - p_true[4]), 1 - p_true[5]])
+    assert torch.allclose(loss, want, rtol=1e-10)
+    negated = O.OracleGraph.copies(n_vars, [[-l for l in c] for c in clauses], 1)
+    assert torch.allclose(O.softplus_loss_adj(-q, negated), loss, rtol=1e-12)
+
+
+def test_posterior_and_rounding_semantics():
+    x = torch.tensor([[1.0, 0.0], [0.0, 1.0], [0.5, 0.5]])
+    p = torch.tensor([0.9, 0.2, 0.5])
+    x0 = torch.stack([1 - p, p], dim=1)
+    out = O.reverse_distribution_step_theoretic(x, x0, 1.0, 1 / 32)     # t=1: alpha=0 -> uniform prior times x_hat
+    assert torch.allclose(out.sum(1), torch.ones(3), atol=1e-6)
+    assert torch.allclose(out, torch.full((3, 2), 0.5), atol=1e-6)      # x_hat at t1=1 is [0.5, 0.5]
+    out = O.reverse_distribution_step_theoretic(x, x0, 1 / 32, 1 / 32)  # last step: t2 = 0
+    assert torch.allclose(out.sum(1), torch.ones(3), atol=1e-6)
+    r = O.randomized_rounding(torch.tensor([[0.3, 0.7], [0.3, 0.7]]), torch.tensor([0.69, 0.71]))
+    assert r.tolist() == [[0.0, 1.0], [1.0, 0.0]]                       # floor(x0 + U); column 0 = "False"
+
+
+def test_train_loss_is_zero_at_full_noise_and_argmin_defaults_to_map_zero():
+    logits = torch.randn(5, 8)
+    labels = torch.randint(0, 2, (5, 1)).float().expand(5, 8)
+    loss = O.train_loss(labels, logits, torch.tensor(1.0))
+    assert torch.all(loss == 0)                                          # Appendix A.9
+    assert int(torch.argmin(loss.sum(0))) == 0
+
+
+def test_oracle_samples_histogram_on_tiny_formula():
+    n_vars, clauses = 3, [[1, 2], [-1, 3]]
+    wts = H.make_weights(seed=2)
+    w = O.weights_to_torch(wts)
+    chains, steps, rounds = 8, 3, 2
+
+    def noise_fn(batch):
+        nz = H.noise_for(n_vars * chains, rounds, 50 + batch, steps=steps)
+        return (torch.from_numpy(nz["uniforms"]), torch.from_numpy(nz["labels"].astype(np.int64)),
+                torch.from_numpy(nz["normals"]))
+
+    hist = O.samples(10, n_vars, clauses, w, noise_fn, chains, n_steps=steps, rounds=rounds, max_batches=6)
+    models = set(synth.enumerate_solutions(n_vars, clauses))
+    assert set(hist) <= models and sum(hist.values()) <= 10
