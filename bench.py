@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- diffusion samples/sec on hard random 3-SAT n=100 (BASELINE.json configs[1]).
+
+One "step" = one full reverse-diffusion run (32 denoising steps x 32 message-passing rounds, early exit
+enabled, reference batch composition of 31 chains per early-exit group) of 4096 chains per GPU.
+`value`  : whole-job samples/s with the formula and weights resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the C ABI with HOST buffers: dsat_set_graph (formula upload) + dsat_sample
+           (results copied back) + the histogram merge, wall clock around the call.
+`roofline`: the dominant kernel class (the MLP linear ops) from CUDA-event marks on the launching stream.
+`message_pass`: the segment-sum SpMM kernels alone on BASELINE configs[4]'s graph (n=10000), HBM GB/s.
+`cpu_baseline`: the CPU oracle port of the same path on the host cores (bounded sample).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_VARS = 100
+CHAINS_PER_GPU = 4096
+DIFFUSION_STEPS = 32
+ROUNDS = 32
+SEED_FORMULA = 0
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._drain, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _drain(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def formula():
+    from diffusionsat_b200 import synth
+    return synth.random_3sat(N_VARS, seed=SEED_FORMULA)          # m = int(4.258 n + 58.26 n^(-2/3)) = 428
+
+
+def mlp_flops_per_round(n_rows, m_rows, f=128, q=128):
+    """Algorithmic (unpadded) FLOPs of the eleven linear launches of one round."""
+    from diffusionsat_b200.weights import mlp_layer_dims
+    dims = mlp_layer_dims(f, q)
+    var_side = sum(i * o for name in ("variables_query", "lit_query", "update_gate", "variables_output") for i, o in dims[name])
+    clause_side = sum(i * o for i, o in dims["clause_update"])
+    return 2.0 * (var_side * n_rows + clause_side * m_rows)
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_oracle_rate(batch_chains, dsteps, rounds, threads, repeats=1, warmup=0):
+    """samples/s of the CPU oracle port: one reference batch, `dsteps` of 32 denoising steps, scaled."""
+    import torch
+    from diffusionsat_b200 import weights
+    from oracle import querysat_oracle as O
+    torch.set_num_threads(threads)
+    n, clauses = formula()
+    graph = O.OracleGraph.copies(n, clauses, batch_chains)
+    w = O.weights_to_torch(weights.init_weights(seed=1234))
+    rng = np.random.default_rng(0)
+    nt = graph.n_vars
+    times = []
+    for it in range(warmup + repeats):
+        uniforms = torch.from_numpy(rng.random((dsteps, nt)).astype(np.float32))
+        labels = torch.from_numpy(rng.integers(0, 2, (dsteps, nt)))
+        normals = torch.from_numpy(rng.standard_normal((dsteps, rounds, nt, 4)).astype(np.float32))
+        t0 = time.perf_counter()
+        O.diffusion(dsteps, graph, w, uniforms, labels, normals, rounds)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_full_run = float(np.mean(times)) * (DIFFUSION_STEPS / dsteps)
+    return batch_chains / per_full_run, float(np.mean(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from diffusionsat_b200.graph import chains_per_reference_batch
+    n, clauses = formula()
+    batch = chains_per_reference_batch(n, len(clauses))
+    threads = os.cpu_count() or 1
+    dsteps = 1
+    rate, step_s = cpu_oracle_rate(batch, dsteps, ROUNDS, threads, repeats=args.steps, warmup=args.warmup)
+    sample = ("%d chains (one reference batch, floor(20000/(2n+m))), %d of %d denoising steps x %d rounds per step, "
+              "scaled x%d" % (batch, dsteps, DIFFUSION_STEPS, ROUNDS, DIFFUSION_STEPS // dsteps))
+    line = {
+        "impl": "reference", "metric": "diffusion samples/sec, 3-SAT n=100", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "hard random 3-SAT n=100 m=%d, 32 denoising steps x 32 rounds, random-init QuerySAT F=Q=128"
+                               % len(clauses)},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "TensorFlow 2.4 / TFP 0.12 are not installable offline; this is the torch-CPU oracle port of the reference path",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def message_pass_roofline(ctx, torch, pk):
+    """Segment-sum SpMM alone on BASELINE configs[4]'s graph: n=10000, m=43000, F=128, fp32."""
+    from diffusionsat_b200 import graph, synth
+    n, m, feat, chains = 10000, 43000, 128, 96          # (2n+m)*chains*F*4 = 3.1 GB per launch > L2
+    nv, clauses = synth.random_3sat(n, m, seed=5)
+    unit = graph.build_unit_graph(nv, clauses)
+    ctx.set_graph(unit, chains=1, group_graphs=0)
+    dev = torch.device("cuda", ctx.device)
+    out = {}
+    for name, direction, rin, rout in (("clause_from_literal", 0, 2 * n, m), ("literal_from_clause", 1, m, 2 * n)):
+        x = torch.randn(chains, rin, feat, device=dev)
+        y = torch.empty(chains, rout, feat, device=dev)
+        torch.cuda.synchronize()
+        for _ in range(3):
+            ctx.spmm(direction, x.data_ptr(), y.data_ptr(), feat, 0, chains)
+        ctx.synchronize()
+        reps = 5
+        ctx.timer_begin()
+        for _ in range(reps):
+            ctx.spmm(direction, x.data_ptr(), y.data_ptr(), feat, 0, chains)
+        ms = ctx.timer_end() / reps
+        nbytes = (rin + rout) * chains * feat * 4 + (unit.nnz + rout + 1) * 4
+        out[name] = {"achieved": nbytes / ms / 1e6, "ms": ms, "bytes": nbytes}
+        del x, y
+    best = max(out.values(), key=lambda d: d["achieved"])
+    worst = min(out.values(), key=lambda d: d["achieved"])
+    return {"bound": "hbm", "achieved": worst["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": worst["achieved"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+            "workload": "segment-sum SpMM, shared adjacency, 3-SAT n=10000 m=43000, %d chains, F=128 fp32" % chains,
+            "clause_from_literal_gbs": out["clause_from_literal"]["achieved"],
+            "literal_from_clause_gbs": out["literal_from_clause"]["achieved"], "best_gbs": best["achieved"]}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from diffusionsat_b200 import _lib, build, graph, weights
+    from diffusionsat_b200 import dist as D
+    from diffusionsat_b200.graph import chains_per_reference_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    build.build()
+    pk = peaks()
+    ctx = _lib.Context(local_rank)
+    wts = weights.init_weights(seed=1234)
+    ctx.set_model(wts)
+    precision = args.precision
+    try:
+        ctx.set_precision({"fp32": _lib.F32, "bf16": _lib.BF16}[precision])
+    except _lib.DsatError:
+        precision = "fp32"
+        ctx.set_precision(_lib.F32)
+    n, clauses = formula()
+    unit = graph.build_unit_graph(n, clauses)
+    batch = chains_per_reference_batch(n, len(clauses))
+    chains = args.chains
+    ctx.set_graph(unit, chains=chains, group_graphs=batch)
+    chain_offset = rank * chains
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step(i):
+        ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=1000 + i, chain_offset=chain_offset)
+
+    for i in range(args.warmup):
+        resident_step(i)
+    ctx.synchronize()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ctx.launch_count()
+    ctx.timer_begin()
+    for i in range(args.steps):
+        resident_step(args.warmup + i)
+    ms = ctx.timer_end()
+    launches = ctx.launch_count() - launches0
+    barrier()
+    clock_info = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * chains * args.steps / (ms_max / 1e3)
+
+    # end to end: host buffers in, host results out, through the C ABI, plus the histogram merge
+    barrier()
+    e2e_steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ctx.set_graph(unit, chains=chains, group_graphs=batch)          # formula upload (host -> device)
+        packed, is_sat, latch, _ = ctx.sample(DIFFUSION_STEPS, ROUNDS, seed=2000 + i, chain_offset=chain_offset)
+        keys, counts = D.local_histogram(packed, is_sat)
+        D.merge_histograms(keys, counts, n)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * chains * e2e_steps / float(t.item())
+    h2d = int(sum(a.nbytes for a in (unit.cl_rowptr, unit.cl_lit, unit.lit_rowptr, unit.lit_clause, unit.var_seg,
+                                     unit.clause_seg)))
+    d2h = int(packed.nbytes + is_sat.nbytes + latch.nbytes)
+    sat_rate = float(is_sat.mean())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # per-class device time of the rounds (CUDA events on the launching stream)
+    prof = ctx.profile_rounds(rounds=4, seed=7)
+    total_ms = sum(v[0] for v in prof.values())
+    gemm_names = list(_lib.Context.PROFILE_CLASSES[:11])
+    gemm_ms = sum(prof[k][0] for k in gemm_names)
+    gemm_launches = sum(prof[k][1] for k in gemm_names)
+    flops = mlp_flops_per_round(ctx.n_rows, ctx.n_clause_rows) * 4
+    achieved_tf = flops / (gemm_ms / 1e3) / 1e12
+    peak_tf = pk["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                "kernel": "sgemm128_kernel (fp32 CUDA cores)" if precision == "fp32" else "tc_linear_kernel (tcgen05 bf16)",
+                "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_round": gemm_ms / total_ms,
+                "flops_per_launch": flops / max(gemm_launches, 1),
+                "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items()}}
+    message_pass = None if args.skip_message_pass else message_pass_roofline(ctx, torch, pk)
+
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        threads = os.cpu_count() or 1
+        rate, secs = cpu_oracle_rate(batch, 1, ROUNDS, threads, repeats=2, warmup=1)
+        cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "%d chains (one reference batch), 1 of 32 denoising steps x 32 rounds, scaled x32; %.1f s per step"
+                         % (batch, secs)}
+
+    line = {
+        "metric": "diffusion samples/sec, 3-SAT n=100", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": "hard random 3-SAT n=100 m=%d (ratio 4.3), %d chains per GPU, 32 denoising steps x 32 rounds, "
+                               "random-init QuerySAT F=Q=128, early-exit groups of %d chains" % (len(clauses), chains, batch),
+                   "chains_per_gpu": chains, "parallelism": "chains sharded, dp%d" % world,
+                   "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)" % (
+                       (ctx.n_rows * 3500 + ctx.n_clause_rows * 850) * 4 / 1e9),
+                   "precision": precision},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "message_pass": message_pass,
+        "cpu_baseline": cpu, "sat_rate": sat_rate,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DSAT_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-message-pass", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "dsat_sample_fetch": (C.c_int, [_vp, _u64p, _u8p, _i32p, _u8p]),
     "dsat_words_per_graph": (C.c_int, [_vp]),
     "dsat_spmm": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "dsat_profile_classes": (C.c_int, []),
+    "dsat_profile_rounds": (C.c_int, [_vp, C.c_int, C.c_uint64, _f32p, _i32p]),
     "dsat_debug_begin": (C.c_int, [_vp, C.c_float, _f32p, _i32p]),
     "dsat_debug_round": (C.c_int, [_vp, C.c_int, _f32p]),
     "dsat_debug_dims": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
@@ -240,6 +242,19 @@ class Context:
     def spmm(self, direction: int, x_dev_ptr: int, y_dev_ptr: int, feat: int, dtype: int, chains: int):
         self._check(self._lib.dsat_spmm(self._h, int(direction), _vp(x_dev_ptr), _vp(y_dev_ptr), int(feat), int(dtype),
                                         int(chains)))
+
+    PROFILE_CLASSES = ("v1_hidden", "query_out", "lit_2", "lit_3", "clause_1", "clause_2", "update_1", "update_2",
+                       "update_3", "output_1", "output_2", "clause_gather", "literal_gather", "pairnorm_clause",
+                       "pairnorm_var", "head", "noise")
+
+    def profile_rounds(self, rounds=4, seed=0):
+        """{class: (total_ms, launches)} of `rounds` rounds, CUDA events on the launching stream."""
+        k = int(self._lib.dsat_profile_classes())
+        ms = np.zeros(k, dtype=np.float32)
+        cnt = np.zeros(k, dtype=np.int32)
+        self._check(self._lib.dsat_profile_rounds(self._h, int(rounds), C.c_uint64(seed), _ptr(ms, C.c_float),
+                                                  _ptr(cnt, C.c_int32)))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES[:k])}
 
     # ------------------------------------------------------------------------ debug
     def debug_begin(self, noise_scale, noisy_num, labels=None):

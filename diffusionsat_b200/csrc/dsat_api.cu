@@ -60,6 +60,11 @@ struct dsat_ctx {
     std::string err;
     long long launches = 0;
     int precision = DSAT_F32;
+    // per-class CUDA-event marks (dsat_profile_rounds)
+    struct ProfMark { cudaEvent_t ev; int cls; };
+    std::vector<ProfMark> prof;
+    size_t prof_used = 0;
+    bool profiling = false;
 
     // model
     bool has_model = false;
@@ -182,7 +187,24 @@ void release_buffers(dsat_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------- launch helpers
+enum ProfClass { PROF_CLAUSE_GATHER = OP_COUNT, PROF_LITERAL_GATHER, PROF_NORM_CLAUSE, PROF_NORM_VAR, PROF_HEAD,
+                 PROF_NOISE, PROF_END, PROF_CLASSES = PROF_END };
+
+// an event before every launch group: the interval up to the next mark belongs to `cls`
+void prof_mark(dsat_ctx* c, int cls) {
+    if (!c->profiling) return;
+    if (c->prof_used == c->prof.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->prof.push_back({e, cls});
+    }
+    c->prof[c->prof_used].cls = cls;
+    cudaEventRecord(c->prof[c->prof_used].ev, c->stream);
+    c->prof_used++;
+}
+
 int run_linear(dsat_ctx* c, int op, const float* A, int lda, float* Y, int ldy, long long rows, int epi) {
+    prof_mark(c, op);
     LinearOp l;
     l.A = A; l.lda = lda; l.W = c->ops[op].w.p; l.ldw = c->ops[op].N; l.bias = c->ops[op].b.p;
     l.Y = Y; l.ldy = ldy; l.rows = (int)rows; l.K = c->ops[op].K; l.N = c->ops[op].N; l.epi = epi; l.qmaps = c->Q;
@@ -254,6 +276,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     int rc;
     {
         const int threads = 256;
+        prof_mark(c, PROF_NOISE);
         round_noise_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
             Nt, normals_dev, c->VROW.p, ldv, F, ns, (unsigned)round);
         LAUNCHED(c);
@@ -266,6 +289,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if ((rc = run_linear(c, OP_L2, c->H1.p + c->HQ, ldh1, c->H2.p, c->HL, Nt, EPI_LRELU))) return rc;
     if ((rc = run_linear(c, OP_L3, c->H2.p, c->HL, c->LIT.p, 2 * Q, Nt, EPI_LINEAR))) return rc;
     // clause side gather: clause_messages and 4*clauses_loss                    (:241, :248, :255-256)
+    prof_mark(c, PROF_CLAUSE_GATHER);
     rc = dispatch_width(c, Q, [&](auto v) {
         constexpr int V = decltype(v)::value;
         clause_gather_kernel<V><<<gather_grid(Mt, c->sm_count), GATHER_WARPS * 32, 0, c->stream>>>(
@@ -277,6 +301,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if ((rc = run_linear(c, OP_C1, c->CROW.p, ldc, c->CH.p, c->HC, Mt, EPI_LRELU))) return rc;
     if ((rc = run_linear(c, OP_C2, c->CH.p, c->HC, c->COUT.p, Q + F, Mt, EPI_LINEAR))) return rc;
     // literal side gather (reads the OLD clause state's neighbours only through cl4/COUT)   (:245-246, :269-273)
+    prof_mark(c, PROF_LITERAL_GATHER);
     rc = dispatch_width(c, Q, [&](auto v) {
         constexpr int V = decltype(v)::value;
         literal_gather_kernel<V><<<gather_grid(Nt, c->sm_count), GATHER_WARPS * 32, 0, c->stream>>>(
@@ -285,6 +310,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if (rc) return rc;
     LAUNCHED(c);
     // clause PairNorm + residual + carry                                        (:263-266, :348)
+    prof_mark(c, PROF_NORM_CLAUSE);
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
@@ -298,6 +324,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if ((rc = run_linear(c, OP_U2, c->U1.p, c->HU, c->U2.p, c->HU, Nt, EPI_LRELU))) return rc;
     if ((rc = run_linear(c, OP_U3, c->U2.p, c->HU, c->UOUT.p, F, Nt, EPI_LINEAR))) return rc;
     // variables PairNorm + residual + carry                                     (:279-280, :347)
+    prof_mark(c, PROF_NORM_VAR);
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
@@ -310,6 +337,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if ((rc = run_linear(c, OP_O1, c->SPRE.p, F, c->O1.p, c->HO, Nt, EPI_LRELU))) return rc;
     if ((rc = run_linear(c, OP_O2, c->O1.p, c->HO, c->LOGITS.p, DSAT_LOGIT_PAD, Nt, EPI_LINEAR))) return rc;
     // logit map selection, SAT check, early exit                                 (:289-338)
+    prof_mark(c, PROF_HEAD);
     head_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->group_graphs, c->LOGITS.p,
                                                          DSAT_LOGIT_PAD, c->labels.p, ls.t, ls.ts, ls.norm_plus,
                                                          c->done.p, c->OUT.p, c->BITS.p, c->graph_sat.p,
@@ -319,6 +347,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         c->n_groups, c->group_graphs, c->total_graphs, round, c->graph_sat.p, c->graph_loss.p, c->done.p,
         c->steps_taken.p, c->loss_sum.p, c->rounds_run.p);
     LAUNCHED(c);
+    prof_mark(c, PROF_END);
     return DSAT_OK;
 }
 
@@ -418,6 +447,7 @@ void dsat_destroy(dsat_ctx* c) {
     }
     c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
     c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release();
+    for (auto& pm : c->prof) cudaEventDestroy(pm.ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -726,6 +756,41 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
     });
     if (rc) return rc;
     LAUNCHED(c);
+    return DSAT_OK;
+}
+
+// --------------------------------------------------------------------------------------- profile
+int dsat_profile_classes(void) { return PROF_CLASSES; }
+
+int dsat_profile_rounds(dsat_ctx* c, int rounds, uint64_t seed, float* class_ms, int32_t* class_launches) {
+    if (!c || !class_ms) return DSAT_ERR_ARG;
+    CK_ARG(c, rounds > 0, "dsat_profile_rounds: rounds must be positive");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    {   // x = 0.5 so that step_begin can round it
+        const long long rows4 = (2 * c->Nt + 3) / 4;
+        fill_cols_kernel<<<(unsigned)((rows4 + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<float*>(c->X.p), 4, rows4, 1, 0.5f);
+        LAUNCHED(c);
+    }
+    NoiseSource ns{seed, 0ull, 0u};
+    if ((rc = begin_call(c, 0.5f, nullptr, nullptr, nullptr, true, ns))) return rc;
+    const LossScalars ls = loss_scalars(0.5f);
+    c->prof_used = 0;
+    c->profiling = true;
+    for (int r = 0; r < rounds && rc == 0; ++r) rc = run_round(c, r, nullptr, ns, ls);
+    c->profiling = false;
+    if (rc) return rc;
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < PROF_CLASSES; ++k) { class_ms[k] = 0.f; if (class_launches) class_launches[k] = 0; }
+    for (size_t i = 0; i + 1 < c->prof_used; ++i) {
+        const int cls = c->prof[i].cls;
+        if (cls < 0 || cls >= PROF_CLASSES) continue;
+        float ms = 0.f;
+        CK_CUDA(c, cudaEventElapsedTime(&ms, c->prof[i].ev, c->prof[i + 1].ev));
+        class_ms[cls] += ms;
+        if (class_launches) class_launches[cls] += 1;
+    }
     return DSAT_OK;
 }
 

@@ -127,6 +127,14 @@ int dsat_words_per_graph(const dsat_ctx* ctx);
  * (tf.sparse.sparse_dense_matmul call sites model/query_sat.py:255,269).  feat in {64,128,256}. */
 int dsat_spmm(dsat_ctx* ctx, int direction, const void* x_dev, void* y_dev, int feat, int dtype, int chains);
 
+/* Per-kernel-class device time of `rounds` message-passing rounds, measured with CUDA events on the
+ * context's stream (bench.py roofline).  Classes 0..10 are the eleven linear ops in launch order
+ * (v1->hidden, query out, lit 2, lit 3, clause 1, clause 2, update 1, 2, 3, output 1, 2), then
+ * clause gather, literal gather, clause PairNorm, variable PairNorm, head, noise.
+ * class_ms / class_launches have dsat_profile_classes() entries. */
+int dsat_profile_classes(void);
+int dsat_profile_rounds(dsat_ctx* ctx, int rounds, uint64_t seed, float* class_ms, int32_t* class_launches);
+
 /* Parity hooks: run the pieces of one model call separately and read/write activation buffers. */
 int dsat_debug_begin(dsat_ctx* ctx, float noise_scale, const float* noisy_num, const int32_t* labels);
 int dsat_debug_round(dsat_ctx* ctx, int round, const float* normals /* [N,4] host */);

@@ -1,0 +1,78 @@
+"""world_size-2 gloo test of the sharding rule and the histogram merge (the path's only collective)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffusionsat_b200 import dist as D
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_samples(chain_ids, n_bits):
+    """Deterministic stand-in for sampler output keyed by GLOBAL chain id."""
+    words = -(-n_bits // 64)
+    packed = np.zeros((len(chain_ids), words), dtype=np.uint64)
+    is_sat = np.zeros(len(chain_ids), dtype=np.uint8)
+    for i, c in enumerate(chain_ids):
+        rng = np.random.default_rng(1000 + int(c) % 7)          # few distinct solutions -> collisions across ranks
+        packed[i] = rng.integers(0, 2**63, size=words, dtype=np.uint64)
+        packed[i, -1] &= np.uint64((1 << (n_bits - 64 * (words - 1))) - 1) if n_bits % 64 else np.uint64(2**64 - 1)
+        is_sat[i] = int(c) % 3 != 0
+    return packed, is_sat
+
+
+def _worker(rank, world, port, total, n_bits, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    off, cnt = D.shard_chains(total, world, rank, multiple_of=4)
+    packed, is_sat = _fake_samples(range(off, off + cnt), n_bits)
+    keys, counts = D.local_histogram(packed, is_sat)
+    merged = D.merge_histograms(keys, counts, n_bits)
+    if rank == 0:
+        torch.save(merged, out_path)
+    else:
+        assert merged is None
+    dist.destroy_process_group()
+
+
+def test_shard_chains_covers_everything():
+    for total, world, mult in ((4096, 8, 31), (10, 4, 3), (5, 8, 1), (65536, 8, 12)):
+        blocks = [D.shard_chains(total, world, r, mult) for r in range(world)]
+        assert sum(c for _, c in blocks) == total
+        pos = 0
+        for off, cnt in blocks:
+            assert off == pos or cnt == 0
+            pos += cnt
+            if cnt and off + cnt < total:
+                assert cnt % mult == 0
+
+
+def test_histogram_merge_world2_equals_single_process(tmp_path):
+    total, n_bits = 37, 100
+    out = str(tmp_path / "merged.pt")
+    mp.spawn(_worker, args=(2, _free_port(), total, n_bits, out), nprocs=2, join=True)
+    merged = torch.load(out, weights_only=False)
+    packed, is_sat = _fake_samples(range(total), n_bits)
+    keys, counts = D.local_histogram(packed, is_sat)
+    single = D.merge_histograms(keys, counts, n_bits)
+    assert merged == single
+    assert sum(merged.values()) == int(is_sat.sum())
+    assert all(0 <= k < (1 << n_bits) for k in merged)
+
+
+def test_local_histogram_limit_and_empty():
+    packed, is_sat = _fake_samples(range(12), 70)
+    keys, counts = D.local_histogram(packed, is_sat, limit=3)
+    assert counts.sum() == 3
+    keys, counts = D.local_histogram(packed, np.zeros(12, dtype=np.uint8))
+    assert keys.shape == (0, 2) and counts.shape == (0,)
+    assert D.merge_histograms(keys, counts, 70) == {}
