@@ -51,6 +51,7 @@ _SIGNATURES = {
     "dsat_spmm": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int]),
     "dsat_profile_classes": (C.c_int, []),
     "dsat_profile_rounds": (C.c_int, [_vp, C.c_int, C.c_uint64, _f32p, _i32p]),
+    "dsat_tc_linear_test": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p]),
     "dsat_debug_begin": (C.c_int, [_vp, C.c_float, _f32p, _i32p]),
     "dsat_debug_round": (C.c_int, [_vp, C.c_int, _f32p]),
     "dsat_debug_dims": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
@@ -255,6 +256,19 @@ class Context:
         self._check(self._lib.dsat_profile_rounds(self._h, int(rounds), C.c_uint64(seed), _ptr(ms, C.c_float),
                                                   _ptr(cnt, C.c_int32)))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES[:k])}
+
+    def tc_linear_test(self, a, w, bias, epi=0, out_bf16=False):
+        """Run the tcgen05 linear kernel alone on host arrays (a [rows,K], w [K,N], bias [N])."""
+        a = _as(a, np.float32)
+        w = _as(w, np.float32)
+        bias = _as(bias, np.float32)
+        rows, k = a.shape
+        n = w.shape[1]
+        out = np.empty((rows, 3 * n if epi == 2 else n), dtype=np.float32)
+        self._check(self._lib.dsat_tc_linear_test(self._h, rows, k, n, _ptr(a, C.c_float), _ptr(w, C.c_float),
+                                                  _ptr(bias, C.c_float), int(epi), int(bool(out_bf16)),
+                                                  _ptr(out, C.c_float)))
+        return out
 
     # ------------------------------------------------------------------------ debug
     def debug_begin(self, noise_scale, noisy_num, labels=None):

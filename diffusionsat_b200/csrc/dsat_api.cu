@@ -90,6 +90,15 @@ struct dsat_ctx {
     // injected noise staging
     DevBuf<float> inj_normals, inj_uniforms, inj_noisy;
     DevBuf<int> inj_labels;
+#ifdef DSAT_WITH_TCGEN05
+    // bf16 activations of the tensor-core path (A operands are fetched by TMA from these)
+    DevBuf<__nv_bfloat16> VROWb, CROWb, H1b, H2b, QSb, LITb, CHb, COUTb, U1b, U2b, SPREb, O1b;
+    DevBuf<float> CNEW;                 // [M, F] fp32 new clause value (PairNorm input)
+    CUtensorMap map_a[OP_COUNT];        // A operand of each linear op
+    CUtensorMap map_b[OP_COUNT];        // transposed bf16 weights
+    int a_box_rows[OP_COUNT] = {0}, b_box_rows[OP_COUNT] = {0};
+    bool has_tc_buffers = false;
+#endif
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
     int ldc() const { return F + 2 * Q; }
@@ -174,6 +183,85 @@ int ensure_buffers(dsat_ctx* c) {
     return DSAT_OK;
 }
 
+#ifdef DSAT_WITH_TCGEN05
+__global__ void mirror_cols_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                   long long rows, int cols) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long long r = i / cols; const int cc = (int)(i % cols);
+    dst[(size_t)r * ld_dst + cc] = __float2bfloat16_rn(src[(size_t)r * ld_src + cc]);
+}
+
+// bf16 activation buffers + the TMA descriptors of every A operand (they depend on the row counts)
+int ensure_tc_buffers(dsat_ctx* c) {
+    if (c->has_tc_buffers) return DSAT_OK;
+    int rc = ensure_buffers(c);
+    if (rc) return rc;
+    const size_t Nt = (size_t)c->Nt, Mt = (size_t)c->Mt;
+    const int F = c->F, Q = c->Q;
+    CK_CUDA(c, c->VROWb.alloc(Nt * c->ldv()));
+    CK_CUDA(c, c->CROWb.alloc(Mt * c->ldc()));
+    CK_CUDA(c, c->H1b.alloc(Nt * c->ldh1()));
+    CK_CUDA(c, c->H2b.alloc(Nt * c->HL));
+    CK_CUDA(c, c->QSb.alloc(Nt * 3 * Q));
+    CK_CUDA(c, c->LITb.alloc(Nt * 2 * Q));
+    CK_CUDA(c, c->CHb.alloc(Mt * c->HC));
+    CK_CUDA(c, c->COUTb.alloc(Mt * Q));
+    CK_CUDA(c, c->CNEW.alloc(Mt * F));
+    CK_CUDA(c, c->U1b.alloc(Nt * c->HU));
+    CK_CUDA(c, c->U2b.alloc(Nt * c->HU));
+    CK_CUDA(c, c->SPREb.alloc(Nt * F));
+    CK_CUDA(c, c->O1b.alloc(Nt * c->HO));
+    CK_CUDA(c, cudaMemsetAsync(c->VROWb.p, 0, c->VROWb.count * 2, c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->CROWb.p, 0, c->CROWb.count * 2, c->stream));
+    struct Src { const void* p; long long rows; int k; int ld; };
+    const Src srcs[OP_COUNT] = {
+        {c->VROWb.p, c->Nt, F + DSAT_AUX_PAD, c->ldv()},        // OP_V1
+        {c->H1b.p, c->Nt, c->HQ, c->ldh1()},                    // OP_Q2
+        {c->H1b.p + c->HQ, c->Nt, c->HL, c->ldh1()},            // OP_L2
+        {c->H2b.p, c->Nt, c->HL, c->HL},                        // OP_L3
+        {c->CROWb.p, c->Mt, F + 2 * Q, c->ldc()},               // OP_C1
+        {c->CHb.p, c->Mt, c->HC, c->HC},                        // OP_C2
+        {c->VROWb.p, c->Nt, F + DSAT_AUX_PAD + 3 * Q, c->ldv()},// OP_U1
+        {c->U1b.p, c->Nt, c->HU, c->HU},                        // OP_U2
+        {c->U2b.p, c->Nt, c->HU, c->HU},                        // OP_U3
+        {c->SPREb.p, c->Nt, F, F},                              // OP_O1
+        {c->O1b.p, c->Nt, c->HO, c->HO},                        // OP_O2
+    };
+    for (int op = 0; op < OP_COUNT; ++op) {
+        if (srcs[op].k != c->ops[op].K) { c->err = "internal: A operand width mismatch"; return DSAT_ERR_STATE; }
+        c->a_box_rows[op] = (int)(srcs[op].rows < tc::BLOCK_M ? srcs[op].rows : tc::BLOCK_M);
+        if (!tc::make_bf16_map(&c->map_a[op], srcs[op].p, srcs[op].rows, srcs[op].k, srcs[op].ld, c->a_box_rows[op])) {
+            c->err = "cuTensorMapEncodeTiled failed for an activation operand";
+            return DSAT_ERR_CUDA;
+        }
+    }
+    c->has_tc_buffers = true;
+    return DSAT_OK;
+}
+
+// bf16 transposed ([N, K64], K-major) copies of the packed fp32 weights and their TMA descriptors
+int tc_pack_weights(dsat_ctx* c) {
+    for (int op = 0; op < OP_COUNT; ++op) {
+        const int K = c->ops[op].K, N = c->ops[op].N;
+        const int K64 = (K + 63) / 64 * 64;
+        std::vector<float> w((size_t)K * N);
+        CK_CUDA(c, cudaMemcpy(w.data(), c->ops[op].w.p, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<__nv_bfloat16> wt((size_t)N * K64, __float2bfloat16(0.f));
+        for (int k = 0; k < K; ++k)
+            for (int n = 0; n < N; ++n) wt[(size_t)n * K64 + k] = __float2bfloat16(w[(size_t)k * N + n]);
+        CK_CUDA(c, c->ops[op].w_bf16.alloc(wt.size()));
+        CK_CUDA(c, cudaMemcpy(c->ops[op].w_bf16.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        c->b_box_rows[op] = N < tc::BLOCK_N ? N : tc::BLOCK_N;
+        if (!tc::make_bf16_map(&c->map_b[op], c->ops[op].w_bf16.p, N, K64, K64, c->b_box_rows[op])) {
+            c->err = "cuTensorMapEncodeTiled failed for a weight operand (no CUDA driver?)";
+            return DSAT_ERR_CUDA;
+        }
+    }
+    return DSAT_OK;
+}
+#endif
+
 void release_buffers(dsat_ctx* c) {
     c->VROW.release(); c->CROW.release(); c->H1.release(); c->H2.release(); c->QS.release(); c->LIT.release();
     c->CH.release(); c->COUT.release(); c->U1.release(); c->U2.release(); c->UOUT.release(); c->SPRE.release();
@@ -183,6 +271,12 @@ void release_buffers(dsat_ctx* c) {
     c->graph_sat.release(); c->graph_map.release(); c->graph_loss.release(); c->latch_step.release();
     c->sat_now.release(); c->is_sat.release(); c->sat_any.release(); c->packed.release();
     c->inj_normals.release(); c->inj_uniforms.release(); c->inj_noisy.release(); c->inj_labels.release();
+#ifdef DSAT_WITH_TCGEN05
+    c->VROWb.release(); c->CROWb.release(); c->H1b.release(); c->H2b.release(); c->QSb.release(); c->LITb.release();
+    c->CHb.release(); c->COUTb.release(); c->CNEW.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
+    c->O1b.release();
+    c->has_tc_buffers = false;
+#endif
     c->has_buffers = false;
 }
 
@@ -243,13 +337,31 @@ LossScalars loss_scalars(float noise_scale) {
     return s;
 }
 
+#ifdef DSAT_WITH_TCGEN05
+static inline bool use_tc(const dsat_ctx* c) { return c->precision == DSAT_BF16; }
+static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p : nullptr; }
+static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : nullptr; }
+#else
+static inline bool use_tc(const dsat_ctx*) { return false; }
+static inline __nv_bfloat16* vrow_b(dsat_ctx*) { return nullptr; }
+static inline __nv_bfloat16* crow_b(dsat_ctx*) { return nullptr; }
+#endif
+
+// buffers of the active precision
+int ensure_active_buffers(dsat_ctx* c) {
+#ifdef DSAT_WITH_TCGEN05
+    if (use_tc(c)) return ensure_tc_buffers(c);
+#endif
+    return ensure_buffers(c);
+}
+
 int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const float* uniforms_dev,
                const int* labels_dev, bool use_x, NoiseSource ns) {
     const long long Nt = c->Nt;
     const int threads = 256;
     step_begin_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
         Nt, noise_scale, use_x ? c->X.p : nullptr, noisy_dev, uniforms_dev, labels_dev, c->labels.p,
-        c->VROW.p, c->ldv(), c->F, ns);
+        c->VROW.p, c->ldv(), c->F, vrow_b(c), ns);
     LAUNCHED(c);
     {   // variables_state = ones, clauses_state = ones (reference model/query_sat.py:141,148)
         long long tot = Nt * (c->F / 4);
@@ -260,6 +372,16 @@ int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const flo
         fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
             c->CROW.p, c->ldc(), c->Mt, c->F / 4, 1.0f);
         LAUNCHED(c);
+        if (use_tc(c)) {
+            tot = Nt * (c->F / 8);
+            fill_cols_bf16_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+                vrow_b(c), c->ldv(), Nt, c->F / 8, 1.0f);
+            LAUNCHED(c);
+            tot = c->Mt * (c->F / 8);
+            fill_cols_bf16_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+                crow_b(c), c->ldc(), c->Mt, c->F / 8, 1.0f);
+            LAUNCHED(c);
+        }
     }
     CK_CUDA(c, cudaMemsetAsync(c->done.p, 0, c->done.count * sizeof(int), c->stream));
     CK_CUDA(c, cudaMemsetAsync(c->steps_taken.p, 0xff, c->steps_taken.count * sizeof(int), c->stream));
@@ -268,44 +390,94 @@ int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const flo
     return DSAT_OK;
 }
 
+#ifdef DSAT_WITH_TCGEN05
+// one tensor-core linear op; out0/out1 describe where the output columns go
+int run_linear_tc(dsat_ctx* c, int op, long long rows, int epi, void* p0, int ld0, bool bf0,
+                  void* p1 = nullptr, int ld1 = 0, bool bf1 = false, int split = 0) {
+    prof_mark(c, op);
+    tc::TcLinear l;
+    l.map_a = c->map_a[op]; l.map_b = c->map_b[op]; l.bias = c->ops[op].b.p;
+    l.out.ptr0 = p0; l.out.ld0 = ld0; l.out.bf16_0 = bf0 ? 1 : 0;
+    l.out.ptr1 = p1; l.out.ld1 = ld1; l.out.bf16_1 = bf1 ? 1 : 0; l.out.split = split;
+    l.rows = (int)rows; l.K = c->ops[op].K; l.N = c->ops[op].N; l.epi = epi; l.qmaps = c->Q;
+    l.a_box_rows = c->a_box_rows[op]; l.b_box_rows = c->b_box_rows[op];
+    CK_CUDA(c, tc::launch_tc_linear(l, c->stream));
+    c->launches++;
+    return DSAT_OK;
+}
+#endif
+
 // One message-passing round (reference model/query_sat.py:225-348).
 int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, LossScalars ls) {
     const long long Nt = c->Nt, Mt = c->Mt;
     const int F = c->F, Q = c->Q, ldv = c->ldv(), ldc = c->ldc(), ldh1 = c->ldh1();
     const UnitGraphDev g = graph_view(c);
+    const bool tcp = use_tc(c);
     int rc;
     {
         const int threads = 256;
         prof_mark(c, PROF_NOISE);
         round_noise_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
-            Nt, normals_dev, c->VROW.p, ldv, F, ns, (unsigned)round);
+            Nt, normals_dev, c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round);
         LAUNCHED(c);
     }
-    // v1 -> [hidden of variables_query | first hidden of lit_query]            (:240, :252)
-    if ((rc = run_linear(c, OP_V1, c->VROW.p, ldv, c->H1.p, ldh1, Nt, EPI_LRELU))) return rc;
-    // query (+ softplus pair)                                                   (:240)
-    if ((rc = run_linear(c, OP_Q2, c->H1.p, ldh1, c->QS.p, 3 * Q, Nt, EPI_QUERY))) return rc;
-    // lit_query layers 2, 3                                                     (:252)
-    if ((rc = run_linear(c, OP_L2, c->H1.p + c->HQ, ldh1, c->H2.p, c->HL, Nt, EPI_LRELU))) return rc;
-    if ((rc = run_linear(c, OP_L3, c->H2.p, c->HL, c->LIT.p, 2 * Q, Nt, EPI_LINEAR))) return rc;
+    // v1 -> [hidden of variables_query | first hidden of lit_query]   (:240, :252)
+    // query (+ softplus pair) (:240);  lit_query layers 2, 3 (:252)
+    if (!tcp) {
+        if ((rc = run_linear(c, OP_V1, c->VROW.p, ldv, c->H1.p, ldh1, Nt, EPI_LRELU))) return rc;
+        if ((rc = run_linear(c, OP_Q2, c->H1.p, ldh1, c->QS.p, 3 * Q, Nt, EPI_QUERY))) return rc;
+        if ((rc = run_linear(c, OP_L2, c->H1.p + c->HQ, ldh1, c->H2.p, c->HL, Nt, EPI_LRELU))) return rc;
+        if ((rc = run_linear(c, OP_L3, c->H2.p, c->HL, c->LIT.p, 2 * Q, Nt, EPI_LINEAR))) return rc;
+    }
+#ifdef DSAT_WITH_TCGEN05
+    else {
+        if ((rc = run_linear_tc(c, OP_V1, Nt, tc::TC_LRELU, c->H1b.p, ldh1, true))) return rc;
+        if ((rc = run_linear_tc(c, OP_Q2, Nt, tc::TC_QUERY, c->QSb.p, 3 * Q, true))) return rc;
+        if ((rc = run_linear_tc(c, OP_L2, Nt, tc::TC_LRELU, c->H2b.p, c->HL, true))) return rc;
+        if ((rc = run_linear_tc(c, OP_L3, Nt, tc::TC_LINEAR, c->LITb.p, 2 * Q, true))) return rc;
+    }
+#endif
     // clause side gather: clause_messages and 4*clauses_loss                    (:241, :248, :255-256)
     prof_mark(c, PROF_CLAUSE_GATHER);
     rc = dispatch_width(c, Q, [&](auto v) {
         constexpr int V = decltype(v)::value;
-        clause_gather_kernel<V><<<gather_grid(Mt, c->sm_count), GATHER_WARPS * 32, 0, c->stream>>>(
-            g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
+        const int grid = gather_grid(Mt, c->sm_count);
+        if (!tcp)
+            clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
+                g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
+#ifdef DSAT_WITH_TCGEN05
+        else
+            clause_gather_kernel<V, __nv_bfloat16><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
+                g, c->chains, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, ldc, F);
+#endif
     });
     if (rc) return rc;
     LAUNCHED(c);
     // clause_update MLP                                                          (:258-261)
-    if ((rc = run_linear(c, OP_C1, c->CROW.p, ldc, c->CH.p, c->HC, Mt, EPI_LRELU))) return rc;
-    if ((rc = run_linear(c, OP_C2, c->CH.p, c->HC, c->COUT.p, Q + F, Mt, EPI_LINEAR))) return rc;
-    // literal side gather (reads the OLD clause state's neighbours only through cl4/COUT)   (:245-246, :269-273)
+    if (!tcp) {
+        if ((rc = run_linear(c, OP_C1, c->CROW.p, ldc, c->CH.p, c->HC, Mt, EPI_LRELU))) return rc;
+        if ((rc = run_linear(c, OP_C2, c->CH.p, c->HC, c->COUT.p, Q + F, Mt, EPI_LINEAR))) return rc;
+    }
+#ifdef DSAT_WITH_TCGEN05
+    else {
+        if ((rc = run_linear_tc(c, OP_C1, Mt, tc::TC_LRELU, c->CHb.p, c->HC, true))) return rc;
+        // message to literals -> bf16, new clause value -> fp32 (PairNorm input)
+        if ((rc = run_linear_tc(c, OP_C2, Mt, tc::TC_LINEAR, c->COUTb.p, Q, true, c->CNEW.p, F, false, Q))) return rc;
+    }
+#endif
+    // literal side gather                                                        (:245-246, :269-273)
     prof_mark(c, PROF_LITERAL_GATHER);
     rc = dispatch_width(c, Q, [&](auto v) {
         constexpr int V = decltype(v)::value;
-        literal_gather_kernel<V><<<gather_grid(Nt, c->sm_count), GATHER_WARPS * 32, 0, c->stream>>>(
-            g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
+        const int grid = gather_grid(Nt, c->sm_count);
+        if (!tcp)
+            literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
+                g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
+#ifdef DSAT_WITH_TCGEN05
+        else
+            literal_gather_kernel<V, __nv_bfloat16><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
+                g, c->chains, c->CROWb.p, ldc, F + Q, c->COUTb.p, Q, c->QSb.p, 3 * Q, c->VROWb.p, ldv, F + DSAT_AUX_PAD);
+#endif
     });
     if (rc) return rc;
     LAUNCHED(c);
@@ -314,28 +486,61 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
-        pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->clause_seg.p, c->n_graphs, c->m, c->total_graphs,
-                                                         c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
+        if (!tcp)
+            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->clause_seg.p, c->n_graphs, c->m, c->total_graphs,
+                                                             c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0,
+                                                             nullptr, 0, nullptr, 0);
+#ifdef DSAT_WITH_TCGEN05
+        else
+            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->clause_seg.p, c->n_graphs, c->m, c->total_graphs,
+                                                             c->CNEW.p, F, 0, c->CROW.p, ldc, nullptr, 0,
+                                                             c->CROWb.p, ldc, nullptr, 0);
+#endif
     });
     if (rc) return rc;
     LAUNCHED(c);
     // update_gate MLP                                                            (:277-278)
-    if ((rc = run_linear(c, OP_U1, c->VROW.p, ldv, c->U1.p, c->HU, Nt, EPI_LRELU))) return rc;
-    if ((rc = run_linear(c, OP_U2, c->U1.p, c->HU, c->U2.p, c->HU, Nt, EPI_LRELU))) return rc;
-    if ((rc = run_linear(c, OP_U3, c->U2.p, c->HU, c->UOUT.p, F, Nt, EPI_LINEAR))) return rc;
+    if (!tcp) {
+        if ((rc = run_linear(c, OP_U1, c->VROW.p, ldv, c->U1.p, c->HU, Nt, EPI_LRELU))) return rc;
+        if ((rc = run_linear(c, OP_U2, c->U1.p, c->HU, c->U2.p, c->HU, Nt, EPI_LRELU))) return rc;
+        if ((rc = run_linear(c, OP_U3, c->U2.p, c->HU, c->UOUT.p, F, Nt, EPI_LINEAR))) return rc;
+    }
+#ifdef DSAT_WITH_TCGEN05
+    else {
+        if ((rc = run_linear_tc(c, OP_U1, Nt, tc::TC_LRELU, c->U1b.p, c->HU, true))) return rc;
+        if ((rc = run_linear_tc(c, OP_U2, Nt, tc::TC_LRELU, c->U2b.p, c->HU, true))) return rc;
+        if ((rc = run_linear_tc(c, OP_U3, Nt, tc::TC_LINEAR, c->UOUT.p, F, false))) return rc;
+    }
+#endif
     // variables PairNorm + residual + carry                                     (:279-280, :347)
     prof_mark(c, PROF_NORM_VAR);
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
-        pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->var_seg.p, c->n_graphs, c->n, c->total_graphs,
-                                                         c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
+        if (!tcp)
+            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->var_seg.p, c->n_graphs, c->n, c->total_graphs,
+                                                             c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F,
+                                                             nullptr, 0, nullptr, 0);
+#ifdef DSAT_WITH_TCGEN05
+        else
+            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->var_seg.p, c->n_graphs, c->n, c->total_graphs,
+                                                             c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F,
+                                                             c->VROWb.p, ldv, c->SPREb.p, F);
+#endif
     });
     if (rc) return rc;
     LAUNCHED(c);
     // variables_output MLP                                                       (:283)
-    if ((rc = run_linear(c, OP_O1, c->SPRE.p, F, c->O1.p, c->HO, Nt, EPI_LRELU))) return rc;
-    if ((rc = run_linear(c, OP_O2, c->O1.p, c->HO, c->LOGITS.p, DSAT_LOGIT_PAD, Nt, EPI_LINEAR))) return rc;
+    if (!tcp) {
+        if ((rc = run_linear(c, OP_O1, c->SPRE.p, F, c->O1.p, c->HO, Nt, EPI_LRELU))) return rc;
+        if ((rc = run_linear(c, OP_O2, c->O1.p, c->HO, c->LOGITS.p, DSAT_LOGIT_PAD, Nt, EPI_LINEAR))) return rc;
+    }
+#ifdef DSAT_WITH_TCGEN05
+    else {
+        if ((rc = run_linear_tc(c, OP_O1, Nt, tc::TC_LRELU, c->O1b.p, c->HO, true))) return rc;
+        if ((rc = run_linear_tc(c, OP_O2, Nt, tc::TC_LINEAR, c->LOGITS.p, DSAT_LOGIT_PAD, false))) return rc;
+    }
+#endif
     // logit map selection, SAT check, early exit                                 (:289-338)
     prof_mark(c, PROF_HEAD);
     head_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->group_graphs, c->LOGITS.p,
@@ -601,7 +806,7 @@ int dsat_model_call(dsat_ctx* c, float noise_scale, const float* noisy_num, cons
     if (!c) return DSAT_ERR_ARG;
     CK_ARG(c, noisy_num && prediction_out && rounds >= 0, "dsat_model_call: null buffer or negative rounds");
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     const size_t Nt = (size_t)c->Nt;
     CK_CUDA(c, c->inj_noisy.alloc(Nt * 2));
@@ -635,7 +840,7 @@ int dsat_model_call(dsat_ctx* c, float noise_scale, const float* noisy_num, cons
 // --------------------------------------------------------------------------------------- sampler
 static int sample_enqueue_impl(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t chain_offset,
                                const float* uniforms_dev, const int* labels_dev, const float* normals_dev) {
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     const long long Nt = c->Nt;
     const UnitGraphDev g = graph_view(c);
@@ -711,7 +916,7 @@ int dsat_sample(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t 
     if (!c) return DSAT_ERR_ARG;
     CK_ARG(c, n_steps > 0 && n_rounds >= 0, "dsat_sample: bad step or round count");
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     const size_t Nt = (size_t)c->Nt;
     if (uniforms) {
@@ -766,7 +971,7 @@ int dsat_profile_rounds(dsat_ctx* c, int rounds, uint64_t seed, float* class_ms,
     if (!c || !class_ms) return DSAT_ERR_ARG;
     CK_ARG(c, rounds > 0, "dsat_profile_rounds: rounds must be positive");
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     {   // x = 0.5 so that step_begin can round it
         const long long rows4 = (2 * c->Nt + 3) / 4;
@@ -830,7 +1035,7 @@ int dsat_debug_dims(const dsat_ctx* cc, int buffer, long long* rows, int* ld) {
 int dsat_debug_read(dsat_ctx* c, int buffer, float* host_out, long long count) {
     if (!c || !host_out) return DSAT_ERR_ARG;
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     float* p; long long rows; int ld;
     if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
@@ -843,20 +1048,87 @@ int dsat_debug_read(dsat_ctx* c, int buffer, float* host_out, long long count) {
 int dsat_debug_write(dsat_ctx* c, int buffer, const float* host_in, long long count) {
     if (!c || !host_in) return DSAT_ERR_ARG;
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     float* p; long long rows; int ld;
     if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
     CK_ARG(c, count == rows * ld, "dsat_debug_write: count must be rows*ld");
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
     CK_CUDA(c, cudaMemcpy(p, host_in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+#ifdef DSAT_WITH_TCGEN05
+    if (use_tc(c) && (buffer == DSAT_BUF_VROW || buffer == DSAT_BUF_CROW)) {   // keep the bf16 state mirror in step
+        __nv_bfloat16* dst = buffer == DSAT_BUF_VROW ? c->VROWb.p : c->CROWb.p;
+        const long long tot = rows * c->F;
+        mirror_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(p, ld, dst, ld, rows, c->F);
+        LAUNCHED(c);
+        CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+#endif
     return DSAT_OK;
+}
+
+// Stand-alone run of the tensor-core linear kernel on host data (parity test of the tcgen05 path):
+// out = epi(bf16(A) @ bf16(W) + bias), out is [rows, N] fp32 (for the query epilogue [rows, 3N]).
+int dsat_tc_linear_test(dsat_ctx* c, int rows, int K, int N, const float* a_host, const float* w_host,
+                        const float* bias_host, int epi, int out_bf16, float* out_host) {
+    if (!c || !a_host || !w_host || !bias_host || !out_host) return DSAT_ERR_ARG;
+#ifndef DSAT_WITH_TCGEN05
+    c->err = "built without the tcgen05 path";
+    return DSAT_ERR_UNSUPPORTED;
+#else
+    CK_ARG(c, rows > 0 && K > 0 && N > 0 && K % 16 == 0 && N % 16 == 0, "dsat_tc_linear_test: K and N must be multiples of 16");
+    CK_ARG(c, epi != tc::TC_QUERY || N % 32 == 0, "query epilogue needs N % 32 == 0");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    const int K64 = (K + 63) / 64 * 64;
+    const int out_cols = epi == tc::TC_QUERY ? 3 * N : N;
+    std::vector<__nv_bfloat16> a((size_t)rows * K), wt((size_t)N * K64, __float2bfloat16(0.f));
+    for (size_t i = 0; i < a.size(); ++i) a[i] = __float2bfloat16(a_host[i]);
+    for (int k = 0; k < K; ++k)
+        for (int n = 0; n < N; ++n) wt[(size_t)n * K64 + k] = __float2bfloat16(w_host[(size_t)k * N + n]);
+    DevBuf<__nv_bfloat16> da, dw, dout_b;
+    DevBuf<float> db, dout_f;
+    CK_CUDA(c, da.alloc(a.size()));
+    CK_CUDA(c, dw.alloc(wt.size()));
+    CK_CUDA(c, db.alloc(N));
+    CK_CUDA(c, dout_b.alloc((size_t)rows * out_cols));
+    CK_CUDA(c, dout_f.alloc((size_t)rows * out_cols));
+    CK_CUDA(c, cudaMemcpy(da.p, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    CK_CUDA(c, cudaMemcpy(dw.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+    CK_CUDA(c, cudaMemcpy(db.p, bias_host, N * sizeof(float), cudaMemcpyHostToDevice));
+    tc::TcLinear l;
+    l.a_box_rows = rows < tc::BLOCK_M ? rows : tc::BLOCK_M;
+    l.b_box_rows = N < tc::BLOCK_N ? N : tc::BLOCK_N;
+    if (!tc::make_bf16_map(&l.map_a, da.p, rows, K, K, l.a_box_rows) || !tc::make_bf16_map(&l.map_b, dw.p, N, K64, K64, l.b_box_rows)) {
+        c->err = "cuTensorMapEncodeTiled failed";
+        da.release(); dw.release(); db.release(); dout_b.release(); dout_f.release();
+        return DSAT_ERR_CUDA;
+    }
+    l.bias = db.p;
+    l.out.ptr0 = out_bf16 ? (void*)dout_b.p : (void*)dout_f.p; l.out.ld0 = out_cols; l.out.bf16_0 = out_bf16 ? 1 : 0;
+    l.out.ptr1 = nullptr; l.out.ld1 = 0; l.out.bf16_1 = 0; l.out.split = 0;
+    l.rows = rows; l.K = K; l.N = N; l.epi = epi; l.qmaps = N;
+    cudaError_t e = tc::launch_tc_linear(l, c->stream);
+    c->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) {
+        if (out_bf16) {
+            std::vector<__nv_bfloat16> ob((size_t)rows * out_cols);
+            e = cudaMemcpy(ob.data(), dout_b.p, ob.size() * 2, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < ob.size(); ++i) out_host[i] = __bfloat162float(ob[i]);
+        } else {
+            e = cudaMemcpy(out_host, dout_f.p, (size_t)rows * out_cols * sizeof(float), cudaMemcpyDeviceToHost);
+        }
+    }
+    da.release(); dw.release(); db.release(); dout_b.release(); dout_f.release();
+    CK_CUDA(c, e);
+    return DSAT_OK;
+#endif
 }
 
 int dsat_debug_begin(dsat_ctx* c, float noise_scale, const float* noisy_num, const int32_t* labels) {
     if (!c || !noisy_num) return DSAT_ERR_ARG;
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     const size_t Nt = (size_t)c->Nt;
     CK_CUDA(c, c->inj_noisy.alloc(Nt * 2));
@@ -875,7 +1147,7 @@ int dsat_debug_begin(dsat_ctx* c, float noise_scale, const float* noisy_num, con
 int dsat_debug_round(dsat_ctx* c, int round, const float* normals) {
     if (!c) return DSAT_ERR_ARG;
     CK_CUDA(c, cudaSetDevice(c->device));
-    int rc = ensure_buffers(c);
+    int rc = ensure_active_buffers(c);
     if (rc) return rc;
     const size_t Nt = (size_t)c->Nt;
     if (normals) {

@@ -118,6 +118,18 @@ __device__ __forceinline__ void lane_store_bf16(__nv_bfloat16* __restrict__ row,
     }
 }
 
+// storage-type generic front ends (T = float or __nv_bfloat16)
+template <int V, typename T>
+__device__ __forceinline__ LaneVec<V> lane_load_t(const T* __restrict__ row, int lane) {
+    if constexpr (sizeof(T) == 2) return lane_load_bf16<V>(reinterpret_cast<const __nv_bfloat16*>(row), lane);
+    else return lane_load<V>(reinterpret_cast<const float*>(row), lane);
+}
+template <int V, typename T>
+__device__ __forceinline__ void lane_store_t(T* __restrict__ row, int lane, const LaneVec<V>& r) {
+    if constexpr (sizeof(T) == 2) lane_store_bf16<V>(reinterpret_cast<__nv_bfloat16*>(row), lane, r);
+    else lane_store<V>(reinterpret_cast<float*>(row), lane, r);
+}
+
 // -------------------------------------------------------------------------------- Philox
 // Philox4x32-10 counter-based generator; the same function is restated in numpy in
 // diffusionsat_b200/philox.py so that host-side tests can inject identical noise.

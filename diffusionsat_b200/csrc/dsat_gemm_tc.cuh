@@ -142,7 +142,8 @@ __device__ __forceinline__ void store_chunk(const TcOut& out, size_t row, int co
 // grid.x = row tiles * n_tiles (N tiles fastest so that CTAs sharing an A tile run back to back)
 __global__ void __launch_bounds__(THREADS, 2)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const float* __restrict__ bias, TcOut out, int rows, int K, int N, int n_tiles, int epi, int qmaps) {
+                 const float* __restrict__ bias, TcOut out, int rows, int K, int N, int n_tiles, int epi, int qmaps,
+                 int a_box_rows, int b_box_rows) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;                                   // STAGES x 16 KB
@@ -181,7 +182,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int s = kb % STAGES;
                 const uint32_t phase = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], phase ^ 1);
-                mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                mbar_expect_tx(&full_bar[s], (uint32_t)(a_box_rows + b_box_rows) * (BLOCK_K * 2));
                 tma_load_2d(smem_a + s * A_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, row0);
                 tma_load_2d(smem_b + s * B_BYTES, &map_b, &full_bar[s], kb * BLOCK_K, n0);
             }
@@ -290,6 +291,7 @@ struct TcLinear {
     const float* bias;
     TcOut out;
     int rows, K, N, epi, qmaps;
+    int a_box_rows, b_box_rows;     // TMA box heights the descriptors were encoded with
 };
 
 inline cudaError_t launch_tc_linear(const TcLinear& op, cudaStream_t stream) {
@@ -303,7 +305,7 @@ inline cudaError_t launch_tc_linear(const TcLinear& op, cudaStream_t stream) {
     const int n_tiles = ceil_div(op.N, BLOCK_N);
     const unsigned grid = (unsigned)(n_tiles * ceil_div(op.rows, BLOCK_M));
     tc_linear_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(op.map_a, op.map_b, op.bias, op.out, op.rows, op.K, op.N,
-                                                             n_tiles, op.epi, op.qmaps);
+                                                             n_tiles, op.epi, op.qmaps, op.a_box_rows, op.b_box_rows);
     return cudaGetLastError();
 }
 

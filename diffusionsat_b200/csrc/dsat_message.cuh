@@ -35,12 +35,12 @@ constexpr int GATHER_WARPS = 8;
 //   cl4[j]  = 4 * exp(-sum_{lit in j} SP[var(lit)][sign(lit)*Q : +Q])        SP = softplus(+-query)
 // LIT rows have leading dimension ld_lit (2Q used), SP rows ld_sp with the pair starting at column sp_off.
 // Output goes to OUT[(c*m + j)*ld_out + out_off : +2Q] = [cmsg | cl4].
-template <int V>
+template <int V, typename T>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
 clause_gather_kernel(UnitGraphDev g, int chains,
-                     const float* __restrict__ LIT, int ld_lit,
-                     const float* __restrict__ SP, int ld_sp, int sp_off,
-                     float* __restrict__ OUT, int ld_out, int out_off) {
+                     const T* __restrict__ LIT, int ld_lit,
+                     const T* __restrict__ SP, int ld_sp, int sp_off,
+                     T* __restrict__ OUT, int ld_out, int out_off) {
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
     const long long total = (long long)chains * g.m;
@@ -57,12 +57,12 @@ clause_gather_kernel(UnitGraphDev g, int chains,
         for (; e + 3 <= e1; e += 3) {   // 3-SAT fast path: three edges in flight
             int c0 = __ldg(g.cl_lit + e), c1 = __ldg(g.cl_lit + e + 1), c2 = __ldg(g.cl_lit + e + 2);
             const size_t r0 = vbase + (c0 >> 1), r1 = vbase + (c1 >> 1), r2 = vbase + (c2 >> 1);
-            LaneVec<V> l0 = lane_load<V>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
-            LaneVec<V> l1 = lane_load<V>(LIT + r1 * ld_lit + (c1 & 1) * Q, lane);
-            LaneVec<V> l2 = lane_load<V>(LIT + r2 * ld_lit + (c2 & 1) * Q, lane);
-            LaneVec<V> s0 = lane_load<V>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
-            LaneVec<V> s1 = lane_load<V>(SP + r1 * ld_sp + sp_off + (c1 & 1) * Q, lane);
-            LaneVec<V> s2 = lane_load<V>(SP + r2 * ld_sp + sp_off + (c2 & 1) * Q, lane);
+            LaneVec<V> l0 = lane_load_t<V, T>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
+            LaneVec<V> l1 = lane_load_t<V, T>(LIT + r1 * ld_lit + (c1 & 1) * Q, lane);
+            LaneVec<V> l2 = lane_load_t<V, T>(LIT + r2 * ld_lit + (c2 & 1) * Q, lane);
+            LaneVec<V> s0 = lane_load_t<V, T>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
+            LaneVec<V> s1 = lane_load_t<V, T>(SP + r1 * ld_sp + sp_off + (c1 & 1) * Q, lane);
+            LaneVec<V> s2 = lane_load_t<V, T>(SP + r2 * ld_sp + sp_off + (c2 & 1) * Q, lane);
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 acc_l.v[i] = ((acc_l.v[i] + l0.v[i]) + l1.v[i]) + l2.v[i];
@@ -72,8 +72,8 @@ clause_gather_kernel(UnitGraphDev g, int chains,
         for (; e < e1; ++e) {
             int c0 = __ldg(g.cl_lit + e);
             const size_t r0 = vbase + (c0 >> 1);
-            LaneVec<V> l0 = lane_load<V>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
-            LaneVec<V> s0 = lane_load<V>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
+            LaneVec<V> l0 = lane_load_t<V, T>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
+            LaneVec<V> s0 = lane_load_t<V, T>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
 #pragma unroll
             for (int i = 0; i < V; ++i) { acc_l.v[i] += l0.v[i]; acc_s.v[i] += s0.v[i]; }
         }
@@ -83,9 +83,9 @@ clause_gather_kernel(UnitGraphDev g, int chains,
             acc_l.v[i] *= rw;
             acc_s.v[i] = 4.0f * expf(-acc_s.v[i]);
         }
-        float* dst = OUT + ((size_t)c * g.m + j) * ld_out + out_off;
-        lane_store<V>(dst, lane, acc_l);
-        lane_store<V>(dst + Q, lane, acc_s);
+        T* dst = OUT + ((size_t)c * g.m + j) * ld_out + out_off;
+        lane_store_t<V, T>(dst, lane, acc_l);
+        lane_store_t<V, T>(dst + Q, lane, acc_s);
     }
 }
 
@@ -96,13 +96,13 @@ clause_gather_kernel(UnitGraphDev g, int chains,
 //   vloss+-[v] = deg_w[+-v] * sum_{j containing +-v} MSG[j] == variables_loss_pos/neg of reference :269-273
 // CL4 rows: ld_cl, column cl_off; MSG rows: ld_msg, column 0; QRY rows: ld_q (query in columns [0,Q)).
 // Output OUT[(c*n+v)*ld_out + out_off : +3Q] = [g | vloss+ | vloss-].
-template <int V>
+template <int V, typename T>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
 literal_gather_kernel(UnitGraphDev g, int chains,
-                      const float* __restrict__ CL4, int ld_cl, int cl_off,
-                      const float* __restrict__ MSG, int ld_msg,
-                      const float* __restrict__ QRY, int ld_q,
-                      float* __restrict__ OUT, int ld_out, int out_off) {
+                      const T* __restrict__ CL4, int ld_cl, int cl_off,
+                      const T* __restrict__ MSG, int ld_msg,
+                      const T* __restrict__ QRY, int ld_q,
+                      T* __restrict__ OUT, int ld_out, int out_off) {
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
     const long long total = (long long)chains * g.n;
@@ -121,10 +121,10 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             int e = e0;
             for (; e + 2 <= e1; e += 2) {
                 const size_t j0 = cbase + __ldg(g.lit_clause + e), j1 = cbase + __ldg(g.lit_clause + e + 1);
-                LaneVec<V> a0 = lane_load<V>(CL4 + j0 * ld_cl + cl_off, lane);
-                LaneVec<V> a1 = lane_load<V>(CL4 + j1 * ld_cl + cl_off, lane);
-                LaneVec<V> b0 = lane_load<V>(MSG + j0 * ld_msg, lane);
-                LaneVec<V> b1 = lane_load<V>(MSG + j1 * ld_msg, lane);
+                LaneVec<V> a0 = lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
+                LaneVec<V> a1 = lane_load_t<V, T>(CL4 + j1 * ld_cl + cl_off, lane);
+                LaneVec<V> b0 = lane_load_t<V, T>(MSG + j0 * ld_msg, lane);
+                LaneVec<V> b1 = lane_load_t<V, T>(MSG + j1 * ld_msg, lane);
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
                     s4[sgn].v[i] = (s4[sgn].v[i] + a0.v[i]) + a1.v[i];
@@ -133,14 +133,14 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             }
             for (; e < e1; ++e) {
                 const size_t j0 = cbase + __ldg(g.lit_clause + e);
-                LaneVec<V> a0 = lane_load<V>(CL4 + j0 * ld_cl + cl_off, lane);
-                LaneVec<V> b0 = lane_load<V>(MSG + j0 * ld_msg, lane);
+                LaneVec<V> a0 = lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
+                LaneVec<V> b0 = lane_load_t<V, T>(MSG + j0 * ld_msg, lane);
 #pragma unroll
                 for (int i = 0; i < V; ++i) { s4[sgn].v[i] += a0.v[i]; ms[sgn].v[i] += b0.v[i]; }
             }
         }
         const size_t row = (size_t)c * g.n + v;
-        LaneVec<V> q = lane_load<V>(QRY + row * ld_q, lane);
+        LaneVec<V> q = lane_load_t<V, T>(QRY + row * ld_q, lane);
         const float vw = __ldg(g.vdeg_w + v);
         const float dwp = __ldg(g.deg_w + 2 * v), dwn = __ldg(g.deg_w + 2 * v + 1);
         LaneVec<V> grad;
@@ -151,10 +151,10 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             ms[0].v[i] *= dwp;
             ms[1].v[i] *= dwn;
         }
-        float* dst = OUT + row * ld_out + out_off;
-        lane_store<V>(dst, lane, grad);
-        lane_store<V>(dst + Q, lane, ms[0]);
-        lane_store<V>(dst + 2 * Q, lane, ms[1]);
+        T* dst = OUT + row * ld_out + out_off;
+        lane_store_t<V, T>(dst, lane, grad);
+        lane_store_t<V, T>(dst + Q, lane, ms[0]);
+        lane_store_t<V, T>(dst + 2 * Q, lane, ms[1]);
     }
 }
 

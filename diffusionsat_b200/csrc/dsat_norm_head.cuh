@@ -26,7 +26,9 @@ __global__ void __launch_bounds__(256)
 pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
                 const float* __restrict__ SRC, int ld_src, int src_off,
                 float* __restrict__ STATE, int ld_state,
-                float* __restrict__ PRE, int ld_pre) {
+                float* __restrict__ PRE, int ld_pre,
+                __nv_bfloat16* __restrict__ STATE_B, int ld_state_b,     // bf16 mirrors for the tensor-core path
+                __nv_bfloat16* __restrict__ PRE_B, int ld_pre_b) {
     constexpr int F = 32 * V;
     __shared__ float red[8][F];
     __shared__ float mean_s[F];
@@ -73,6 +75,8 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
                 carried.v[i] = __fadd_rn(__fmul_rn(nw.v[i], 0.2f), __fmul_rn(nw.v[i], 0.8f));
             }
             if (PRE) lane_store<V>(PRE + r * ld_pre, lane, nw);
+            if (PRE_B) lane_store_bf16<V>(PRE_B + r * ld_pre_b, lane, nw);
+            if (STATE_B) lane_store_bf16<V>(STATE_B + r * ld_state_b, lane, carried);
             lane_store<V>(srow, lane, carried);
         }
         __syncthreads();
@@ -214,7 +218,8 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
                                   const float* __restrict__ uniforms_in,   // [n_rows] or null -> Philox
                                   const int* __restrict__ labels_in,       // [n_rows] or null -> Philox
                                   int* __restrict__ labels,
-                                  float* __restrict__ VROW, int ld, int aux_off, NoiseSource ns) {
+                                  float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
+                                  NoiseSource ns) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     float a, b;
@@ -231,13 +236,22 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
     reinterpret_cast<float4*>(aux)[1] = make_float4(a, b, noise_scale, 0.f);
     reinterpret_cast<float4*>(aux)[2] = make_float4(0.f, 0.f, 0.f, 0.f);
     reinterpret_cast<float4*>(aux)[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (VROW_B) {   // columns 4..15 of the bf16 aux block (0..3 are the per-round normals)
+        __nv_bfloat16* auxb = VROW_B + (size_t)r * ld + aux_off;
+        __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+        reinterpret_cast<__nv_bfloat162*>(auxb)[2] = __floats2bfloat162_rn(a, b);
+        reinterpret_cast<__nv_bfloat162*>(auxb)[3] = __floats2bfloat162_rn(noise_scale, 0.f);
+#pragma unroll
+        for (int i = 4; i < 8; ++i) reinterpret_cast<__nv_bfloat162*>(auxb)[i] = z;
+    }
     labels[r] = labels_in ? labels_in[r]
                           : (int)(noise_draw(ns.seed, ns.element_offset + r, ns.step, 0, STREAM_LABEL).x & 1u);
 }
 
 // Fresh N(0,1)[.,4] every round (reference model/query_sat.py:239).
 __global__ void round_noise_kernel(long long n_rows, const float* __restrict__ normals_in /*[n_rows,4] or null*/,
-                                   float* __restrict__ VROW, int ld, int aux_off, NoiseSource ns, unsigned int round) {
+                                   float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
+                                   NoiseSource ns, unsigned int round) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     float4 nrm;
@@ -249,6 +263,21 @@ __global__ void round_noise_kernel(long long n_rows, const float* __restrict__ n
         box_muller(p.z, p.w, nrm.z, nrm.w);
     }
     reinterpret_cast<float4*>(VROW + (size_t)r * ld + aux_off)[0] = nrm;
+    if (VROW_B) {
+        __nv_bfloat162* auxb = reinterpret_cast<__nv_bfloat162*>(VROW_B + (size_t)r * ld + aux_off);
+        auxb[0] = __floats2bfloat162_rn(nrm.x, nrm.y);
+        auxb[1] = __floats2bfloat162_rn(nrm.z, nrm.w);
+    }
+}
+
+__global__ void fill_cols_bf16_kernel(__nv_bfloat16* __restrict__ dst, int ld, long long rows, int cols8, float value) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols8) return;
+    const long long r = i / cols8; const int c = (int)(i % cols8);
+    __nv_bfloat162 v = __floats2bfloat162_rn(value, value);
+    uint4 pack;
+    pack.x = pack.y = pack.z = pack.w = *reinterpret_cast<uint32_t*>(&v);
+    reinterpret_cast<uint4*>(dst + (size_t)r * ld)[c] = pack;
 }
 
 __global__ void fill_cols_kernel(float* __restrict__ dst, int ld, long long rows, int cols4, float value) {

@@ -135,6 +135,12 @@ int dsat_spmm(dsat_ctx* ctx, int direction, const void* x_dev, void* y_dev, int 
 int dsat_profile_classes(void);
 int dsat_profile_rounds(dsat_ctx* ctx, int rounds, uint64_t seed, float* class_ms, int32_t* class_launches);
 
+/* Stand-alone run of the tcgen05 linear kernel on host data (parity of the tensor-core MLP path,
+ * model/mlp.py:42-50): out = epi(bf16(a) @ bf16(w) + bias); a [rows,K], w [K,N], out [rows,N] fp32
+ * ([rows,3N] for epi 2 = query epilogue with the softplus pair); epi 0 linear, 1 leaky-relu 0.2. */
+int dsat_tc_linear_test(dsat_ctx* ctx, int rows, int K, int N, const float* a_host, const float* w_host,
+                        const float* bias_host, int epi, int out_bf16, float* out_host);
+
 /* Parity hooks: run the pieces of one model call separately and read/write activation buffers. */
 int dsat_debug_begin(dsat_ctx* ctx, float noise_scale, const float* noisy_num, const int32_t* labels);
 int dsat_debug_round(dsat_ctx* ctx, int round, const float* normals /* [N,4] host */);
