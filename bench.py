@@ -293,6 +293,7 @@ def run_ours(args):
                 "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_round": gemm_ms / total_ms,
                 "flops_per_launch": flops / max(gemm_launches, 1),
                 "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items()}}
+    working_set_gb = (ctx.n_rows * 3500 + ctx.n_clause_rows * 850) * (4 if precision == "fp32" else 2) / 1e9
     message_pass = None if args.skip_message_pass else message_pass_roofline(ctx, torch, pk)
 
     cpu = None
@@ -310,8 +311,8 @@ def run_ours(args):
         "config": {"workload": "hard random 3-SAT n=100 m=%d (ratio 4.3), %d chains per GPU, 32 denoising steps x 32 rounds, "
                                "random-init QuerySAT F=Q=128, early-exit groups of %d chains" % (len(clauses), chains, batch),
                    "chains_per_gpu": chains, "parallelism": "chains sharded, dp%d" % world,
-                   "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)" % (
-                       (ctx.n_rows * 3500 + ctx.n_clause_rows * 850) * 4 / 1e9),
+                   "l2": "activations touched per round ~%.1f GB >> 126 MB L2: inputs larger than L2, no flush needed"
+                         % working_set_gb,
                    "precision": precision},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "message_pass": message_pass,

@@ -229,7 +229,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (epi == TC_QUERY) {      // softplus(+q), softplus(-q) next to the query
                         float sp[32], sn[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) { sp[j] = softplus_f(v[j]); sn[j] = softplus_f(-v[j]); }
+                        for (int j = 0; j < 32; ++j) {
+                            // softplus(x) = max(x,0) + log(1 + exp(-|x|)); softplus(-x) = softplus(x) - x.
+                            // fast intrinsics: the result is rounded to bf16 anyway
+                            const float tail = __logf(1.0f + __expf(-fabsf(v[j])));
+                            sp[j] = fmaxf(v[j], 0.f) + tail;
+                            sn[j] = fmaxf(-v[j], 0.f) + tail;
+                        }
                         store_chunk(out, row, col + qmaps, sp);
                         store_chunk(out, row, col + 2 * qmaps, sn);
                     }
