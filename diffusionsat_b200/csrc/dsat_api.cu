@@ -15,6 +15,7 @@
 #include "dsat_norm_head.cuh"
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
+#include "dsat_mlp_fused.cuh"
 #endif
 
 using namespace dsat;
@@ -98,6 +99,10 @@ struct dsat_ctx {
     CUtensorMap map_b[OP_COUNT];        // transposed bf16 weights
     int a_box_rows[OP_COUNT] = {0}, b_box_rows[OP_COUNT] = {0};
     bool has_tc_buffers = false;
+    // whole-MLP kernels (dsat_mlp_fused.cuh): query, literal, clause, update, output
+    fm::FusedMlp fused[5];
+    bool fused_ready = false;
+    bool use_fused = true;
 #endif
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
@@ -236,6 +241,51 @@ int ensure_tc_buffers(dsat_ctx* c) {
             return DSAT_ERR_CUDA;
         }
     }
+    {   // whole-MLP kernels: one launch per MLP, hidden activations stay in shared memory
+        enum { FQ = 0, FL, FC, FU, FO };
+        const int k64_v1 = (c->ops[OP_V1].K + 63) / 64 * 64;
+        struct L { int op; int n; const __nv_bfloat16* w; const float* b; int epi; };
+        auto build = [&](int which, int a_op, std::initializer_list<L> layers, tc::TcOut out) -> bool {
+            fm::FusedMlp& f = c->fused[which];
+            f.map_a = c->map_a[a_op];
+            f.p.n_layers = (int)layers.size();
+            f.p.rows = (int)(a_op == OP_C1 ? c->Mt : c->Nt);
+            f.p.a_box_rows = c->a_box_rows[a_op];
+            f.p.qmaps = Q;
+            f.p.out = out;
+            int i = 0;
+            for (const L& l : layers) {
+                const int K = c->ops[l.op].K, K64 = (K + 63) / 64 * 64;
+                f.p.layer[i].K = K; f.p.layer[i].N = l.n; f.p.layer[i].epi = l.epi; f.p.layer[i].bias = l.b;
+                f.p.layer[i].box_rows = l.n < 256 ? l.n : 256;
+                if (!tc::make_bf16_map(&f.map_w[i], l.w, l.n, K64, K64, f.p.layer[i].box_rows)) return false;
+                ++i;
+            }
+            return fm::plan_fused(f);
+        };
+        auto W = [&](int op) { return (const __nv_bfloat16*)c->ops[op].w_bf16.p; };
+        auto B = [&](int op) { return (const float*)c->ops[op].b.p; };
+        tc::TcOut o;
+        bool ok = true;
+        o = {c->QSb.p, 3 * Q, 1, nullptr, 0, 0, 0};
+        ok = ok && build(FQ, OP_V1, {{OP_V1, c->HQ, W(OP_V1), B(OP_V1), tc::TC_LRELU},
+                                     {OP_Q2, Q, W(OP_Q2), B(OP_Q2), tc::TC_QUERY}}, o);
+        o = {c->LITb.p, 2 * Q, 1, nullptr, 0, 0, 0};
+        ok = ok && build(FL, OP_V1, {{OP_V1, c->HL, W(OP_V1) + (size_t)c->HQ * k64_v1, B(OP_V1) + c->HQ, tc::TC_LRELU},
+                                     {OP_L2, c->HL, W(OP_L2), B(OP_L2), tc::TC_LRELU},
+                                     {OP_L3, 2 * Q, W(OP_L3), B(OP_L3), tc::TC_LINEAR}}, o);
+        o = {c->COUTb.p, Q, 1, c->CNEW.p, F, 0, Q};
+        ok = ok && build(FC, OP_C1, {{OP_C1, c->HC, W(OP_C1), B(OP_C1), tc::TC_LRELU},
+                                     {OP_C2, Q + F, W(OP_C2), B(OP_C2), tc::TC_LINEAR}}, o);
+        o = {c->UOUT.p, F, 0, nullptr, 0, 0, 0};
+        ok = ok && build(FU, OP_U1, {{OP_U1, c->HU, W(OP_U1), B(OP_U1), tc::TC_LRELU},
+                                     {OP_U2, c->HU, W(OP_U2), B(OP_U2), tc::TC_LRELU},
+                                     {OP_U3, F, W(OP_U3), B(OP_U3), tc::TC_LINEAR}}, o);
+        o = {c->LOGITS.p, DSAT_LOGIT_PAD, 0, nullptr, 0, 0, 0};
+        ok = ok && build(FO, OP_O1, {{OP_O1, c->HO, W(OP_O1), B(OP_O1), tc::TC_LRELU},
+                                     {OP_O2, DSAT_LOGIT_PAD, W(OP_O2), B(OP_O2), tc::TC_LINEAR}}, o);
+        c->fused_ready = ok;
+    }
     c->has_tc_buffers = true;
     return DSAT_OK;
 }
@@ -338,7 +388,7 @@ LossScalars loss_scalars(float noise_scale) {
 }
 
 #ifdef DSAT_WITH_TCGEN05
-static inline bool use_tc(const dsat_ctx* c) { return c->precision == DSAT_BF16; }
+static inline bool use_tc(const dsat_ctx* c) { return c->precision == DSAT_BF16 || c->precision == DSAT_BF16_UNFUSED; }
 static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p : nullptr; }
 static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : nullptr; }
 #else
@@ -407,12 +457,24 @@ int run_linear_tc(dsat_ctx* c, int op, long long rows, int epi, void* p0, int ld
 }
 #endif
 
+#ifdef DSAT_WITH_TCGEN05
+int run_fused(dsat_ctx* c, int which, int prof_class) {
+    prof_mark(c, prof_class);
+    CK_CUDA(c, fm::launch_fused(c->fused[which], c->stream));
+    c->launches++;
+    return DSAT_OK;
+}
+#endif
+
 // One message-passing round (reference model/query_sat.py:225-348).
 int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, LossScalars ls) {
     const long long Nt = c->Nt, Mt = c->Mt;
     const int F = c->F, Q = c->Q, ldv = c->ldv(), ldc = c->ldc(), ldh1 = c->ldh1();
     const UnitGraphDev g = graph_view(c);
     const bool tcp = use_tc(c);
+#ifdef DSAT_WITH_TCGEN05
+    const bool fusedp = tcp && c->precision == DSAT_BF16 && c->fused_ready;
+#endif
     int rc;
     {
         const int threads = 256;
@@ -431,10 +493,15 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     }
 #ifdef DSAT_WITH_TCGEN05
     else {
+        if (fusedp) {
+            if ((rc = run_fused(c, 0, OP_Q2))) return rc;
+            if ((rc = run_fused(c, 1, OP_L3))) return rc;
+        } else {
         if ((rc = run_linear_tc(c, OP_V1, Nt, tc::TC_LRELU, c->H1b.p, ldh1, true))) return rc;
         if ((rc = run_linear_tc(c, OP_Q2, Nt, tc::TC_QUERY, c->QSb.p, 3 * Q, true))) return rc;
         if ((rc = run_linear_tc(c, OP_L2, Nt, tc::TC_LRELU, c->H2b.p, c->HL, true))) return rc;
         if ((rc = run_linear_tc(c, OP_L3, Nt, tc::TC_LINEAR, c->LITb.p, 2 * Q, true))) return rc;
+        }
     }
 #endif
     // clause side gather: clause_messages and 4*clauses_loss                    (:241, :248, :255-256)
@@ -460,9 +527,13 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     }
 #ifdef DSAT_WITH_TCGEN05
     else {
+        if (fusedp) {
+            if ((rc = run_fused(c, 2, OP_C2))) return rc;
+        } else {
         if ((rc = run_linear_tc(c, OP_C1, Mt, tc::TC_LRELU, c->CHb.p, c->HC, true))) return rc;
         // message to literals -> bf16, new clause value -> fp32 (PairNorm input)
         if ((rc = run_linear_tc(c, OP_C2, Mt, tc::TC_LINEAR, c->COUTb.p, Q, true, c->CNEW.p, F, false, Q))) return rc;
+        }
     }
 #endif
     // literal side gather                                                        (:245-246, :269-273)
@@ -507,9 +578,13 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     }
 #ifdef DSAT_WITH_TCGEN05
     else {
+        if (fusedp) {
+            if ((rc = run_fused(c, 3, OP_U3))) return rc;
+        } else {
         if ((rc = run_linear_tc(c, OP_U1, Nt, tc::TC_LRELU, c->U1b.p, c->HU, true))) return rc;
         if ((rc = run_linear_tc(c, OP_U2, Nt, tc::TC_LRELU, c->U2b.p, c->HU, true))) return rc;
         if ((rc = run_linear_tc(c, OP_U3, Nt, tc::TC_LINEAR, c->UOUT.p, F, false))) return rc;
+        }
     }
 #endif
     // variables PairNorm + residual + carry                                     (:279-280, :347)
@@ -537,8 +612,12 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     }
 #ifdef DSAT_WITH_TCGEN05
     else {
+        if (fusedp) {
+            if ((rc = run_fused(c, 4, OP_O2))) return rc;
+        } else {
         if ((rc = run_linear_tc(c, OP_O1, Nt, tc::TC_LRELU, c->O1b.p, c->HO, true))) return rc;
         if ((rc = run_linear_tc(c, OP_O2, Nt, tc::TC_LINEAR, c->LOGITS.p, DSAT_LOGIT_PAD, false))) return rc;
+        }
     }
 #endif
     // logit map selection, SAT check, early exit                                 (:289-338)
@@ -695,7 +774,7 @@ int dsat_set_precision(dsat_ctx* c, int dtype) {
     if (!c) return DSAT_ERR_ARG;
     if (dtype == DSAT_F32) { c->precision = dtype; return DSAT_OK; }
 #ifdef DSAT_WITH_TCGEN05
-    if (dtype == DSAT_BF16) { c->precision = dtype; return DSAT_OK; }
+    if (dtype == DSAT_BF16 || dtype == DSAT_BF16_UNFUSED) { c->precision = dtype; return DSAT_OK; }
 #endif
     c->err = "precision not available in this build";
     return DSAT_ERR_UNSUPPORTED;

@@ -35,7 +35,8 @@ enum dsat_status {
     DSAT_ERR_UNSUPPORTED = -4
 };
 
-enum dsat_dtype { DSAT_F32 = 0, DSAT_BF16 = 1 };
+/* DSAT_BF16: tcgen05 path with one kernel per MLP; DSAT_BF16_UNFUSED: one tcgen05 kernel per Dense layer */
+enum dsat_dtype { DSAT_F32 = 0, DSAT_BF16 = 1, DSAT_BF16_UNFUSED = 2 };
 
 /* debug/parity access to the activation buffers of one round (dsat_debug_read / dsat_debug_write) */
 enum dsat_buffer {

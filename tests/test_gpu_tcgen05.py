@@ -80,3 +80,25 @@ def test_bf16_sampler_runs_and_is_deterministic(ctx):
     vals = unpack_assignments(a[0], n_vars)
     for v, s in zip(vals, a[1]):
         assert (v in models) == bool(s)          # the SAT flag is exact integer work in both precisions
+
+
+def test_fused_mlp_kernels_match_per_layer_kernels(ctx):
+    """One kernel per MLP (hidden activations in shared memory) against one kernel per Dense layer:
+    same bf16 rounding points, same accumulation order -> logits agree to fp32 round-off."""
+    n_vars, chains, rounds = 100, 7, 3
+    _, clauses = synth.random_3sat(n_vars, seed=4)
+    wts = H.make_weights(seed=9)
+    n_rows = n_vars * chains
+    noise = H.noise_for(n_rows, rounds, 3)
+    noisy = O.randomized_rounding(torch.full((n_rows, 2), 0.5), torch.from_numpy(noise["uniform"])).numpy()
+    ctx.set_model(wts)
+    ctx.set_graph(G.build_unit_graph(n_vars, clauses), chains=chains, group_graphs=0)
+    out = {}
+    for name, code in (("fused", _lib.BF16), ("per_layer", 2)):
+        ctx.set_precision(code)
+        ctx.debug_begin(0.5, noisy, noise["labels"])
+        for r in range(rounds):
+            ctx.debug_round(r, noise["normals"][r])
+        out[name] = (ctx.debug_read("LOGITS").copy(), ctx.debug_read("SPRE").copy(), ctx.debug_read("CROW")[:, :128].copy())
+    for a, b in zip(out["fused"], out["per_layer"]):
+        assert H.rel_err(a, b) < 2e-3
