@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -19,6 +20,15 @@
 #endif
 
 using namespace dsat;
+
+// Synchronous copy that is also ordered against the context's NON-BLOCKING stream: a pageable
+// host-to-device cudaMemcpy may return while its DMA is still in flight, and work queued afterwards on a
+// non-blocking stream is not ordered behind it.
+static cudaError_t dsat_memcpy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, kind);
+    if (e == cudaSuccess && kind == cudaMemcpyHostToDevice) e = cudaDeviceSynchronize();
+    return e;
+}
 
 namespace {
 
@@ -93,8 +103,7 @@ struct dsat_ctx {
     DevBuf<int> inj_labels;
 #ifdef DSAT_WITH_TCGEN05
     // bf16 activations of the tensor-core path (A operands are fetched by TMA from these)
-    DevBuf<__nv_bfloat16> VROWb, CROWb, H1b, H2b, QSb, LITb, CHb, COUTb, U1b, U2b, SPREb, O1b;
-    DevBuf<float> CNEW;                 // [M, F] fp32 new clause value (PairNorm input)
+    DevBuf<__nv_bfloat16> VROWb, CROWb, H1b, H2b, QSb, LITb, CHb, COUTb, U1b, U2b, UOUTb, SPREb, O1b;
     CUtensorMap map_a[OP_COUNT];        // A operand of each linear op
     CUtensorMap map_b[OP_COUNT];        // transposed bf16 weights
     int a_box_rows[OP_COUNT] = {0}, b_box_rows[OP_COUNT] = {0};
@@ -103,6 +112,7 @@ struct dsat_ctx {
     fm::FusedMlp fused[5];
     bool fused_ready = false;
     bool use_fused = true;
+    bool use_smem_gather = true;
 #endif
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
@@ -211,8 +221,8 @@ int ensure_tc_buffers(dsat_ctx* c) {
     CK_CUDA(c, c->QSb.alloc(Nt * 3 * Q));
     CK_CUDA(c, c->LITb.alloc(Nt * 2 * Q));
     CK_CUDA(c, c->CHb.alloc(Mt * c->HC));
-    CK_CUDA(c, c->COUTb.alloc(Mt * Q));
-    CK_CUDA(c, c->CNEW.alloc(Mt * F));
+    CK_CUDA(c, c->COUTb.alloc(Mt * (Q + F)));
+    CK_CUDA(c, c->UOUTb.alloc(Nt * F));
     CK_CUDA(c, c->U1b.alloc(Nt * c->HU));
     CK_CUDA(c, c->U2b.alloc(Nt * c->HU));
     CK_CUDA(c, c->SPREb.alloc(Nt * F));
@@ -274,10 +284,10 @@ int ensure_tc_buffers(dsat_ctx* c) {
         ok = ok && build(FL, OP_V1, {{OP_V1, c->HL, W(OP_V1) + (size_t)c->HQ * k64_v1, B(OP_V1) + c->HQ, tc::TC_LRELU},
                                      {OP_L2, c->HL, W(OP_L2), B(OP_L2), tc::TC_LRELU},
                                      {OP_L3, 2 * Q, W(OP_L3), B(OP_L3), tc::TC_LINEAR}}, o);
-        o = {c->COUTb.p, Q, 1, c->CNEW.p, F, 0, Q};
+        o = {c->COUTb.p, Q + F, 1, nullptr, 0, 0, 0};
         ok = ok && build(FC, OP_C1, {{OP_C1, c->HC, W(OP_C1), B(OP_C1), tc::TC_LRELU},
                                      {OP_C2, Q + F, W(OP_C2), B(OP_C2), tc::TC_LINEAR}}, o);
-        o = {c->UOUT.p, F, 0, nullptr, 0, 0, 0};
+        o = {c->UOUTb.p, F, 1, nullptr, 0, 0, 0};
         ok = ok && build(FU, OP_U1, {{OP_U1, c->HU, W(OP_U1), B(OP_U1), tc::TC_LRELU},
                                      {OP_U2, c->HU, W(OP_U2), B(OP_U2), tc::TC_LRELU},
                                      {OP_U3, F, W(OP_U3), B(OP_U3), tc::TC_LINEAR}}, o);
@@ -296,12 +306,12 @@ int tc_pack_weights(dsat_ctx* c) {
         const int K = c->ops[op].K, N = c->ops[op].N;
         const int K64 = (K + 63) / 64 * 64;
         std::vector<float> w((size_t)K * N);
-        CK_CUDA(c, cudaMemcpy(w.data(), c->ops[op].w.p, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        CK_CUDA(c, dsat_memcpy_sync(w.data(), c->ops[op].w.p, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
         std::vector<__nv_bfloat16> wt((size_t)N * K64, __float2bfloat16(0.f));
         for (int k = 0; k < K; ++k)
             for (int n = 0; n < N; ++n) wt[(size_t)n * K64 + k] = __float2bfloat16(w[(size_t)k * N + n]);
         CK_CUDA(c, c->ops[op].w_bf16.alloc(wt.size()));
-        CK_CUDA(c, cudaMemcpy(c->ops[op].w_bf16.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        CK_CUDA(c, dsat_memcpy_sync(c->ops[op].w_bf16.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
         c->b_box_rows[op] = N < tc::BLOCK_N ? N : tc::BLOCK_N;
         if (!tc::make_bf16_map(&c->map_b[op], c->ops[op].w_bf16.p, N, K64, K64, c->b_box_rows[op])) {
             c->err = "cuTensorMapEncodeTiled failed for a weight operand (no CUDA driver?)";
@@ -323,7 +333,7 @@ void release_buffers(dsat_ctx* c) {
     c->inj_normals.release(); c->inj_uniforms.release(); c->inj_noisy.release(); c->inj_labels.release();
 #ifdef DSAT_WITH_TCGEN05
     c->VROWb.release(); c->CROWb.release(); c->H1b.release(); c->H2b.release(); c->QSb.release(); c->LITb.release();
-    c->CHb.release(); c->COUTb.release(); c->CNEW.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
+    c->CHb.release(); c->COUTb.release(); c->UOUTb.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
     c->O1b.release();
     c->has_tc_buffers = false;
 #endif
@@ -460,9 +470,73 @@ int run_linear_tc(dsat_ctx* c, int op, long long rows, int epi, void* p0, int ld
 #ifdef DSAT_WITH_TCGEN05
 int run_fused(dsat_ctx* c, int which, int prof_class) {
     prof_mark(c, prof_class);
-    CK_CUDA(c, fm::launch_fused(c->fused[which], c->stream));
+    CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
     c->launches++;
     return DSAT_OK;
+}
+#endif
+
+#ifdef DSAT_WITH_TCGEN05
+// Shared-memory staged gathers (small formulas): pick the widest feature slice whose two tables fit;
+// returns false when they do not fit (the L2-gather kernels run instead).
+static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out) {
+    const int widths[2] = {128, 64};
+    for (int pass = 0; pass < 2; ++pass)                 // first try to leave room for two CTAs per SM
+        for (int w : widths) {
+            if (w > Q || Q % w) continue;
+            const size_t bytes = 2 * table_rows * (size_t)w * 2;
+            if (bytes <= (pass == 0 ? 112u * 1024u : 220u * 1024u)) { *bytes_out = bytes; return w; }
+        }
+    return 0;
+}
+
+template <typename K>
+static bool set_dyn_smem(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) == cudaSuccess;
+}
+
+bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
+    if (c->n_graphs != 1 || !c->use_smem_gather) return false;
+    size_t bytes = 0;
+    const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes);
+    if (!w) return false;
+    dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
+    using T = __nv_bfloat16;
+    const int Q = c->Q;
+    if (w == 128) {
+        static bool ok = set_dyn_smem(clause_gather_smem_kernel<4, T>);
+        if (!ok) return false;
+        clause_gather_smem_kernel<4, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
+                                                                          c->CROWb.p, c->ldc(), c->F);
+    } else {
+        static bool ok = set_dyn_smem(clause_gather_smem_kernel<2, T>);
+        if (!ok) return false;
+        clause_gather_smem_kernel<2, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
+                                                                          c->CROWb.p, c->ldc(), c->F);
+    }
+    return true;
+}
+
+bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
+    if (c->n_graphs != 1 || !c->use_smem_gather) return false;
+    size_t bytes = 0;
+    const int w = pick_slice_width((size_t)c->m, c->Q, &bytes);
+    if (!w) return false;
+    dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
+    using T = __nv_bfloat16;
+    const int Q = c->Q, F = c->F;
+    if (w == 128) {
+        static bool ok = set_dyn_smem(literal_gather_smem_kernel<4, T>);
+        if (!ok) return false;
+        literal_gather_smem_kernel<4, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
+                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
+    } else {
+        static bool ok = set_dyn_smem(literal_gather_smem_kernel<2, T>);
+        if (!ok) return false;
+        literal_gather_smem_kernel<2, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
+                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
+    }
+    return true;
 }
 #endif
 
@@ -473,7 +547,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     const UnitGraphDev g = graph_view(c);
     const bool tcp = use_tc(c);
 #ifdef DSAT_WITH_TCGEN05
-    const bool fusedp = tcp && c->precision == DSAT_BF16 && c->fused_ready;
+    const bool fusedp = tcp && c->precision == DSAT_BF16 && c->fused_ready && c->use_fused;
 #endif
     int rc;
     {
@@ -513,7 +587,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
 #ifdef DSAT_WITH_TCGEN05
-        else
+        else if (!launch_clause_gather_smem(c, g))
             clause_gather_kernel<V, __nv_bfloat16><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, ldc, F);
 #endif
@@ -532,7 +606,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         } else {
         if ((rc = run_linear_tc(c, OP_C1, Mt, tc::TC_LRELU, c->CHb.p, c->HC, true))) return rc;
         // message to literals -> bf16, new clause value -> fp32 (PairNorm input)
-        if ((rc = run_linear_tc(c, OP_C2, Mt, tc::TC_LINEAR, c->COUTb.p, Q, true, c->CNEW.p, F, false, Q))) return rc;
+        if ((rc = run_linear_tc(c, OP_C2, Mt, tc::TC_LINEAR, c->COUTb.p, Q + F, true))) return rc;
         }
     }
 #endif
@@ -545,9 +619,9 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
 #ifdef DSAT_WITH_TCGEN05
-        else
+        else if (!launch_literal_gather_smem(c, g))
             literal_gather_kernel<V, __nv_bfloat16><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
-                g, c->chains, c->CROWb.p, ldc, F + Q, c->COUTb.p, Q, c->QSb.p, 3 * Q, c->VROWb.p, ldv, F + DSAT_AUX_PAD);
+                g, c->chains, c->CROWb.p, ldc, F + Q, c->COUTb.p, Q + F, c->QSb.p, 3 * Q, c->VROWb.p, ldv, F + DSAT_AUX_PAD);
 #endif
     });
     if (rc) return rc;
@@ -558,14 +632,12 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
         if (!tcp)
-            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->clause_seg.p, c->n_graphs, c->m, c->total_graphs,
-                                                             c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0,
-                                                             nullptr, 0, nullptr, 0);
+            pairnorm_kernel<V, float, float><<<grid, 256, 0, c->stream>>>(
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
 #ifdef DSAT_WITH_TCGEN05
         else
-            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->clause_seg.p, c->n_graphs, c->m, c->total_graphs,
-                                                             c->CNEW.p, F, 0, c->CROW.p, ldc, nullptr, 0,
-                                                             c->CROWb.p, ldc, nullptr, 0);
+            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, c->stream>>>(
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUTb.p, Q + F, Q, c->CROWb.p, ldc, nullptr, 0);
 #endif
     });
     if (rc) return rc;
@@ -583,7 +655,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         } else {
         if ((rc = run_linear_tc(c, OP_U1, Nt, tc::TC_LRELU, c->U1b.p, c->HU, true))) return rc;
         if ((rc = run_linear_tc(c, OP_U2, Nt, tc::TC_LRELU, c->U2b.p, c->HU, true))) return rc;
-        if ((rc = run_linear_tc(c, OP_U3, Nt, tc::TC_LINEAR, c->UOUT.p, F, false))) return rc;
+        if ((rc = run_linear_tc(c, OP_U3, Nt, tc::TC_LINEAR, c->UOUTb.p, F, true))) return rc;
         }
     }
 #endif
@@ -593,14 +665,12 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
         if (!tcp)
-            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->var_seg.p, c->n_graphs, c->n, c->total_graphs,
-                                                             c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F,
-                                                             nullptr, 0, nullptr, 0);
+            pairnorm_kernel<V, float, float><<<grid, 256, 0, c->stream>>>(
+                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
 #ifdef DSAT_WITH_TCGEN05
         else
-            pairnorm_kernel<V><<<grid, 256, 0, c->stream>>>(c->var_seg.p, c->n_graphs, c->n, c->total_graphs,
-                                                             c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F,
-                                                             c->VROWb.p, ldv, c->SPREb.p, F);
+            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, c->stream>>>(
+                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUTb.p, F, 0, c->VROWb.p, ldv, c->SPREb.p, F);
 #endif
     });
     if (rc) return rc;
@@ -646,8 +716,8 @@ int pack_weights(dsat_ctx* c, const float* const* kernels, const float* const* b
         c->ops[op].K = K; c->ops[op].N = N;
         CK_CUDA(c, c->ops[op].w.alloc((size_t)K * N));
         CK_CUDA(c, c->ops[op].b.alloc((size_t)N));
-        CK_CUDA(c, cudaMemcpy(c->ops[op].w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
-        CK_CUDA(c, cudaMemcpy(c->ops[op].b.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK_CUDA(c, dsat_memcpy_sync(c->ops[op].w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK_CUDA(c, dsat_memcpy_sync(c->ops[op].b.p, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
         return DSAT_OK;
     };
     // copy a [rows, cols] block of a reference kernel (leading dim src_ld) into a packed matrix
@@ -714,6 +784,14 @@ int dsat_create(int device, dsat_ctx** out) {
     c->stream = c->own_stream;
     cudaEventCreate(&c->ev0);
     cudaEventCreate(&c->ev1);
+#ifdef DSAT_WITH_TCGEN05
+    {   // A/B switches for measurements: DSAT_FUSED_MLP=0, DSAT_SMEM_GATHER=0
+        const char* e = getenv("DSAT_FUSED_MLP");
+        if (e && e[0] == '0') c->use_fused = false;
+        e = getenv("DSAT_SMEM_GATHER");
+        if (e && e[0] == '0') c->use_smem_gather = false;
+    }
+#endif
     *out = c;
     return DSAT_OK;
 }
@@ -856,12 +934,12 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     auto up_i = [&](DevBuf<int>& b, const int32_t* h, size_t cnt) -> cudaError_t {
         cudaError_t e = b.alloc(cnt > 0 ? cnt : 1);
         if (e != cudaSuccess || cnt == 0) return e;
-        return cudaMemcpy(b.p, h, cnt * sizeof(int), cudaMemcpyHostToDevice);
+        return dsat_memcpy_sync(b.p, h, cnt * sizeof(int), cudaMemcpyHostToDevice);
     };
     auto up_f = [&](DevBuf<float>& b, const std::vector<float>& h) -> cudaError_t {
         cudaError_t e = b.alloc(h.size());
         if (e != cudaSuccess) return e;
-        return cudaMemcpy(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+        return dsat_memcpy_sync(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
     };
     CK_CUDA(c, up_i(c->cl_rowptr, cl_rowptr, n_clauses + 1));
     CK_CUDA(c, up_i(c->cl_lit, cl_lit, nnz));
@@ -983,7 +1061,7 @@ int dsat_sample_fetch(dsat_ctx* c, uint64_t* packed, uint8_t* is_sat, int32_t* l
         // cum_accuracy of diffusion(): a graph counts once any step's rounded prediction satisfied it,
         // which is exactly "latched" (reference DiffusionSampler.py:119-130,154-170)
         std::vector<int> ls(G);
-        CK_CUDA(c, cudaMemcpy(ls.data(), c->latch_step.p, G * sizeof(int), cudaMemcpyDeviceToHost));
+        CK_CUDA(c, dsat_memcpy_sync(ls.data(), c->latch_step.p, G * sizeof(int), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < G; ++i) sat_any_step[i] = ls[i] >= 0;
     }
     return DSAT_OK;
@@ -1120,7 +1198,28 @@ int dsat_debug_read(dsat_ctx* c, int buffer, float* host_out, long long count) {
     if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
     CK_ARG(c, count == rows * ld, "dsat_debug_read: count must be rows*ld");
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
-    CK_CUDA(c, cudaMemcpy(host_out, p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+#ifdef DSAT_WITH_TCGEN05
+    if (use_tc(c)) {    // on the tensor-core path these buffers live in bf16: convert for the caller
+        const __nv_bfloat16* src = nullptr;
+        switch (buffer) {
+            case DSAT_BUF_VROW: src = c->VROWb.p; break;
+            case DSAT_BUF_CROW: src = c->CROWb.p; break;
+            case DSAT_BUF_SPRE: src = c->SPREb.p; break;
+            case DSAT_BUF_QS: src = c->QSb.p; break;
+            case DSAT_BUF_LIT: src = c->LITb.p; break;
+            case DSAT_BUF_COUT: src = c->COUTb.p; break;
+            case DSAT_BUF_UOUT: src = c->UOUTb.p; break;
+            default: break;
+        }
+        if (src) {
+            std::vector<__nv_bfloat16> tmp((size_t)count);
+            CK_CUDA(c, dsat_memcpy_sync(tmp.data(), src, (size_t)count * 2, cudaMemcpyDeviceToHost));
+            for (long long i = 0; i < count; ++i) host_out[i] = __bfloat162float(tmp[i]);
+            return DSAT_OK;
+        }
+    }
+#endif
+    CK_CUDA(c, dsat_memcpy_sync(host_out, p, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
     return DSAT_OK;
 }
 
@@ -1133,12 +1232,12 @@ int dsat_debug_write(dsat_ctx* c, int buffer, const float* host_in, long long co
     if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
     CK_ARG(c, count == rows * ld, "dsat_debug_write: count must be rows*ld");
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
-    CK_CUDA(c, cudaMemcpy(p, host_in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    CK_CUDA(c, dsat_memcpy_sync(p, host_in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
 #ifdef DSAT_WITH_TCGEN05
     if (use_tc(c) && (buffer == DSAT_BUF_VROW || buffer == DSAT_BUF_CROW)) {   // keep the bf16 state mirror in step
         __nv_bfloat16* dst = buffer == DSAT_BUF_VROW ? c->VROWb.p : c->CROWb.p;
-        const long long tot = rows * c->F;
-        mirror_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(p, ld, dst, ld, rows, c->F);
+        const long long tot = rows * ld;
+        mirror_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(p, ld, dst, ld, rows, ld);
         LAUNCHED(c);
         CK_CUDA(c, cudaStreamSynchronize(c->stream));
     }
@@ -1171,9 +1270,9 @@ int dsat_tc_linear_test(dsat_ctx* c, int rows, int K, int N, const float* a_host
     CK_CUDA(c, db.alloc(N));
     CK_CUDA(c, dout_b.alloc((size_t)rows * out_cols));
     CK_CUDA(c, dout_f.alloc((size_t)rows * out_cols));
-    CK_CUDA(c, cudaMemcpy(da.p, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
-    CK_CUDA(c, cudaMemcpy(dw.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
-    CK_CUDA(c, cudaMemcpy(db.p, bias_host, N * sizeof(float), cudaMemcpyHostToDevice));
+    CK_CUDA(c, dsat_memcpy_sync(da.p, a.data(), a.size() * 2, cudaMemcpyHostToDevice));
+    CK_CUDA(c, dsat_memcpy_sync(dw.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+    CK_CUDA(c, dsat_memcpy_sync(db.p, bias_host, N * sizeof(float), cudaMemcpyHostToDevice));
     tc::TcLinear l;
     l.a_box_rows = rows < tc::BLOCK_M ? rows : tc::BLOCK_M;
     l.b_box_rows = N < tc::BLOCK_N ? N : tc::BLOCK_N;
@@ -1192,10 +1291,10 @@ int dsat_tc_linear_test(dsat_ctx* c, int rows, int K, int N, const float* a_host
     if (e == cudaSuccess) {
         if (out_bf16) {
             std::vector<__nv_bfloat16> ob((size_t)rows * out_cols);
-            e = cudaMemcpy(ob.data(), dout_b.p, ob.size() * 2, cudaMemcpyDeviceToHost);
+            e = dsat_memcpy_sync(ob.data(), dout_b.p, ob.size() * 2, cudaMemcpyDeviceToHost);
             for (size_t i = 0; i < ob.size(); ++i) out_host[i] = __bfloat162float(ob[i]);
         } else {
-            e = cudaMemcpy(out_host, dout_f.p, (size_t)rows * out_cols * sizeof(float), cudaMemcpyDeviceToHost);
+            e = dsat_memcpy_sync(out_host, dout_f.p, (size_t)rows * out_cols * sizeof(float), cudaMemcpyDeviceToHost);
         }
     }
     da.release(); dw.release(); db.release(); dout_b.release(); dout_f.release();
@@ -1235,7 +1334,7 @@ int dsat_debug_round(dsat_ctx* c, int round, const float* normals) {
     }
     float noise_scale = 0.f;
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
-    CK_CUDA(c, cudaMemcpy(&noise_scale, c->VROW.p + c->F + 6, sizeof(float), cudaMemcpyDeviceToHost));
+    CK_CUDA(c, dsat_memcpy_sync(&noise_scale, c->VROW.p + c->F + 6, sizeof(float), cudaMemcpyDeviceToHost));
     NoiseSource ns{0ull, 0ull, 0u};
     rc = run_round(c, round, normals ? c->inj_normals.p : nullptr, ns, loss_scalars(noise_scale));
     if (rc) return rc;
@@ -1249,11 +1348,11 @@ int dsat_debug_groups(dsat_ctx* c, int32_t* done, int32_t* steps_taken, float* l
     CK_ARG(c, c->has_buffers, "no buffers yet");
     CK_CUDA(c, cudaSetDevice(c->device));
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (done) CK_CUDA(c, cudaMemcpy(done, c->done.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
-    if (steps_taken) CK_CUDA(c, cudaMemcpy(steps_taken, c->steps_taken.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
-    if (loss_sum) CK_CUDA(c, cudaMemcpy(loss_sum, c->loss_sum.p, c->n_groups * sizeof(float), cudaMemcpyDeviceToHost));
-    if (graph_sat) CK_CUDA(c, cudaMemcpy(graph_sat, c->graph_sat.p, c->total_graphs * sizeof(int), cudaMemcpyDeviceToHost));
-    if (graph_map) CK_CUDA(c, cudaMemcpy(graph_map, c->graph_map.p, c->total_graphs * sizeof(int), cudaMemcpyDeviceToHost));
+    if (done) CK_CUDA(c, dsat_memcpy_sync(done, c->done.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
+    if (steps_taken) CK_CUDA(c, dsat_memcpy_sync(steps_taken, c->steps_taken.p, c->n_groups * sizeof(int), cudaMemcpyDeviceToHost));
+    if (loss_sum) CK_CUDA(c, dsat_memcpy_sync(loss_sum, c->loss_sum.p, c->n_groups * sizeof(float), cudaMemcpyDeviceToHost));
+    if (graph_sat) CK_CUDA(c, dsat_memcpy_sync(graph_sat, c->graph_sat.p, c->total_graphs * sizeof(int), cudaMemcpyDeviceToHost));
+    if (graph_map) CK_CUDA(c, dsat_memcpy_sync(graph_map, c->graph_map.p, c->total_graphs * sizeof(int), cudaMemcpyDeviceToHost));
     return DSAT_OK;
 }
 

@@ -124,6 +124,30 @@ __device__ __forceinline__ LaneVec<V> lane_load_t(const T* __restrict__ row, int
     if constexpr (sizeof(T) == 2) return lane_load_bf16<V>(reinterpret_cast<const __nv_bfloat16*>(row), lane);
     else return lane_load<V>(reinterpret_cast<const float*>(row), lane);
 }
+// coherent loads for rows that the same kernel also writes
+template <int V, typename T>
+__device__ __forceinline__ LaneVec<V> lane_load_rw_t(const T* row, int lane) {
+    if constexpr (sizeof(T) == 2) {
+        LaneVec<V> r;
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(row);
+        if constexpr (V == 2) {
+            __nv_bfloat162 t = reinterpret_cast<const __nv_bfloat162*>(p)[lane];
+            r.v[0] = __low2float(t); r.v[1] = __high2float(t);
+        } else {
+#pragma unroll
+            for (int c = 0; c < V / 4; ++c) {
+                uint2 raw = reinterpret_cast<const uint2*>(p + c * 128)[lane];
+                __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+                __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+                r.v[4 * c + 0] = __low2float(a); r.v[4 * c + 1] = __high2float(a);
+                r.v[4 * c + 2] = __low2float(b); r.v[4 * c + 3] = __high2float(b);
+            }
+        }
+        return r;
+    } else {
+        return lane_load_rw<V>(reinterpret_cast<const float*>(row), lane);
+    }
+}
 template <int V, typename T>
 __device__ __forceinline__ void lane_store_t(T* __restrict__ row, int lane, const LaneVec<V>& r) {
     if constexpr (sizeof(T) == 2) lane_store_bf16<V>(reinterpret_cast<__nv_bfloat16*>(row), lane, r);

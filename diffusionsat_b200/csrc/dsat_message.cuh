@@ -222,3 +222,128 @@ inline int gather_grid(long long total_rows, int sm_count) {
 }
 
 }  // namespace dsat
+
+// ===================================================================== shared-memory staged variants
+// For small formulas the gathered tables of one chain fit in shared memory: a CTA copies the chain's
+// rows in once with coalesced 16-byte loads (each row read from L2/HBM exactly once) and every edge
+// then reads shared memory instead of L2.  blockIdx.x = chain, blockIdx.y = feature slice of width
+// W = 32*VS (the features are independent, so a slice is a complete sub-problem).
+namespace dsat {
+
+template <typename T>
+__device__ __forceinline__ void stage_rows(T* __restrict__ dst, const T* __restrict__ src, int rows, int ld_src,
+                                           int width, int tid, int nthreads) {
+    const int vec_per_row = width * (int)sizeof(T) / 16;
+    const int total = rows * vec_per_row;
+    for (int i = tid; i < total; i += nthreads) {
+        const int r = i / vec_per_row, v = i % vec_per_row;
+        reinterpret_cast<uint4*>(dst + (size_t)r * width)[v] =
+            __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld_src) + v);
+    }
+}
+
+// clause side: tables LIT[n][2 halves][W] and SP[n][2 halves][W] of the chain's slice
+template <int VS, typename T>
+__global__ void __launch_bounds__(1024)
+clause_gather_smem_kernel(UnitGraphDev g, int Q,
+                          const T* __restrict__ LIT, int ld_lit,
+                          const T* __restrict__ SP, int ld_sp, int sp_off,
+                          T* __restrict__ OUT, int ld_out, int out_off) {
+    constexpr int W = 32 * VS;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    T* t_lit = reinterpret_cast<T*>(gsm);                       // [2n][W]  row = 2*var + sign
+    T* t_sp = t_lit + (size_t)2 * g.n * W;
+    const int chain = blockIdx.x, slice = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const size_t vbase = (size_t)chain * g.n;
+    // positive half-rows then negative half-rows interleaved as literal codes: stage each sign separately
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        // rows of sign `sgn` land at t[(2*v + sgn) * W]: stage with an output stride of 2*W
+        const int vec_per_row = W * (int)sizeof(T) / 16;
+        for (int i = tid; i < g.n * vec_per_row; i += blockDim.x) {
+            const int v = i / vec_per_row, k = i % vec_per_row;
+            reinterpret_cast<uint4*>(t_lit + (size_t)(2 * v + sgn) * W)[k] =
+                __ldg(reinterpret_cast<const uint4*>(LIT + (vbase + v) * ld_lit + sgn * Q + slice * W) + k);
+            reinterpret_cast<uint4*>(t_sp + (size_t)(2 * v + sgn) * W)[k] =
+                __ldg(reinterpret_cast<const uint4*>(SP + (vbase + v) * ld_sp + sp_off + sgn * Q + slice * W) + k);
+        }
+    }
+    __syncthreads();
+    for (int j = warp; j < g.m; j += nwarps) {
+        const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
+        LaneVec<VS> acc_l, acc_s;
+#pragma unroll
+        for (int i = 0; i < VS; ++i) { acc_l.v[i] = 0.f; acc_s.v[i] = 0.f; }
+        for (int e = e0; e < e1; ++e) {
+            const int code = __ldg(g.cl_lit + e);
+            LaneVec<VS> l0 = lane_load_rw_t<VS, T>(t_lit + (size_t)code * W, lane);
+            LaneVec<VS> s0 = lane_load_rw_t<VS, T>(t_sp + (size_t)code * W, lane);
+#pragma unroll
+            for (int i = 0; i < VS; ++i) { acc_l.v[i] += l0.v[i]; acc_s.v[i] += s0.v[i]; }
+        }
+        const float rw = __ldg(g.rev_w + j);
+#pragma unroll
+        for (int i = 0; i < VS; ++i) {
+            acc_l.v[i] *= rw;
+            acc_s.v[i] = 4.0f * __expf(-acc_s.v[i]);
+        }
+        T* dst = OUT + ((size_t)chain * g.m + j) * ld_out + out_off + slice * W;
+        lane_store_t<VS, T>(dst, lane, acc_l);
+        lane_store_t<VS, T>(dst + Q, lane, acc_s);
+    }
+}
+
+// literal side: tables CL4[m][W] and MSG[m][W] of the chain's slice
+template <int VS, typename T>
+__global__ void __launch_bounds__(1024)
+literal_gather_smem_kernel(UnitGraphDev g, int Q,
+                           const T* __restrict__ CL4, int ld_cl, int cl_off,
+                           const T* __restrict__ MSG, int ld_msg,
+                           const T* __restrict__ QRY, int ld_q,
+                           T* __restrict__ OUT, int ld_out, int out_off) {
+    constexpr int W = 32 * VS;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    T* t_cl = reinterpret_cast<T*>(gsm);                        // [m][W]
+    T* t_ms = t_cl + (size_t)g.m * W;
+    const int chain = blockIdx.x, slice = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const size_t cbase = (size_t)chain * g.m;
+    stage_rows<T>(t_cl, CL4 + cbase * ld_cl + cl_off + slice * W, g.m, ld_cl, W, tid, blockDim.x);
+    stage_rows<T>(t_ms, MSG + cbase * ld_msg + slice * W, g.m, ld_msg, W, tid, blockDim.x);
+    __syncthreads();
+    for (int v = warp; v < g.n; v += nwarps) {
+        LaneVec<VS> s4[2], ms[2];
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+#pragma unroll
+            for (int i = 0; i < VS; ++i) { s4[sgn].v[i] = 0.f; ms[sgn].v[i] = 0.f; }
+            const int code = 2 * v + sgn;
+            const int e0 = __ldg(g.lit_rowptr + code), e1 = __ldg(g.lit_rowptr + code + 1);
+            for (int e = e0; e < e1; ++e) {
+                const int j = __ldg(g.lit_clause + e);
+                LaneVec<VS> a0 = lane_load_rw_t<VS, T>(t_cl + (size_t)j * W, lane);
+                LaneVec<VS> b0 = lane_load_rw_t<VS, T>(t_ms + (size_t)j * W, lane);
+#pragma unroll
+                for (int i = 0; i < VS; ++i) { s4[sgn].v[i] += a0.v[i]; ms[sgn].v[i] += b0.v[i]; }
+            }
+        }
+        const size_t row = (size_t)chain * g.n + v;
+        LaneVec<VS> q = lane_load_t<VS, T>(QRY + row * ld_q + slice * W, lane);
+        const float vw = __ldg(g.vdeg_w + v);
+        const float dwp = __ldg(g.deg_w + 2 * v), dwn = __ldg(g.deg_w + 2 * v + 1);
+        LaneVec<VS> grad;
+#pragma unroll
+        for (int i = 0; i < VS; ++i) {
+            const float sg = 1.0f / (1.0f + __expf(-q.v[i]));
+            grad.v[i] = (-sg * s4[0].v[i] + (1.0f - sg) * s4[1].v[i]) * vw;
+            ms[0].v[i] *= dwp;
+            ms[1].v[i] *= dwn;
+        }
+        T* dst = OUT + row * ld_out + out_off + slice * W;
+        lane_store_t<VS, T>(dst, lane, grad);
+        lane_store_t<VS, T>(dst + Q, lane, ms[0]);
+        lane_store_t<VS, T>(dst + 2 * Q, lane, ms[1]);
+    }
+}
+
+}  // namespace dsat

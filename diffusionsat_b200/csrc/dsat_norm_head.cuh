@@ -20,15 +20,14 @@ __device__ __forceinline__ int lane_col(int lane, int i) {
 //   x *= rsqrt(mean_f(x^2) + 1e-6)                   per node
 // fused with the caller's  new = x*0.25 + 0.1*old  (model/query_sat.py:265-266, 279-280) and with the
 // end-of-round  s = s*0.2 + s*0.8  (:347-348).  PRE (optional) receives the state before that carry:
-// it is what variables_output reads (:283).
-template <int V>
+// it is what variables_output reads (:283).  TS / TX = storage type of the input and of the state
+// (float on the fp32 path, bf16 on the tensor-core path; the arithmetic is fp32 either way).
+template <int V, typename TS, typename TX>
 __global__ void __launch_bounds__(256)
 pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
-                const float* __restrict__ SRC, int ld_src, int src_off,
-                float* __restrict__ STATE, int ld_state,
-                float* __restrict__ PRE, int ld_pre,
-                __nv_bfloat16* __restrict__ STATE_B, int ld_state_b,     // bf16 mirrors for the tensor-core path
-                __nv_bfloat16* __restrict__ PRE_B, int ld_pre_b) {
+                const TS* __restrict__ SRC, int ld_src, int src_off,
+                TX* __restrict__ STATE, int ld_state,
+                TX* __restrict__ PRE, int ld_pre) {
     constexpr int F = 32 * V;
     __shared__ float red[8][F];
     __shared__ float mean_s[F];
@@ -42,7 +41,7 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
 #pragma unroll
         for (int i = 0; i < V; ++i) sum.v[i] = 0.f;
         for (size_t r = r0 + warp; r < r1; r += 8) {
-            LaneVec<V> x = lane_load<V>(SRC + r * ld_src + src_off, lane);
+            LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
 #pragma unroll
             for (int i = 0; i < V; ++i) sum.v[i] += x.v[i] * wgt;
         }
@@ -60,24 +59,22 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
 #pragma unroll
         for (int i = 0; i < V; ++i) mean.v[i] = mean_s[lane_col<V>(lane, i)];
         for (size_t r = r0 + warp; r < r1; r += 8) {
-            LaneVec<V> x = lane_load<V>(SRC + r * ld_src + src_off, lane);
+            LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
             float ss = 0.f;
 #pragma unroll
             for (int i = 0; i < V; ++i) { x.v[i] -= mean.v[i]; ss += x.v[i] * x.v[i]; }
             ss = warp_sum(ss);
             const float inv = rsqrtf(ss / (float)F + 1.0e-6f);
-            float* srow = STATE + r * ld_state;
-            LaneVec<V> old = lane_load_rw<V>(srow, lane);
+            TX* srow = STATE + r * ld_state;
+            LaneVec<V> old = lane_load_rw_t<V, TX>(srow, lane);
             LaneVec<V> nw, carried;
 #pragma unroll
             for (int i = 0; i < V; ++i) {
                 nw.v[i] = __fadd_rn(__fmul_rn(x.v[i] * inv, 0.25f), __fmul_rn(0.1f, old.v[i]));
                 carried.v[i] = __fadd_rn(__fmul_rn(nw.v[i], 0.2f), __fmul_rn(nw.v[i], 0.8f));
             }
-            if (PRE) lane_store<V>(PRE + r * ld_pre, lane, nw);
-            if (PRE_B) lane_store_bf16<V>(PRE_B + r * ld_pre_b, lane, nw);
-            if (STATE_B) lane_store_bf16<V>(STATE_B + r * ld_state_b, lane, carried);
-            lane_store<V>(srow, lane, carried);
+            if (PRE) lane_store_t<V, TX>(PRE + r * ld_pre, lane, nw);
+            lane_store_t<V, TX>(srow, lane, carried);
         }
         __syncthreads();
     }
