@@ -17,6 +17,7 @@
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
 #include "dsat_mlp_fused.cuh"
+#include "dsat_message_tma.cuh"
 #endif
 
 using namespace dsat;
@@ -113,6 +114,11 @@ struct dsat_ctx {
     bool fused_ready = false;
     bool use_fused = true;
     bool use_smem_gather = true;
+    // TMA-staged persistent gathers (dsat_message_tma.cuh)
+    CUtensorMap map_g_lit, map_g_sp, map_g_cl, map_g_ms;
+    tg::GatherPlan gp_clause, gp_literal;
+    bool tma_clause_ready = false, tma_literal_ready = false;
+    bool use_tma_gather = false;     // measured slightly slower than the cooperative-load staging at cfg2: opt-in (DSAT_TMA_GATHER=1)
 #endif
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
@@ -295,6 +301,27 @@ int ensure_tc_buffers(dsat_ctx* c) {
         ok = ok && build(FO, OP_O1, {{OP_O1, c->HO, W(OP_O1), B(OP_O1), tc::TC_LRELU},
                                      {OP_O2, DSAT_LOGIT_PAD, W(OP_O2), B(OP_O2), tc::TC_LINEAR}}, o);
         c->fused_ready = ok;
+    }
+    {   // TMA-staged gathers: one formula per chain whose tables fit in shared memory twice
+        c->tma_clause_ready = c->tma_literal_ready = false;
+        if (c->n_graphs == 1 && 2 * Q <= 256) {
+            tg::GatherPlan& gc = c->gp_clause;
+            gc.width = 2 * Q; gc.slices = 1;
+            gc.boxes = (c->n + 255) / 256;
+            gc.box_rows = (c->n + gc.boxes - 1) / gc.boxes;
+            gc.table_bytes = gc.boxes * gc.box_rows * gc.width * 2;
+            gc.smem_bytes = 4 * gc.table_bytes + 64 + 128;
+            if (gc.smem_bytes <= 226 * 1024 &&
+                tc::make_bf16_map_plain(&c->map_g_lit, c->LITb.p, c->Nt, 2 * Q, 2 * Q, 2 * Q, gc.box_rows) &&
+                tc::make_bf16_map_plain(&c->map_g_sp, c->QSb.p + Q, c->Nt, 2 * Q, 3 * Q, 2 * Q, gc.box_rows))
+                c->tma_clause_ready = true;
+        }
+        if (c->n_graphs == 1 && tg::plan_gather(c->m, Q, 128, &c->gp_literal)) {
+            const tg::GatherPlan& gl = c->gp_literal;
+            if (tc::make_bf16_map_plain(&c->map_g_cl, c->CROWb.p + F + Q, c->Mt, Q, c->ldc(), gl.width, gl.box_rows) &&
+                tc::make_bf16_map_plain(&c->map_g_ms, c->COUTb.p, c->Mt, Q, Q + F, gl.width, gl.box_rows))
+                c->tma_literal_ready = true;
+        }
     }
     c->has_tc_buffers = true;
     return DSAT_OK;
@@ -492,10 +519,29 @@ static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out) {
 
 template <typename K>
 static bool set_dyn_smem(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) == cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
 }
 
 bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
+    if (c->tma_clause_ready && c->use_tma_gather && (c->Q == 128 || c->Q == 64)) {
+        const int grid = c->chains < c->sm_count ? c->chains : c->sm_count;
+        const tg::GatherPlan& gp = c->gp_clause;
+        if (c->Q == 128) {
+            static bool ok = set_dyn_smem(tg::clause_gather_tma_kernel<4>);
+            if (ok) {
+                tg::clause_gather_tma_kernel<4><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
+                    c->map_g_lit, c->map_g_sp, g, c->chains, gp, c->CROWb.p, c->ldc(), c->F);
+                return true;
+            }
+        } else {
+            static bool ok = set_dyn_smem(tg::clause_gather_tma_kernel<2>);
+            if (ok) {
+                tg::clause_gather_tma_kernel<2><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
+                    c->map_g_lit, c->map_g_sp, g, c->chains, gp, c->CROWb.p, c->ldc(), c->F);
+                return true;
+            }
+        }
+    }
     if (c->n_graphs != 1 || !c->use_smem_gather) return false;
     size_t bytes = 0;
     const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes);
@@ -518,6 +564,28 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
 }
 
 bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
+    if (c->tma_literal_ready && c->use_tma_gather) {
+        const tg::GatherPlan& gp = c->gp_literal;
+        const int items = c->chains * gp.slices;
+        const int grid = items < c->sm_count ? items : c->sm_count;
+        if (gp.width == 128) {
+            static bool ok = set_dyn_smem(tg::literal_gather_tma_kernel<4>);
+            if (ok) {
+                tg::literal_gather_tma_kernel<4><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
+                    c->map_g_cl, c->map_g_ms, g, c->chains, c->Q, gp, c->QSb.p, 3 * c->Q, c->VROWb.p, c->ldv(),
+                    c->F + DSAT_AUX_PAD);
+                return true;
+            }
+        } else if (gp.width == 64) {
+            static bool ok = set_dyn_smem(tg::literal_gather_tma_kernel<2>);
+            if (ok) {
+                tg::literal_gather_tma_kernel<2><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
+                    c->map_g_cl, c->map_g_ms, g, c->chains, c->Q, gp, c->QSb.p, 3 * c->Q, c->VROWb.p, c->ldv(),
+                    c->F + DSAT_AUX_PAD);
+                return true;
+            }
+        }
+    }
     if (c->n_graphs != 1 || !c->use_smem_gather) return false;
     size_t bytes = 0;
     const int w = pick_slice_width((size_t)c->m, c->Q, &bytes);
@@ -632,11 +700,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
         if (!tcp)
-            pairnorm_kernel<V, float, float><<<grid, 256, 0, c->stream>>>(
+            pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
 #ifdef DSAT_WITH_TCGEN05
         else
-            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, c->stream>>>(
+            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUTb.p, Q + F, Q, c->CROWb.p, ldc, nullptr, 0);
 #endif
     });
@@ -665,11 +733,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
         if (!tcp)
-            pairnorm_kernel<V, float, float><<<grid, 256, 0, c->stream>>>(
+            pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
 #ifdef DSAT_WITH_TCGEN05
         else
-            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, c->stream>>>(
+            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUTb.p, F, 0, c->VROWb.p, ldv, c->SPREb.p, F);
 #endif
     });
@@ -790,6 +858,8 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e && e[0] == '0') c->use_fused = false;
         e = getenv("DSAT_SMEM_GATHER");
         if (e && e[0] == '0') c->use_smem_gather = false;
+        e = getenv("DSAT_TMA_GATHER");
+        if (e) c->use_tma_gather = e[0] != '0';
     }
 #endif
     *out = c;

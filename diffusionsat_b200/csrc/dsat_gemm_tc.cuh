@@ -292,6 +292,21 @@ inline bool make_bf16_map(CUtensorMap* map, const void* base, long long rows, in
     return r == CUDA_SUCCESS;
 }
 
+// 2-D bf16 tensor, dense (unswizzled) boxes of box_cols x box_rows: staging of gather tables
+inline bool make_bf16_map_plain(CUtensorMap* map, const void* base, long long rows, int cols, int ld, int box_cols,
+                                int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 struct TcLinear {
     CUtensorMap map_a, map_b;
     const float* bias;

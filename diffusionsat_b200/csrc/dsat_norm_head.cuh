@@ -22,14 +22,17 @@ __device__ __forceinline__ int lane_col(int lane, int i) {
 // end-of-round  s = s*0.2 + s*0.8  (:347-348).  PRE (optional) receives the state before that carry:
 // it is what variables_output reads (:283).  TS / TX = storage type of the input and of the state
 // (float on the fp32 path, bf16 on the tensor-core path; the arithmetic is fp32 either way).
+constexpr int PN_WARPS = 8;
+constexpr int PN_UNROLL = 4;      // rows in flight per warp (memory-level parallelism)
+
 template <int V, typename TS, typename TX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PN_WARPS * 32)
 pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
                 const TS* __restrict__ SRC, int ld_src, int src_off,
                 TX* __restrict__ STATE, int ld_state,
                 TX* __restrict__ PRE, int ld_pre) {
     constexpr int F = 32 * V;
-    __shared__ float red[8][F];
+    __shared__ float red[PN_WARPS][F];
     __shared__ float mean_s[F];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
@@ -40,33 +43,43 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
         LaneVec<V> sum;
 #pragma unroll
         for (int i = 0; i < V; ++i) sum.v[i] = 0.f;
-        for (size_t r = r0 + warp; r < r1; r += 8) {
-            LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
+        {
+            size_t r = r0 + warp;
+            for (; r + (PN_UNROLL - 1) * PN_WARPS < r1; r += PN_UNROLL * PN_WARPS) {
+                LaneVec<V> x[PN_UNROLL];
 #pragma unroll
-            for (int i = 0; i < V; ++i) sum.v[i] += x.v[i] * wgt;
+                for (int u = 0; u < PN_UNROLL; ++u)
+                    x[u] = lane_load_t<V, TS>(SRC + (r + u * PN_WARPS) * ld_src + src_off, lane);
+#pragma unroll
+                for (int u = 0; u < PN_UNROLL; ++u)
+#pragma unroll
+                    for (int i = 0; i < V; ++i) sum.v[i] += x[u].v[i] * wgt;
+            }
+            for (; r < r1; r += PN_WARPS) {
+                LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
+#pragma unroll
+                for (int i = 0; i < V; ++i) sum.v[i] += x.v[i] * wgt;
+            }
         }
 #pragma unroll
         for (int i = 0; i < V; ++i) red[warp][lane_col<V>(lane, i)] = sum.v[i];
         __syncthreads();
-        for (int col = tid; col < F; col += 256) {
+        for (int col = tid; col < F; col += PN_WARPS * 32) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += red[w][col];
+            for (int w = 0; w < PN_WARPS; ++w) s += red[w][col];
             mean_s[col] = s;
         }
         __syncthreads();
         LaneVec<V> mean;
 #pragma unroll
         for (int i = 0; i < V; ++i) mean.v[i] = mean_s[lane_col<V>(lane, i)];
-        for (size_t r = r0 + warp; r < r1; r += 8) {
-            LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
+        auto finish_row = [&](size_t r, LaneVec<V> x, const LaneVec<V>& old) {
             float ss = 0.f;
 #pragma unroll
             for (int i = 0; i < V; ++i) { x.v[i] -= mean.v[i]; ss += x.v[i] * x.v[i]; }
             ss = warp_sum(ss);
             const float inv = rsqrtf(ss / (float)F + 1.0e-6f);
-            TX* srow = STATE + r * ld_state;
-            LaneVec<V> old = lane_load_rw_t<V, TX>(srow, lane);
             LaneVec<V> nw, carried;
 #pragma unroll
             for (int i = 0; i < V; ++i) {
@@ -74,7 +87,25 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
                 carried.v[i] = __fadd_rn(__fmul_rn(nw.v[i], 0.2f), __fmul_rn(nw.v[i], 0.8f));
             }
             if (PRE) lane_store_t<V, TX>(PRE + r * ld_pre, lane, nw);
-            lane_store_t<V, TX>(srow, lane, carried);
+            lane_store_t<V, TX>(STATE + r * ld_state, lane, carried);
+        };
+        {
+            size_t r = r0 + warp;
+            for (; r + (PN_UNROLL - 1) * PN_WARPS < r1; r += PN_UNROLL * PN_WARPS) {
+                LaneVec<V> x[PN_UNROLL], old[PN_UNROLL];
+#pragma unroll
+                for (int u = 0; u < PN_UNROLL; ++u) {
+                    x[u] = lane_load_t<V, TS>(SRC + (r + u * PN_WARPS) * ld_src + src_off, lane);
+                    old[u] = lane_load_rw_t<V, TX>(STATE + (r + u * PN_WARPS) * ld_state, lane);
+                }
+#pragma unroll
+                for (int u = 0; u < PN_UNROLL; ++u) finish_row(r + u * PN_WARPS, x[u], old[u]);
+            }
+            for (; r < r1; r += PN_WARPS) {
+                LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
+                LaneVec<V> old = lane_load_rw_t<V, TX>(STATE + r * ld_state, lane);
+                finish_row(r, x, old);
+            }
         }
         __syncthreads();
     }
