@@ -348,6 +348,17 @@ def _pow(x, y):
 
 def install():
     """Register the shim as `tensorflow`, `tensorflow_probability`, … in sys.modules. Returns the tf module."""
+    # EagerTensor.numpy() works on anything; torch refuses on tensors that are part of an autograd graph
+    # (the Dense kernels require grad so that the reference's inner GradientTape works)
+    if not getattr(torch.Tensor.numpy, "_dsat_patched", False):
+        _orig_numpy = torch.Tensor.numpy
+
+        def _numpy(self, *a, **k):
+            return _orig_numpy(self.detach(), *a, **k)
+
+        _numpy._dsat_patched = True
+        torch.Tensor.numpy = _numpy
+
     tf = types.ModuleType("tensorflow")
     tf.float32, tf.int32, tf.int64, tf.bool = float32, int32, int64, bool_
     tf.Tensor = torch.Tensor

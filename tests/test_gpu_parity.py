@@ -248,3 +248,34 @@ def test_sampler_end_to_end(ctx, tmp_path):
     sampler2 = DiffusionSampler(str(wpath), str(cnf), context=ctx, chains_per_launch=2048, seed=3,
                                 max_nodes_per_batch=130)
     assert sampler2.samples(100) == hist
+
+
+# ---------------------------------------------------------------- against the reference's own source
+# golden vectors from tests/golden/make_model_golden.py (reference model/query_sat.py and
+# satuniformity/DiffusionSampler.py executed over the torch-backed TF stand-in)
+from tests.test_oracle_vs_reference_golden import DIFF_TAGS, STEP_TAGS, diff_case, step_case  # noqa: E402
+
+
+@pytest.mark.parametrize("tag", STEP_TAGS)
+def test_cuda_model_call_matches_reference_source(ctx, tag):
+    c = step_case(tag)
+    wts = H.W.init_weights(seed=c["wseed"], bias_scale=0.1)
+    bind(ctx, c["n_vars"], c["clauses"], c["chains"], wts)
+    pred, steps, loss = ctx.model_call(c["noise_scale"], c["noisy"], labels=c["labels"], normals=c["normals"],
+                                       rounds=c["rounds"])
+    assert steps[0] == c["steps_taken"]
+    check("prediction vs reference source", pred, c["prediction"], 1e-3)
+    assert abs(loss[0] - c["loss"]) < 1e-3 * max(1.0, abs(c["loss"]))
+
+
+@pytest.mark.parametrize("tag", DIFF_TAGS)
+def test_cuda_diffusion_matches_reference_source(ctx, tag):
+    c = diff_case(tag)
+    wts = H.W.init_weights(seed=c["wseed"], bias_scale=0.1)
+    bind(ctx, c["n_vars"], c["clauses"], c["chains"], wts, group=c["chains"])
+    packed, is_sat, latch, _ = ctx.sample(c["steps"], c["rounds"], uniforms=c["uniforms"], labels=c["labels"],
+                                          normals=c["normals"])
+    from diffusionsat_b200.sampler import unpack_assignments
+    got = unpack_assignments(packed, c["n_vars"])
+    want = [O.encode_assignment(c["predictions"][i * c["n_vars"]:(i + 1) * c["n_vars"]]) for i in range(c["chains"])]
+    assert got == want
