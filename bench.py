@@ -161,36 +161,44 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ our arm
 def message_pass_roofline(ctx, torch, pk):
-    """Segment-sum SpMM alone on BASELINE configs[4]'s graph: n=10000, m=43000, F=128, fp32."""
+    """Segment-sum SpMM alone on BASELINE configs[4]'s graph (n=10000, m=43000): sweep over the feature
+    width and storage type; the headline entry is F=128 fp32 (the model's width), worst direction."""
     from diffusionsat_b200 import graph, synth
-    n, m, feat, chains = 10000, 43000, 128, 96          # (2n+m)*chains*F*4 = 3.1 GB per launch > L2
+    n, m = 10000, 43000
     nv, clauses = synth.random_3sat(n, m, seed=5)
     unit = graph.build_unit_graph(nv, clauses)
     ctx.set_graph(unit, chains=1, group_graphs=0)
     dev = torch.device("cuda", ctx.device)
-    out = {}
-    for name, direction, rin, rout in (("clause_from_literal", 0, 2 * n, m), ("literal_from_clause", 1, m, 2 * n)):
-        x = torch.randn(chains, rin, feat, device=dev)
-        y = torch.empty(chains, rout, feat, device=dev)
-        torch.cuda.synchronize()
-        for _ in range(3):
-            ctx.spmm(direction, x.data_ptr(), y.data_ptr(), feat, 0, chains)
-        ctx.synchronize()
-        reps = 5
-        ctx.timer_begin()
-        for _ in range(reps):
-            ctx.spmm(direction, x.data_ptr(), y.data_ptr(), feat, 0, chains)
-        ms = ctx.timer_end() / reps
-        nbytes = (rin + rout) * chains * feat * 4 + (unit.nnz + rout + 1) * 4
-        out[name] = {"achieved": nbytes / ms / 1e6, "ms": ms, "bytes": nbytes}
-        del x, y
-    best = max(out.values(), key=lambda d: d["achieved"])
-    worst = min(out.values(), key=lambda d: d["achieved"])
-    return {"bound": "hbm", "achieved": worst["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": worst["achieved"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-            "workload": "segment-sum SpMM, shared adjacency, 3-SAT n=10000 m=43000, %d chains, F=128 fp32" % chains,
-            "clause_from_literal_gbs": out["clause_from_literal"]["achieved"],
-            "literal_from_clause_gbs": out["literal_from_clause"]["achieved"], "best_gbs": best["achieved"]}
+    sweep = {}
+    for feat, dtype_name, tdt, code in ((128, "f32", torch.float32, 0), (64, "f32", torch.float32, 0),
+                                        (256, "f32", torch.float32, 0), (128, "bf16", torch.bfloat16, 1)):
+        es = 4 if code == 0 else 2
+        chains = max(8, int(3.0e9 / ((2 * n + m) * feat * es)))          # ~3 GB per launch, far beyond L2
+        res = {}
+        for name, direction, rin, rout in (("clause_from_literal", 0, 2 * n, m), ("literal_from_clause", 1, m, 2 * n)):
+            x = torch.randn(chains, rin, feat, device=dev).to(tdt)
+            y = torch.empty(chains, rout, feat, device=dev, dtype=tdt)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                ctx.spmm(direction, x.data_ptr(), y.data_ptr(), feat, code, chains)
+            ctx.synchronize()
+            reps = 5
+            ctx.timer_begin()
+            for _ in range(reps):
+                ctx.spmm(direction, x.data_ptr(), y.data_ptr(), feat, code, chains)
+            ms = ctx.timer_end() / reps
+            nbytes = (rin + rout) * chains * feat * es + (unit.nnz + rout + 1) * 4
+            res[name] = {"gbs": nbytes / ms / 1e6, "ms": ms, "bytes": nbytes, "chains": chains}
+            del x, y
+        sweep["F%d_%s" % (feat, dtype_name)] = res
+    head = sweep["F128_f32"]
+    worst = min(head.values(), key=lambda d: d["gbs"])
+    return {"bound": "hbm", "achieved": worst["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": worst["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+            "workload": "segment-sum SpMM, shared adjacency, 3-SAT n=10000 m=43000, %d chains, F=128 fp32; bytes = "
+                        "(R_in+R_out)*C*F*s + (nnz+R_out+1)*4" % worst["chains"],
+            "avg_launch_ms": worst["ms"], "bytes_per_launch": worst["bytes"],
+            "sweep_gbs": {k: {d: round(v[d]["gbs"], 1) for d in v} for k, v in sweep.items()}}
 
 
 def run_ours(args):
@@ -289,7 +297,8 @@ def run_ours(args):
     peak_tf = pk["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
-                "kernel": "sgemm128_kernel (fp32 CUDA cores)" if precision == "fp32" else "tc_linear_kernel (tcgen05 bf16)",
+                "kernel": "sgemm128_kernel (fp32 CUDA cores)" if precision == "fp32"
+                          else "fused_mlp_kernel (tcgen05 bf16, one persistent launch per MLP, 5 per round)",
                 "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_round": gemm_ms / total_ms,
                 "flops_per_launch": flops / max(gemm_launches, 1),
                 "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items()}}

@@ -550,14 +550,14 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     using T = __nv_bfloat16;
     const int Q = c->Q;
     if (w == 128) {
-        static bool ok = set_dyn_smem(clause_gather_smem_kernel<4, T>);
+        static bool ok = set_dyn_smem(clause_gather_smem_kernel<128>);
         if (!ok) return false;
-        clause_gather_smem_kernel<4, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
+        clause_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
                                                                           c->CROWb.p, c->ldc(), c->F);
     } else {
-        static bool ok = set_dyn_smem(clause_gather_smem_kernel<2, T>);
+        static bool ok = set_dyn_smem(clause_gather_smem_kernel<64>);
         if (!ok) return false;
-        clause_gather_smem_kernel<2, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
+        clause_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
                                                                           c->CROWb.p, c->ldc(), c->F);
     }
     return true;
@@ -594,14 +594,14 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     using T = __nv_bfloat16;
     const int Q = c->Q, F = c->F;
     if (w == 128) {
-        static bool ok = set_dyn_smem(literal_gather_smem_kernel<4, T>);
+        static bool ok = set_dyn_smem(literal_gather_smem_kernel<128>);
         if (!ok) return false;
-        literal_gather_smem_kernel<4, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
+        literal_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
                                                                            c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
     } else {
-        static bool ok = set_dyn_smem(literal_gather_smem_kernel<2, T>);
+        static bool ok = set_dyn_smem(literal_gather_smem_kernel<64>);
         if (!ok) return false;
-        literal_gather_smem_kernel<2, T><<<grid, 1024, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
+        literal_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
                                                                            c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
     }
     return true;

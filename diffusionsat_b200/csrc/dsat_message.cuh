@@ -226,123 +226,185 @@ inline int gather_grid(long long total_rows, int sm_count) {
 // ===================================================================== shared-memory staged variants
 // For small formulas the gathered tables of one chain fit in shared memory: a CTA copies the chain's
 // rows in once with coalesced 16-byte loads (each row read from L2/HBM exactly once) and every edge
-// then reads shared memory instead of L2.  blockIdx.x = chain, blockIdx.y = feature slice of width
-// W = 32*VS (the features are independent, so a slice is a complete sub-problem).
+// then reads shared memory instead of L2.  blockIdx.x = chain, blockIdx.y = feature slice of width W
+// (the features are independent, so a slice is a complete sub-problem).  bf16 storage, fp32 sums.
+// Work split inside a warp: LPR = W/8 lanes share one output row (16 bytes = 8 features per lane), so a
+// warp produces 32/LPR rows per pass: the index loads and address arithmetic are amortised over 8
+// features instead of 4.
 namespace dsat {
+
+struct Acc8 { float v[8]; };
+
+__device__ __forceinline__ void acc8_zero(Acc8& a) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = 0.f;
+}
+// add 8 bf16 (one uint4) to 8 fp32 accumulators; bf16 -> fp32 is a shift / mask of the 32-bit pair
+__device__ __forceinline__ void acc8_add(Acc8& a, const uint4& w) {
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a.v[2 * i] += __uint_as_float(u[i] << 16);
+        a.v[2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(u[i] << 16);
+        f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 w;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+    w.x = *reinterpret_cast<uint32_t*>(&p0); w.y = *reinterpret_cast<uint32_t*>(&p1);
+    w.z = *reinterpret_cast<uint32_t*>(&p2); w.w = *reinterpret_cast<uint32_t*>(&p3);
+    return w;
+}
 
 template <typename T>
 __device__ __forceinline__ void stage_rows(T* __restrict__ dst, const T* __restrict__ src, int rows, int ld_src,
                                            int width, int tid, int nthreads) {
     const int vec_per_row = width * (int)sizeof(T) / 16;
     const int total = rows * vec_per_row;
-    for (int i = tid; i < total; i += nthreads) {
-        const int r = i / vec_per_row, v = i % vec_per_row;
-        reinterpret_cast<uint4*>(dst + (size_t)r * width)[v] =
-            __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld_src) + v);
+    constexpr int U = 8;                                    // independent 16-byte loads in flight per thread
+    for (int i0 = tid; i0 < total; i0 += U * nthreads) {
+        uint4 a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nthreads;
+            if (i < total) a[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(i / vec_per_row) * ld_src) + i % vec_per_row);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nthreads;
+            if (i < total) reinterpret_cast<uint4*>(dst + (size_t)(i / vec_per_row) * width)[i % vec_per_row] = a[u];
+        }
     }
 }
 
-// clause side: tables LIT[n][2 halves][W] and SP[n][2 halves][W] of the chain's slice
-template <int VS, typename T>
+// clause side: tables LIT[2n][W] and SP[2n][W] of the chain's slice (row = literal code 2*var+sign)
+template <int W>
 __global__ void __launch_bounds__(1024)
 clause_gather_smem_kernel(UnitGraphDev g, int Q,
-                          const T* __restrict__ LIT, int ld_lit,
-                          const T* __restrict__ SP, int ld_sp, int sp_off,
-                          T* __restrict__ OUT, int ld_out, int out_off) {
-    constexpr int W = 32 * VS;
+                          const __nv_bfloat16* __restrict__ LIT, int ld_lit,
+                          const __nv_bfloat16* __restrict__ SP, int ld_sp, int sp_off,
+                          __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off) {
+    using T = __nv_bfloat16;
+    constexpr int LPR = W / 8, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
-    T* t_lit = reinterpret_cast<T*>(gsm);                       // [2n][W]  row = 2*var + sign
+    T* t_lit = reinterpret_cast<T*>(gsm);
     T* t_sp = t_lit + (size_t)2 * g.n * W;
     const int chain = blockIdx.x, slice = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
     const size_t vbase = (size_t)chain * g.n;
-    // positive half-rows then negative half-rows interleaved as literal codes: stage each sign separately
-    for (int sgn = 0; sgn < 2; ++sgn) {
-        // rows of sign `sgn` land at t[(2*v + sgn) * W]: stage with an output stride of 2*W
-        const int vec_per_row = W * (int)sizeof(T) / 16;
-        for (int i = tid; i < g.n * vec_per_row; i += blockDim.x) {
-            const int v = i / vec_per_row, k = i % vec_per_row;
-            reinterpret_cast<uint4*>(t_lit + (size_t)(2 * v + sgn) * W)[k] =
-                __ldg(reinterpret_cast<const uint4*>(LIT + (vbase + v) * ld_lit + sgn * Q + slice * W) + k);
-            reinterpret_cast<uint4*>(t_sp + (size_t)(2 * v + sgn) * W)[k] =
-                __ldg(reinterpret_cast<const uint4*>(SP + (vbase + v) * ld_sp + sp_off + sgn * Q + slice * W) + k);
+    {   // stage both tables: 4 independent 16-byte loads per table in flight per thread
+        const int total = 2 * g.n * LPR;                    // (variable, sign, 16-byte piece)
+        constexpr int U = 4;
+        for (int i0 = tid; i0 < total; i0 += U * blockDim.x) {
+            uint4 a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const int code = i / LPR, k = i % LPR, v = code >> 1, sgn = code & 1;
+                    a[u] = __ldg(reinterpret_cast<const uint4*>(LIT + (vbase + v) * ld_lit + sgn * Q + slice * W) + k);
+                    b[u] = __ldg(reinterpret_cast<const uint4*>(SP + (vbase + v) * ld_sp + sp_off + sgn * Q + slice * W) + k);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const int code = i / LPR, k = i % LPR;
+                    reinterpret_cast<uint4*>(t_lit + (size_t)code * W)[k] = a[u];
+                    reinterpret_cast<uint4*>(t_sp + (size_t)code * W)[k] = b[u];
+                }
+            }
         }
     }
     __syncthreads();
-    for (int j = warp; j < g.m; j += nwarps) {
-        const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
-        LaneVec<VS> acc_l, acc_s;
-#pragma unroll
-        for (int i = 0; i < VS; ++i) { acc_l.v[i] = 0.f; acc_s.v[i] = 0.f; }
+    for (int j0 = warp * RPW; j0 < g.m; j0 += nwarps * RPW) {
+        const int j = j0 + sub;
+        const bool live = j < g.m;
+        const int e0 = live ? __ldg(g.cl_rowptr + j) : 0, e1 = live ? __ldg(g.cl_rowptr + j + 1) : 0;
+        Acc8 al, as;
+        acc8_zero(al); acc8_zero(as);
         for (int e = e0; e < e1; ++e) {
             const int code = __ldg(g.cl_lit + e);
-            LaneVec<VS> l0 = lane_load_rw_t<VS, T>(t_lit + (size_t)code * W, lane);
-            LaneVec<VS> s0 = lane_load_rw_t<VS, T>(t_sp + (size_t)code * W, lane);
-#pragma unroll
-            for (int i = 0; i < VS; ++i) { acc_l.v[i] += l0.v[i]; acc_s.v[i] += s0.v[i]; }
+            acc8_add(al, reinterpret_cast<const uint4*>(t_lit + (size_t)code * W)[li]);
+            acc8_add(as, reinterpret_cast<const uint4*>(t_sp + (size_t)code * W)[li]);
         }
-        const float rw = __ldg(g.rev_w + j);
+        if (live) {
+            const float rw = __ldg(g.rev_w + j);
+            float ol[8], os[8];
 #pragma unroll
-        for (int i = 0; i < VS; ++i) {
-            acc_l.v[i] *= rw;
-            acc_s.v[i] = 4.0f * __expf(-acc_s.v[i]);
+            for (int i = 0; i < 8; ++i) { ol[i] = al.v[i] * rw; os[i] = 4.0f * __expf(-as.v[i]); }
+            T* dst = OUT + ((size_t)chain * g.m + j) * ld_out + out_off + slice * W;
+            reinterpret_cast<uint4*>(dst)[li] = pack8(ol);
+            reinterpret_cast<uint4*>(dst + Q)[li] = pack8(os);
         }
-        T* dst = OUT + ((size_t)chain * g.m + j) * ld_out + out_off + slice * W;
-        lane_store_t<VS, T>(dst, lane, acc_l);
-        lane_store_t<VS, T>(dst + Q, lane, acc_s);
     }
 }
 
 // literal side: tables CL4[m][W] and MSG[m][W] of the chain's slice
-template <int VS, typename T>
+template <int W>
 __global__ void __launch_bounds__(1024)
 literal_gather_smem_kernel(UnitGraphDev g, int Q,
-                           const T* __restrict__ CL4, int ld_cl, int cl_off,
-                           const T* __restrict__ MSG, int ld_msg,
-                           const T* __restrict__ QRY, int ld_q,
-                           T* __restrict__ OUT, int ld_out, int out_off) {
-    constexpr int W = 32 * VS;
+                           const __nv_bfloat16* __restrict__ CL4, int ld_cl, int cl_off,
+                           const __nv_bfloat16* __restrict__ MSG, int ld_msg,
+                           const __nv_bfloat16* __restrict__ QRY, int ld_q,
+                           __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off) {
+    using T = __nv_bfloat16;
+    constexpr int LPR = W / 8, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
-    T* t_cl = reinterpret_cast<T*>(gsm);                        // [m][W]
+    T* t_cl = reinterpret_cast<T*>(gsm);
     T* t_ms = t_cl + (size_t)g.m * W;
     const int chain = blockIdx.x, slice = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
     const size_t cbase = (size_t)chain * g.m;
     stage_rows<T>(t_cl, CL4 + cbase * ld_cl + cl_off + slice * W, g.m, ld_cl, W, tid, blockDim.x);
     stage_rows<T>(t_ms, MSG + cbase * ld_msg + slice * W, g.m, ld_msg, W, tid, blockDim.x);
     __syncthreads();
-    for (int v = warp; v < g.n; v += nwarps) {
-        LaneVec<VS> s4[2], ms[2];
+    for (int v0 = warp * RPW; v0 < g.n; v0 += nwarps * RPW) {
+        const int v = v0 + sub;
+        const bool live = v < g.n;
+        Acc8 s4[2], ms[2];
 #pragma unroll
         for (int sgn = 0; sgn < 2; ++sgn) {
-#pragma unroll
-            for (int i = 0; i < VS; ++i) { s4[sgn].v[i] = 0.f; ms[sgn].v[i] = 0.f; }
+            acc8_zero(s4[sgn]); acc8_zero(ms[sgn]);
             const int code = 2 * v + sgn;
-            const int e0 = __ldg(g.lit_rowptr + code), e1 = __ldg(g.lit_rowptr + code + 1);
+            const int e0 = live ? __ldg(g.lit_rowptr + code) : 0, e1 = live ? __ldg(g.lit_rowptr + code + 1) : 0;
             for (int e = e0; e < e1; ++e) {
                 const int j = __ldg(g.lit_clause + e);
-                LaneVec<VS> a0 = lane_load_rw_t<VS, T>(t_cl + (size_t)j * W, lane);
-                LaneVec<VS> b0 = lane_load_rw_t<VS, T>(t_ms + (size_t)j * W, lane);
-#pragma unroll
-                for (int i = 0; i < VS; ++i) { s4[sgn].v[i] += a0.v[i]; ms[sgn].v[i] += b0.v[i]; }
+                acc8_add(s4[sgn], reinterpret_cast<const uint4*>(t_cl + (size_t)j * W)[li]);
+                acc8_add(ms[sgn], reinterpret_cast<const uint4*>(t_ms + (size_t)j * W)[li]);
             }
         }
-        const size_t row = (size_t)chain * g.n + v;
-        LaneVec<VS> q = lane_load_t<VS, T>(QRY + row * ld_q + slice * W, lane);
-        const float vw = __ldg(g.vdeg_w + v);
-        const float dwp = __ldg(g.deg_w + 2 * v), dwn = __ldg(g.deg_w + 2 * v + 1);
-        LaneVec<VS> grad;
+        if (live) {
+            const size_t row = (size_t)chain * g.n + v;
+            float q[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(QRY + row * ld_q + slice * W) + li), q);
+            const float vw = __ldg(g.vdeg_w + v);
+            const float dwp = __ldg(g.deg_w + 2 * v), dwn = __ldg(g.deg_w + 2 * v + 1);
+            float grad[8], lp[8], ln[8];
 #pragma unroll
-        for (int i = 0; i < VS; ++i) {
-            const float sg = 1.0f / (1.0f + __expf(-q.v[i]));
-            grad.v[i] = (-sg * s4[0].v[i] + (1.0f - sg) * s4[1].v[i]) * vw;
-            ms[0].v[i] *= dwp;
-            ms[1].v[i] *= dwn;
+            for (int i = 0; i < 8; ++i) {
+                const float sg = 1.0f / (1.0f + __expf(-q[i]));
+                grad[i] = (-sg * s4[0].v[i] + (1.0f - sg) * s4[1].v[i]) * vw;
+                lp[i] = ms[0].v[i] * dwp;
+                ln[i] = ms[1].v[i] * dwn;
+            }
+            T* dst = OUT + row * ld_out + out_off + slice * W;
+            reinterpret_cast<uint4*>(dst)[li] = pack8(grad);
+            reinterpret_cast<uint4*>(dst + Q)[li] = pack8(lp);
+            reinterpret_cast<uint4*>(dst + 2 * Q)[li] = pack8(ln);
         }
-        T* dst = OUT + row * ld_out + out_off + slice * W;
-        lane_store_t<VS, T>(dst, lane, grad);
-        lane_store_t<VS, T>(dst + Q, lane, ms[0]);
-        lane_store_t<VS, T>(dst + 2 * Q, lane, ms[1]);
     }
 }
 
