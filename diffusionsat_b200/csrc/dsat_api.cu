@@ -17,6 +17,7 @@
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
 #include "dsat_mlp_fused.cuh"
+#include "dsat_mlp_pair.cuh"
 #include "dsat_message_tma.cuh"
 #endif
 
@@ -113,6 +114,7 @@ struct dsat_ctx {
     fm::FusedMlp fused[5];
     bool fused_ready = false;
     bool use_fused = true;
+    bool use_pair = false;            // cta_group::2 whole-MLP kernels (DSAT_MLP_PAIR=1)
     bool use_smem_gather = true;
     // TMA-staged persistent gathers (dsat_message_tma.cuh)
     CUtensorMap map_g_lit, map_g_sp, map_g_cl, map_g_ms;
@@ -275,9 +277,12 @@ int ensure_tc_buffers(dsat_ctx* c) {
                 f.p.layer[i].K = K; f.p.layer[i].N = l.n; f.p.layer[i].epi = l.epi; f.p.layer[i].bias = l.b;
                 f.p.layer[i].box_rows = l.n < 256 ? l.n : 256;
                 if (!tc::make_bf16_map(&f.map_w[i], l.w, l.n, K64, K64, f.p.layer[i].box_rows)) return false;
+                if (!tc::make_bf16_map(&f.map_wp[i], l.w, l.n, K64, K64, f.p.layer[i].box_rows / 2)) return false;
                 ++i;
             }
-            return fm::plan_fused(f);
+            if (!fm::plan_fused(f)) return false;
+            f.pair_ok = fm2::pair_supported(f) && f.pp.slots >= 2;
+            return true;
         };
         auto W = [&](int op) { return (const __nv_bfloat16*)c->ops[op].w_bf16.p; };
         auto B = [&](int op) { return (const float*)c->ops[op].b.p; };
@@ -497,7 +502,15 @@ int run_linear_tc(dsat_ctx* c, int op, long long rows, int epi, void* p0, int ld
 #ifdef DSAT_WITH_TCGEN05
 int run_fused(dsat_ctx* c, int which, int prof_class) {
     prof_mark(c, prof_class);
-    CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
+    if (c->use_pair && c->fused[which].pair_ok) {
+        fm::FusedMlp g = c->fused[which];
+        g.p = g.pp;
+        g.smem_bytes = g.smem_bytes_pair;
+        for (int l = 0; l < fm::MAX_LAYERS; ++l) g.map_w[l] = g.map_wp[l];
+        CK_CUDA(c, fm2::launch_fused_pair(g, c->sm_count, c->stream));
+    } else {
+        CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
+    }
     c->launches++;
     return DSAT_OK;
 }
@@ -856,6 +869,8 @@ int dsat_create(int device, dsat_ctx** out) {
     {   // A/B switches for measurements: DSAT_FUSED_MLP=0, DSAT_SMEM_GATHER=0
         const char* e = getenv("DSAT_FUSED_MLP");
         if (e && e[0] == '0') c->use_fused = false;
+        e = getenv("DSAT_MLP_PAIR");
+        if (e) c->use_pair = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
         if (e && e[0] == '0') c->use_smem_gather = false;
         e = getenv("DSAT_TMA_GATHER");

@@ -27,7 +27,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int THREADS = 192;
 constexpr int MAX_LAYERS = 3;
-constexpr int MAX_SLOTS = 4;
+constexpr int MAX_SLOTS = 8;
 constexpr int AH_BLOCK_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB: 128 rows x 64 bf16
 constexpr int TMEM_COLS = 512;
 constexpr int STAGE_ROW = 128 + 16;                        // bytes per staged row (one 32-column fp32 chunk + pad)
@@ -303,6 +303,11 @@ struct FusedMlp {
     CUtensorMap map_w[MAX_LAYERS];
     FmParams p;
     int smem_bytes;
+    // CTA-pair variant (dsat_mlp_pair.cuh): weight maps with half-height boxes, its own ring plan
+    CUtensorMap map_wp[MAX_LAYERS];
+    FmParams pp;
+    int smem_bytes_pair;
+    bool pair_ok;
 };
 
 // shared-memory plan; returns false when the MLP does not fit
@@ -321,10 +326,20 @@ inline bool plan_fused(FusedMlp& f) {
     p.ah_blocks = blocks;
     p.slot_bytes = (max_box * BLOCK_K * 2 + 1023) / 1024 * 1024;
     p.n_tiles = ceil_div(p.rows, BLOCK_M);
+    // pair variant: each CTA holds half of every weight block, so slots are half as large
+    f.pp = p;
+    f.pp.slot_bytes = (max_box / 2 * BLOCK_K * 2 + 1023) / 1024 * 1024;
+    f.pp.slots = 0;
+    for (int slots = MAX_SLOTS; slots >= 2; --slots) {
+        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * f.pp.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 4;
+        if (total <= SMEM_LIMIT) { f.pp.slots = slots; f.smem_bytes_pair = total; break; }
+    }
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
         const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 4;
         if (total <= SMEM_LIMIT) {
             p.slots = slots;
+            f.pp.ah_blocks = p.ah_blocks; f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs;
+            for (int l = 0; l < p.n_layers; ++l) f.pp.layer[l].bias_off = p.layer[l].bias_off;
             f.smem_bytes = total;
             return true;
         }
