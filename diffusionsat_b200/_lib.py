@@ -50,6 +50,7 @@ _SIGNATURES = {
     "dsat_words_per_graph": (C.c_int, [_vp]),
     "dsat_spmm": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int]),
     "dsat_profile_classes": (C.c_int, []),
+    "dsat_profile_fused": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_longlong)]),
     "dsat_profile_rounds": (C.c_int, [_vp, C.c_int, C.c_uint64, _f32p, _i32p]),
     "dsat_tc_linear_test": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_int, _f32p]),
     "dsat_debug_begin": (C.c_int, [_vp, C.c_float, _f32p, _i32p]),
@@ -256,6 +257,11 @@ class Context:
         self._check(self._lib.dsat_profile_rounds(self._h, int(rounds), C.c_uint64(seed), _ptr(ms, C.c_float),
                                                   _ptr(cnt, C.c_int32)))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(self.PROFILE_CLASSES[:k])}
+
+    def profile_fused(self, which):
+        arr = (C.c_longlong * 16)()
+        self._check(self._lib.dsat_profile_fused(self._h, int(which), arr))
+        return list(arr)
 
     def tc_linear_test(self, a, w, bias, epi=0, out_bf16=False):
         """Run the tcgen05 linear kernel alone on host arrays (a [rows,K], w [K,N], bias [N])."""

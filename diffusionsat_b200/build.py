@@ -11,8 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libdsat.so")
 SOURCES = ["dsat_api.cu"]
-HEADERS = ["dsat_common.cuh", "dsat_gemm_simt.cuh", "dsat_gemm_tc.cuh", "dsat_message.cuh", "dsat_norm_head.cuh",
-           os.path.join("..", "..", "include", "dsat.h")]
+
+
+def _headers():
+    found = [f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    return found + [os.path.join("..", "..", "include", "dsat.h")]
 
 
 def _nvcc() -> str:
@@ -26,7 +29,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + _headers()]
     return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
 
 

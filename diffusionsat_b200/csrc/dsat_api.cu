@@ -270,6 +270,7 @@ int ensure_tc_buffers(dsat_ctx* c) {
             f.p.rows = (int)(a_op == OP_C1 ? c->Mt : c->Nt);
             f.p.a_box_rows = c->a_box_rows[a_op];
             f.p.qmaps = Q;
+            f.p.prof = nullptr;
             f.p.out = out;
             int i = 0;
             for (const L& l : layers) {
@@ -1207,6 +1208,32 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
 }
 
 // --------------------------------------------------------------------------------------- profile
+// Cycle breakdown of CTA 0 of one whole-MLP kernel (0 query, 1 literal, 2 clause, 3 update, 4 output): 16 counters,
+// see dsat_mlp_fused.cuh.  The activations must have been produced by a previous round.
+int dsat_profile_fused(dsat_ctx* c, int which, long long* counters16) {
+    if (!c || !counters16 || which < 0 || which > 4) return DSAT_ERR_ARG;
+#ifndef DSAT_WITH_TCGEN05
+    return DSAT_ERR_UNSUPPORTED;
+#else
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_tc_buffers(c);
+    if (rc) return rc;
+    CK_ARG(c, c->fused_ready, "fused kernels unavailable");
+    DevBuf<long long> d;
+    CK_CUDA(c, d.alloc(16));
+    CK_CUDA(c, cudaMemsetAsync(d.p, 0, 16 * sizeof(long long), c->stream));
+    fm::FusedMlp f = c->fused[which];
+    f.p.prof = d.p;
+    cudaError_t e = fm::launch_fused(f, c->sm_count, c->stream);
+    c->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = dsat_memcpy_sync(counters16, d.p, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    d.release();
+    CK_CUDA(c, e);
+    return DSAT_OK;
+#endif
+}
+
 int dsat_profile_classes(void) { return PROF_CLASSES; }
 
 int dsat_profile_rounds(dsat_ctx* c, int rounds, uint64_t seed, float* class_ms, int32_t* class_launches) {

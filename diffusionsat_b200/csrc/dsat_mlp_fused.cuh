@@ -25,7 +25,8 @@ using tc::TcOut;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;                 // 2 + 4 warps (pair kernel); the single-CTA kernel runs 2 + epi_warps warps
+constexpr int MAX_THREADS = 320;
 constexpr int MAX_LAYERS = 3;
 constexpr int MAX_SLOTS = 8;
 constexpr int AH_BLOCK_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB: 128 rows x 64 bf16
@@ -47,11 +48,172 @@ struct FmParams {
     int n_layers;
     FmLayer layer[MAX_LAYERS];
     int rows, n_tiles, a_box_rows, ah_blocks, slots, slot_bytes, two_bufs, qmaps;
+    int stage_row;         // bytes per staged output row: 80 when every output is bf16 (64 B + pad), else 144
+    int bias_total;        // floats in the shared bias array (a bf16 copy follows it)
+    int epi_warps;         // 4 or 8 epilogue warps: with 8, two warps share a TMEM lane quadrant and alternate 32-column chunks
     TcOut out;
+    long long* prof;       // optional [16] cycle counters of CTA 0 (wait/work breakdown), nullptr = off
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+#define DSAT_TIMED_WAIT(acc, call)                 \
+    do {                                           \
+        if (timing) {                              \
+            const long long t0__ = clock64();      \
+            call;                                  \
+            acc += clock64() - t0__;               \
+        } else {                                   \
+            call;                                  \
+        }                                          \
+    } while (0)
+
+// ---- explicit shared-space accesses and split TMEM load / wait (software pipelining of the epilogue)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    // volatile keeps the order relative to the (volatile) fences and barrier operations; no "memory" clobber, so the
+    // compiler does not have to re-load every memory-resident value after each store
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void tmem_ld_32cols_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// wait for the outstanding tcgen05.ld; the registers are in/out operands so that no use is scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 pack;
+    pack.x = *reinterpret_cast<uint32_t*>(&p0); pack.y = *reinterpret_cast<uint32_t*>(&p1);
+    pack.z = *reinterpret_cast<uint32_t*>(&p2); pack.w = *reinterpret_cast<uint32_t*>(&p3);
+    return pack;
+}
+
+// bias (+ leaky relu) of one 32-column chunk; the 32 biases come in as eight 16-byte shared loads
+__device__ __forceinline__ void bias_act_chunk(const uint32_t (&raw)[32], uint32_t bias_addr, bool lrelu, float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b = lds128f(bias_addr + 16 * q);
+        const float x0 = __uint_as_float(raw[4 * q]) + b.x, x1 = __uint_as_float(raw[4 * q + 1]) + b.y;
+        const float x2 = __uint_as_float(raw[4 * q + 2]) + b.z, x3 = __uint_as_float(raw[4 * q + 3]) + b.w;
+        v[4 * q] = lrelu ? fmaxf(x0, 0.2f * x0) : x0;
+        v[4 * q + 1] = lrelu ? fmaxf(x1, 0.2f * x1) : x1;
+        v[4 * q + 2] = lrelu ? fmaxf(x2, 0.2f * x2) : x2;
+        v[4 * q + 3] = lrelu ? fmaxf(x3, 0.2f * x3) : x3;
+    }
+}
+
+// bf16 outputs: round the fp32 accumulator to bf16 pairs first, then bias add and leaky relu on packed pairs
+// (HADD2/HMUL2/HMNMX2.BF16): 2.3x fewer instructions per chunk than the fp32 version; the result is stored as
+// bf16 either way.  32 bf16 biases = four 16-byte shared loads.
+__device__ __forceinline__ void bias_act_chunk_bf16(const uint32_t (&raw)[32], uint32_t bias_b_addr, bool lrelu, uint4 (&out)[4]) {
+    const __nv_bfloat162 slope = __floats2bfloat162_rn(0.2f, 0.2f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 b = lds128(bias_b_addr + 16 * q);
+        const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(raw[8 * q + 2 * i]), __uint_as_float(raw[8 * q + 2 * i + 1]));
+            x = __hadd2(x, *reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+            if (lrelu) x = __hmax2(x, __hmul2(x, slope));
+            ow[i] = *reinterpret_cast<uint32_t*>(&x);
+        }
+        out[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// packed variant of store_chunk_fast for bf16 outputs
+__device__ __forceinline__ void store_chunk_packed(uint32_t stage_addr, int stage_row, int lane, const uint4 (&w)[4], int valid,
+                                                   uint8_t* gbase, size_t row_pitch_bytes, size_t row_first,
+                                                   int rows_left, int col) {
+    const uint32_t mine = stage_addr + lane * stage_row;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sts128(mine + 16 * q, w[q]);
+    __syncwarp();
+    const int valid_pieces = valid / 8;
+    uint4 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int pidx = lane + 32 * k;
+        t[k] = lds128(stage_addr + (pidx >> 2) * stage_row + 16 * (pidx & 3));
+    }
+    uint8_t* g0 = gbase + row_first * row_pitch_bytes + (size_t)col * 2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int pidx = lane + 32 * k;
+        const int rr = pidx >> 2, piece = pidx & 3;
+        if (rr < rows_left && piece < valid_pieces)
+            *reinterpret_cast<uint4*>(g0 + (size_t)rr * row_pitch_bytes + 16 * piece) = t[k];
+    }
+    __syncwarp();
+}
+
+// one 32-column chunk of one output row per lane -> global memory through a per-warp transpose buffer (explicit
+// shared-space accesses: the generic-pointer version stalled every store on a generic load)
+template <bool BF16>
+__device__ __forceinline__ void store_chunk_fast(uint32_t stage_addr, int stage_row, int lane, const float (&v)[32], int valid,
+                                                 uint8_t* gbase, size_t row_pitch_bytes, size_t row_first,
+                                                 int rows_left, int col) {
+    const uint32_t mine = stage_addr + lane * stage_row;
+    if (BF16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sts128(mine + 16 * q, pack8_bf16(&v[8 * q]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint4 w;
+            w.x = __float_as_uint(v[4 * q]); w.y = __float_as_uint(v[4 * q + 1]);
+            w.z = __float_as_uint(v[4 * q + 2]); w.w = __float_as_uint(v[4 * q + 3]);
+            sts128(mine + 16 * q, w);
+        }
+    }
+    __syncwarp();
+    constexpr int ES = BF16 ? 2 : 4;
+    constexpr int PIECES = BF16 ? 4 : 8;
+    const int valid_pieces = valid * ES / 16;
+    uint4 t[PIECES];
+#pragma unroll
+    for (int k = 0; k < PIECES; ++k) {
+        const int pidx = lane + 32 * k;
+        t[k] = lds128(stage_addr + (pidx / PIECES) * stage_row + 16 * (pidx % PIECES));
+    }
+    uint8_t* g0 = gbase + row_first * row_pitch_bytes + (size_t)col * ES;
+#pragma unroll
+    for (int k = 0; k < PIECES; ++k) {
+        const int pidx = lane + 32 * k;
+        const int rr = pidx / PIECES, piece = pidx % PIECES;
+        if (rr < rows_left && piece < valid_pieces)
+            *reinterpret_cast<uint4*>(g0 + (size_t)rr * row_pitch_bytes + 16 * piece) = t[k];
+    }
+    __syncwarp();
 }
 
 // one 32-column chunk of one output row per lane -> global memory through a per-warp transpose buffer
@@ -90,7 +252,84 @@ __device__ __forceinline__ void store_chunk_coalesced(uint8_t* stage, int lane, 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+
+struct EpiCtx {           // loop-invariant scalars of one (tile, layer) epilogue, all in registers
+    uint32_t lane_addr, ah_addr, bl_addr, blb_addr, stage_addr;
+    int N, epi, cpar, cstep, r, lane, qmaps, stage_row;
+    size_t row_first; int rows_left;
+    void* ptr0; void* ptr1; int ld0, ld1, bf0, bf1, split;
+};
+
+template <bool HIDDEN>
+__device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&raw)[32], int c) {
+    const bool lrelu = e.epi == tc::TC_LRELU;
+    if (HIDDEN) {
+        // K-major SWIZZLE_128B: 16-byte chunk j of row r of block kb sits at kb*16KB + r*128 + ((j ^ (r & 7)) << 4)
+        uint4 w[4];
+        bias_act_chunk_bf16(raw, e.blb_addr + 2u * (uint32_t)c, lrelu, w);
+        const uint32_t blk = e.ah_addr + (uint32_t)(c >> 6) * AH_BLOCK_BYTES + (uint32_t)e.r * 128;
+        const int j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (c + 8 * q < e.N) sts128(blk + (uint32_t)(((j0 + q) ^ (e.r & 7)) << 4), w[q]);
+        return;
+    }
+    const bool second = e.ptr1 != nullptr && c >= e.split;
+    uint8_t* gbase = reinterpret_cast<uint8_t*>(second ? e.ptr1 : e.ptr0);
+    const int is_bf16 = second ? e.bf1 : e.bf0;
+    const size_t pitch = (size_t)(second ? e.ld1 : e.ld0) * (is_bf16 ? 2 : 4);
+    const int cc = second ? c - e.split : c;
+    const int valid = min(32, e.N - c);
+    if (is_bf16 && e.epi != tc::TC_QUERY) {
+        uint4 w[4];
+        bias_act_chunk_bf16(raw, e.blb_addr + 2u * (uint32_t)c, lrelu, w);
+        store_chunk_packed(e.stage_addr, e.stage_row, e.lane, w, valid, gbase, pitch, e.row_first, e.rows_left, cc);
+        return;
+    }
+    float v[32];
+    bias_act_chunk(raw, e.bl_addr + 4u * (uint32_t)c, lrelu, v);
+    if (is_bf16) store_chunk_fast<true>(e.stage_addr, e.stage_row, e.lane, v, valid, gbase, pitch, e.row_first, e.rows_left, cc);
+    else store_chunk_fast<false>(e.stage_addr, e.stage_row, e.lane, v, valid, gbase, pitch, e.row_first, e.rows_left, cc);
+    if (e.epi == tc::TC_QUERY) {
+        float sp[32], sn[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float t = __logf(1.0f + __expf(-fabsf(v[i])));
+            sp[i] = fmaxf(v[i], 0.f) + t;
+            sn[i] = fmaxf(-v[i], 0.f) + t;
+        }
+        if (is_bf16) {
+            store_chunk_fast<true>(e.stage_addr, e.stage_row, e.lane, sp, valid, gbase, pitch, e.row_first, e.rows_left, cc + e.qmaps);
+            store_chunk_fast<true>(e.stage_addr, e.stage_row, e.lane, sn, valid, gbase, pitch, e.row_first, e.rows_left, cc + 2 * e.qmaps);
+        } else {
+            store_chunk_fast<false>(e.stage_addr, e.stage_row, e.lane, sp, valid, gbase, pitch, e.row_first, e.rows_left, cc + e.qmaps);
+            store_chunk_fast<false>(e.stage_addr, e.stage_row, e.lane, sn, valid, gbase, pitch, e.row_first, e.rows_left, cc + 2 * e.qmaps);
+        }
+    }
+}
+
+// Drain one accumulator: software pipeline, the tcgen05.ld of the next chunk is in flight while this one is
+// processed.  For the last layer the accumulator is handed back (tmem_empty) as soon as this warp's last TMEM
+// read has landed; for hidden layers the caller arrives after the shared-memory stores are fenced.
+template <bool HIDDEN>
+__device__ __forceinline__ void epi_drain(const EpiCtx& e, uint64_t* tmem_empty_bar) {
+    bool released = false;
+#pragma unroll 1
+    for (int c = 32 * e.cpar; c < e.N; c += e.cstep) {
+        uint32_t ra[32];
+        tmem_ld_32cols_async(e.lane_addr + (uint32_t)c, ra);
+        tmem_ld_wait(ra);
+        if (!HIDDEN && c + e.cstep >= e.N) {     // last TMEM read of this warp: hand the accumulator back early
+            tc::tcgen05_fence_before();
+            mbar_arrive(tmem_empty_bar);
+            released = true;
+        }
+        epi_process<HIDDEN>(e, ra, c);
+    }
+    if (!HIDDEN && !released) { tc::tcgen05_fence_before(); mbar_arrive(tmem_empty_bar); }
+}
+
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w0,
                  const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, FmParams p) {
     using namespace tc;
@@ -99,7 +338,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t* ah = smem;
     uint8_t* ring = smem + (size_t)p.ah_blocks * AH_BLOCK_BYTES;
     uint8_t* stage_all = ring + (size_t)p.slots * p.slot_bytes;
-    uint8_t* tail = stage_all + STAGE_BYTES;
+    uint8_t* tail = stage_all + (size_t)p.epi_warps * 32 * p.stage_row;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* ah_free = a_full + 1;
     uint64_t* h_full = a_full + 2;
@@ -111,13 +350,17 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     float* bias_s = reinterpret_cast<float*>(tail + BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int epi_threads = 32 * p.epi_warps;
     const CUtensorMap* map_w[MAX_LAYERS] = {&map_w0, &map_w1, &map_w2};
+    const bool timing = p.prof != nullptr && blockIdx.x == 0;
+    const long long t_kernel0 = timing ? clock64() : 0;
+    long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         mbar_init(ah_free, 1);
-        mbar_init(h_full, 128);
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+        mbar_init(h_full, epi_threads);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], epi_threads); }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -131,8 +374,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     if (warp >= 2) {
         for (int l = 0; l < p.n_layers; ++l)
-            for (int i = threadIdx.x - 64; i < p.layer[l].N; i += 128)
-                bias_s[p.layer[l].bias_off + i] = __ldg(p.layer[l].bias + i);
+            for (int i = threadIdx.x - 64; i < p.layer[l].N; i += epi_threads) {
+                const float b = __ldg(p.layer[l].bias + i);
+                bias_s[p.layer[l].bias_off + i] = b;
+                reinterpret_cast<__nv_bfloat16*>(bias_s + p.bias_total)[p.layer[l].bias_off + i] = __float2bfloat16_rn(b);
+            }
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -146,7 +392,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             int slot = 0; uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                if (it > 0) mbar_wait(ah_free, (uint32_t)((it - 1) & 1));       // tile it-1 no longer reads AH
+                if (it > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((it - 1) & 1)));   // tile it-1 no longer reads AH
                 mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
                 for (int kb = 0; kb < k0_blocks; ++kb)
                     tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
@@ -155,7 +401,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int halves = (p.layer[l].N + 255) / 256;
                     for (int kb = 0; kb < kbs; ++kb)
                         for (int h = 0; h < halves; ++h) {
-                            mbar_wait(&ring_empty[slot], phase ^ 1);
+                            DSAT_TIMED_WAIT(w1, mbar_wait(&ring_empty[slot], phase ^ 1));
                             mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[l].box_rows * (BLOCK_K * 2));
                             tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K, h * 256);
                             if (++slot == p.slots) { slot = 0; phase ^= 1; }
@@ -171,9 +417,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 for (int l = 0; l < n_layers; ++l, ++g) {
                     const int buf = p.two_bufs ? (g & 1) : 0;
                     const int use = p.two_bufs ? (g >> 1) : g;
-                    mbar_wait(&tmem_empty[buf], (uint32_t)((use & 1) ^ 1));     // accumulator drained (first use passes)
-                    if (l == 0) mbar_wait(a_full, (uint32_t)(it & 1));
-                    else { mbar_wait(h_full, (uint32_t)(hcount & 1)); ++hcount; }
+                    DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_empty[buf], (uint32_t)((use & 1) ^ 1)));   // accumulator drained
+                    if (l == 0) DSAT_TIMED_WAIT(w1, mbar_wait(a_full, (uint32_t)(it & 1)));
+                    else { DSAT_TIMED_WAIT(w2, mbar_wait(h_full, (uint32_t)(hcount & 1))); ++hcount; }
                     tcgen05_fence_after();
                     const int K = p.layer[l].K, N = p.layer[l].N;
                     const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
@@ -185,13 +431,16 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int h = 0; h < halves; ++h) {
                             const int bn = min(256, N - h * 256);
                             const uint32_t idesc = make_idesc_bf16(BLOCK_M, bn);
-                            mbar_wait(&ring_full[slot], phase);
+                            DSAT_TIMED_WAIT(w3, mbar_wait(&ring_full[slot], phase));
                             tcgen05_fence_after();
                             const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
+                            const long long t_i0 = timing ? clock64() : 0;
                             for (int k = 0; k < ksteps; ++k)
                                 umma_bf16(acc + (uint32_t)(h * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                           (kb | k) != 0);
+                            const long long t_i1 = timing ? clock64() : 0;
                             tcgen05_commit(&ring_empty[slot]);
+                            if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
                             if (++slot == p.slots) { slot = 0; phase ^= 1; }
                         }
                     }
@@ -200,97 +449,57 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 }
             }
         }
-    } else {               // ================================ epilogue warps 2..5
+    } else {               // ================================ epilogue warps (4 or 8)
         const int quad = warp & 3;
-        const int r = quad * 32 + lane;                    // row inside the tile = TMEM lane
-        uint8_t* stage = stage_all + (warp - 2) * (32 * STAGE_ROW);
+        EpiCtx e;
+        e.r = quad * 32 + lane;                            // row inside the tile = TMEM lane
+        e.lane = lane;
+        e.cpar = (warp - 2) >> 2;                          // which 32-column chunks of the quadrant this warp takes
+        e.cstep = 32 * (p.epi_warps >> 2);
+        e.stage_row = p.stage_row;
+        e.stage_addr = smem_u32(stage_all) + (uint32_t)(warp - 2) * (32 * p.stage_row);
+        e.ah_addr = smem_u32(ah);
+        e.qmaps = p.qmaps;
+        e.ptr0 = p.out.ptr0; e.ptr1 = p.out.ptr1; e.ld0 = p.out.ld0; e.ld1 = p.out.ld1;
+        e.bf0 = p.out.bf16_0; e.bf1 = p.out.bf16_1; e.split = p.out.split;
+        const uint32_t bias_addr0 = smem_u32(bias_s);
         int g = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int row0 = tile * BLOCK_M;
+            e.row_first = (size_t)tile * BLOCK_M + quad * 32;
+            e.rows_left = p.rows - (int)e.row_first;
             for (int l = 0; l < n_layers; ++l, ++g) {
                 const int buf = p.two_bufs ? (g & 1) : 0;
                 const int use = p.two_bufs ? (g >> 1) : g;
-                const int N = p.layer[l].N, epi = p.layer[l].epi;
-                const float* bl = bias_s + p.layer[l].bias_off;
-                const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
-                mbar_wait(&tmem_full[buf], (uint32_t)(use & 1));
+                e.N = p.layer[l].N; e.epi = p.layer[l].epi;
+                e.bl_addr = bias_addr0 + 4u * (uint32_t)p.layer[l].bias_off;
+                e.blb_addr = bias_addr0 + 4u * (uint32_t)p.bias_total + 2u * (uint32_t)p.layer[l].bias_off;
+                e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
+                DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_full[buf], (uint32_t)(use & 1)));
                 tcgen05_fence_after();
+                const long long t_epi0 = timing ? clock64() : 0;
                 if (l + 1 < n_layers) {
-                    // hidden activations -> AH region, K-major SWIZZLE_128B: 16-byte chunk j of row r of block kb
-                    // sits at kb*16KB + r*128 + ((j ^ (r & 7)) << 4)
-                    for (int c = 0; c < N; c += 32) {
-                        uint32_t raw[32];
-                        tmem_ld_32cols(lane_addr + (uint32_t)c, raw);
-                        uint8_t* blk = ah + (size_t)(c >> 6) * AH_BLOCK_BYTES + (size_t)r * 128;
-                        const int j0 = (c & 63) >> 3;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            if (c + 8 * q < N) {
-                                float v[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const float x = __uint_as_float(raw[8 * q + e]) + bl[c + 8 * q + e];
-                                    v[e] = (epi == TC_LRELU) ? (x > 0.f ? x : 0.2f * x) : x;
-                                }
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-                                uint4 pack;
-                                pack.x = *reinterpret_cast<uint32_t*>(&p0); pack.y = *reinterpret_cast<uint32_t*>(&p1);
-                                pack.z = *reinterpret_cast<uint32_t*>(&p2); pack.w = *reinterpret_cast<uint32_t*>(&p3);
-                                *reinterpret_cast<uint4*>(blk + (((j0 + q) ^ (r & 7)) << 4)) = pack;
-                            }
-                        }
-                    }
+                    epi_drain<true>(e, &tmem_empty[buf]);
                     tcgen05_fence_before();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the MMA (async proxy)
                     mbar_arrive(&tmem_empty[buf]);
                     mbar_arrive(h_full);
+                    if (timing) w1 += clock64() - t_epi0;
                 } else {
-                    const bool split = p.out.ptr1 != nullptr;
-                    const size_t row_first = (size_t)row0 + quad * 32;
-                    const int rows_left = p.rows - (int)row_first;          // rows of this warp that exist (may be <= 0)
-                    for (int c = 0; c < N; c += 32) {
-                        uint32_t raw[32];
-                        tmem_ld_32cols(lane_addr + (uint32_t)c, raw);
-                        if (c + 32 >= N) {                  // last TMEM read of this accumulator: hand it back early
-                            tcgen05_fence_before();
-                            mbar_arrive(&tmem_empty[buf]);
-                        }
-                        float v[32];
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const float x = __uint_as_float(raw[e]) + ((c + e < N) ? bl[c + e] : 0.f);
-                            v[e] = (epi == TC_LRELU) ? (x > 0.f ? x : 0.2f * x) : x;
-                        }
-                        const bool second = split && c >= p.out.split;
-                        uint8_t* gbase = reinterpret_cast<uint8_t*>(second ? p.out.ptr1 : p.out.ptr0);
-                        const int is_bf16 = second ? p.out.bf16_1 : p.out.bf16_0;
-                        const size_t pitch = (size_t)(second ? p.out.ld1 : p.out.ld0) * (is_bf16 ? 2 : 4);
-                        const int cc = second ? c - p.out.split : c;
-                        const int valid = min(32, N - c);
-                        if (is_bf16) store_chunk_coalesced<true>(stage, lane, v, valid, gbase, pitch, row_first, rows_left, cc);
-                        else store_chunk_coalesced<false>(stage, lane, v, valid, gbase, pitch, row_first, rows_left, cc);
-                        if (epi == TC_QUERY) {
-                            float sp[32], sn[32];
-#pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const float t = __logf(1.0f + __expf(-fabsf(v[e])));
-                                sp[e] = fmaxf(v[e], 0.f) + t;
-                                sn[e] = fmaxf(-v[e], 0.f) + t;
-                            }
-                            if (is_bf16) {
-                                store_chunk_coalesced<true>(stage, lane, sp, valid, gbase, pitch, row_first, rows_left, cc + p.qmaps);
-                                store_chunk_coalesced<true>(stage, lane, sn, valid, gbase, pitch, row_first, rows_left, cc + 2 * p.qmaps);
-                            } else {
-                                store_chunk_coalesced<false>(stage, lane, sp, valid, gbase, pitch, row_first, rows_left, cc + p.qmaps);
-                                store_chunk_coalesced<false>(stage, lane, sn, valid, gbase, pitch, row_first, rows_left, cc + 2 * p.qmaps);
-                            }
-                        }
-                    }
+                    epi_drain<false>(e, &tmem_empty[buf]);
+                    if (timing) w2 += clock64() - t_epi0;
                 }
             }
         }
     }
+    if (timing && lane == 0 && (warp == 0 || warp == 1 || warp == 2)) {
+        // [0] kernel cycles; producer: [1] ah_free wait [2] ring_empty wait; MMA: [3] tmem_empty wait [4] a_full wait
+        // [5] h_full wait [6] ring_full wait; epilogue warp 2: [7] tmem_full wait [8] hidden epilogues [9] final epilogues
+        const long long total = clock64() - t_kernel0;
+        if (warp == 0) { p.prof[0] = total; p.prof[1] = w0; p.prof[2] = w1; }
+        if (warp == 1) { p.prof[3] = w0; p.prof[4] = w1; p.prof[5] = w2; p.prof[6] = w3; p.prof[10] = total; p.prof[12] = w4; p.prof[13] = w5; }
+        if (warp == 2) { p.prof[7] = w0; p.prof[8] = w1; p.prof[9] = w2; p.prof[11] = total; p.prof[14] = w3; p.prof[15] = w4; }
+    }
+    (void)w4; (void)w5;
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
@@ -324,6 +533,7 @@ inline bool plan_fused(FusedMlp& f) {
         if (p.layer[l].N > 256) p.two_bufs = 0;
     }
     p.ah_blocks = blocks;
+    p.bias_total = bias_total;
     p.slot_bytes = (max_box * BLOCK_K * 2 + 1023) / 1024 * 1024;
     p.n_tiles = ceil_div(p.rows, BLOCK_M);
     // pair variant: each CTA holds half of every weight block, so slots are half as large
@@ -331,11 +541,24 @@ inline bool plan_fused(FusedMlp& f) {
     f.pp.slot_bytes = (max_box / 2 * BLOCK_K * 2 + 1023) / 1024 * 1024;
     f.pp.slots = 0;
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * f.pp.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 4;
+        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * f.pp.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 6;
         if (total <= SMEM_LIMIT) { f.pp.slots = slots; f.smem_bytes_pair = total; break; }
     }
+    {
+        const FmLayer& last = p.layer[p.n_layers - 1];
+        const bool all_bf16 = p.out.bf16_0 && (p.out.ptr1 == nullptr || p.out.bf16_1) && last.epi != tc::TC_QUERY;
+        p.stage_row = all_bf16 ? 80 : STAGE_ROW;
+    }
+    p.epi_warps = 4;
+    for (int ew : {8, 4}) {     // prefer 8 epilogue warps when two ring slots still fit
+        if (1024 + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 6 <= SMEM_LIMIT) {
+            p.epi_warps = ew;
+            break;
+        }
+    }
+    f.pp.epi_warps = 4;
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 4;
+        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + p.epi_warps * 32 * p.stage_row + BAR_BYTES + bias_total * 6;
         if (total <= SMEM_LIMIT) {
             p.slots = slots;
             f.pp.ah_blocks = p.ah_blocks; f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs;
@@ -356,7 +579,7 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         configured = true;
     }
     const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
-    fused_mlp_kernel<<<grid, THREADS, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1],
+    fused_mlp_kernel<<<grid, 64 + 32 * f.p.epi_warps, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1],
                                                                f.map_w[f.p.n_layers > 2 ? 2 : 1], f.p);
     return cudaGetLastError();
 }

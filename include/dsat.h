@@ -134,6 +134,8 @@ int dsat_spmm(dsat_ctx* ctx, int direction, const void* x_dev, void* y_dev, int 
  * clause gather, literal gather, clause PairNorm, variable PairNorm, head, noise.
  * class_ms / class_launches have dsat_profile_classes() entries. */
 int dsat_profile_classes(void);
+/* clock64 wait/work breakdown of CTA 0 of one whole-MLP kernel (0 query .. 4 output); 16 counters */
+int dsat_profile_fused(dsat_ctx* ctx, int which, long long* counters16);
 int dsat_profile_rounds(dsat_ctx* ctx, int rounds, uint64_t seed, float* class_ms, int32_t* class_launches);
 
 /* Stand-alone run of the tcgen05 linear kernel on host data (parity of the tensor-core MLP path,
