@@ -132,17 +132,18 @@ __device__ __forceinline__ void bias_act_chunk(const uint32_t (&raw)[32], uint32
 // bf16 outputs: round the fp32 accumulator to bf16 pairs first, then bias add and leaky relu on packed pairs
 // (HADD2/HMUL2/HMNMX2.BF16): 2.3x fewer instructions per chunk than the fp32 version; the result is stored as
 // bf16 either way.  32 bf16 biases = four 16-byte shared loads.
-__device__ __forceinline__ void bias_act_chunk_bf16(const uint32_t (&raw)[32], uint32_t bias_b_addr, bool lrelu, uint4 (&out)[4]) {
+__device__ __forceinline__ void bias_act_chunk_bf16(const uint32_t (&raw)[32], uint32_t bias_f_addr, bool lrelu, uint4 (&out)[4]) {
+    // bias add in fp32 (one rounding to bf16, as on the per-layer path), leaky relu on packed bf16 pairs
     const __nv_bfloat162 slope = __floats2bfloat162_rn(0.2f, 0.2f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint4 b = lds128(bias_b_addr + 16 * q);
-        const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+        const float4 b0 = lds128f(bias_f_addr + 32 * q), b1 = lds128f(bias_f_addr + 32 * q + 16);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         uint32_t ow[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(raw[8 * q + 2 * i]), __uint_as_float(raw[8 * q + 2 * i + 1]));
-            x = __hadd2(x, *reinterpret_cast<const __nv_bfloat162*>(&bw[i]));
+            __nv_bfloat162 x = __floats2bfloat162_rn(__uint_as_float(raw[8 * q + 2 * i]) + bb[2 * i],
+                                                     __uint_as_float(raw[8 * q + 2 * i + 1]) + bb[2 * i + 1]);
             if (lrelu) x = __hmax2(x, __hmul2(x, slope));
             ow[i] = *reinterpret_cast<uint32_t*>(&x);
         }
@@ -266,7 +267,7 @@ __device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&ra
     if (HIDDEN) {
         // K-major SWIZZLE_128B: 16-byte chunk j of row r of block kb sits at kb*16KB + r*128 + ((j ^ (r & 7)) << 4)
         uint4 w[4];
-        bias_act_chunk_bf16(raw, e.blb_addr + 2u * (uint32_t)c, lrelu, w);
+        bias_act_chunk_bf16(raw, e.bl_addr + 4u * (uint32_t)c, lrelu, w);
         const uint32_t blk = e.ah_addr + (uint32_t)(c >> 6) * AH_BLOCK_BYTES + (uint32_t)e.r * 128;
         const int j0 = (c & 63) >> 3;
 #pragma unroll
@@ -282,7 +283,7 @@ __device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&ra
     const int valid = min(32, e.N - c);
     if (is_bf16 && e.epi != tc::TC_QUERY) {
         uint4 w[4];
-        bias_act_chunk_bf16(raw, e.blb_addr + 2u * (uint32_t)c, lrelu, w);
+        bias_act_chunk_bf16(raw, e.bl_addr + 4u * (uint32_t)c, lrelu, w);
         store_chunk_packed(e.stage_addr, e.stage_row, e.lane, w, valid, gbase, pitch, e.row_first, e.rows_left, cc);
         return;
     }

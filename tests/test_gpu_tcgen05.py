@@ -101,4 +101,4 @@ def test_fused_mlp_kernels_match_per_layer_kernels(ctx):
             ctx.debug_round(r, noise["normals"][r])
         out[name] = (ctx.debug_read("LOGITS").copy(), ctx.debug_read("SPRE").copy(), ctx.debug_read("CROW")[:, :128].copy())
     for a, b in zip(out["fused"], out["per_layer"]):
-        assert H.rel_err(a, b) < 2e-2      # bias add in packed bf16 on the fused path, fp32 on the per-layer path
+        assert H.rel_err(a, b) < 5e-2      # two bf16 realisations (leaky relu on packed bf16 pairs vs fp32); same bound as against the oracle
