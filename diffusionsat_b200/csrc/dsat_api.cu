@@ -520,13 +520,17 @@ int run_fused(dsat_ctx* c, int which, int prof_class) {
 #ifdef DSAT_WITH_TCGEN05
 // Shared-memory staged gathers (small formulas): pick the widest feature slice whose two tables fit;
 // returns false when they do not fit (the L2-gather kernels run instead).
-static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out) {
-    const int widths[2] = {128, 64};
-    for (int pass = 0; pass < 2; ++pass)                 // first try to leave room for two CTAs per SM
+static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int budget_kb) {
+    // budget_kb: shared memory per CTA we aim for (smaller slices -> more co-resident CTAs, so one CTA's staging
+    // overlaps the others' compute); DSAT_GATHER_KB overrides it for experiments
+    static const int env_kb = getenv("DSAT_GATHER_KB") ? atoi(getenv("DSAT_GATHER_KB")) : 0;
+    if (env_kb > 0) budget_kb = env_kb;
+    const int widths[3] = {128, 64, 32};
+    for (int pass = 0; pass < 2; ++pass)
         for (int w : widths) {
             if (w > Q || Q % w) continue;
             const size_t bytes = 2 * table_rows * (size_t)w * 2;
-            if (bytes <= (pass == 0 ? 112u * 1024u : 220u * 1024u)) { *bytes_out = bytes; return w; }
+            if (bytes <= (size_t)(pass == 0 ? budget_kb : 220) * 1024u) { *bytes_out = bytes; return w; }
         }
     return 0;
 }
@@ -558,7 +562,7 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     }
     if (c->n_graphs != 1 || !c->use_smem_gather) return false;
     size_t bytes = 0;
-    const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes);
+    const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes, 56);    // measured best at cfg2: 4 CTAs per SM
     if (!w) return false;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
     using T = __nv_bfloat16;
@@ -568,10 +572,15 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
         if (!ok) return false;
         clause_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
                                                                           c->CROWb.p, c->ldc(), c->F);
-    } else {
+    } else if (w == 64) {
         static bool ok = set_dyn_smem(clause_gather_smem_kernel<64>);
         if (!ok) return false;
         clause_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
+                                                                          c->CROWb.p, c->ldc(), c->F);
+    } else {
+        static bool ok = set_dyn_smem(clause_gather_smem_kernel<32>);
+        if (!ok) return false;
+        clause_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
                                                                           c->CROWb.p, c->ldc(), c->F);
     }
     return true;
@@ -602,7 +611,7 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     }
     if (c->n_graphs != 1 || !c->use_smem_gather) return false;
     size_t bytes = 0;
-    const int w = pick_slice_width((size_t)c->m, c->Q, &bytes);
+    const int w = pick_slice_width((size_t)c->m, c->Q, &bytes, 112);
     if (!w) return false;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
     using T = __nv_bfloat16;
@@ -612,10 +621,15 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
         if (!ok) return false;
         literal_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
                                                                            c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
-    } else {
+    } else if (w == 64) {
         static bool ok = set_dyn_smem(literal_gather_smem_kernel<64>);
         if (!ok) return false;
         literal_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
+                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
+    } else {
+        static bool ok = set_dyn_smem(literal_gather_smem_kernel<32>);
+        if (!ok) return false;
+        literal_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
                                                                            c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
     }
     return true;
