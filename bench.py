@@ -303,6 +303,17 @@ def run_ours(args):
                 "flops_per_launch": flops / max(gemm_launches, 1),
                 "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items()}}
     working_set_gb = (ctx.n_rows * 3500 + ctx.n_clause_rows * 850) * (4 if precision == "fp32" else 2) / 1e9
+    # the two in-model message-passing kernels at the bench configuration: compulsory bytes / event time
+    es = 4 if precision == "fp32" else 2
+    q = 128
+    nnz = unit.nnz
+    cg_bytes = ctx.n_rows * 4 * q * es + ctx.n_clause_rows * 2 * q * es + (nnz + unit.n_clauses + 1) * 4
+    lg_bytes = ctx.n_clause_rows * 2 * q * es + ctx.n_rows * q * es + ctx.n_rows * 3 * q * es + (nnz + 2 * unit.n_vars + 1) * 4
+    in_model = {}
+    for name, nbytes in (("clause_gather", cg_bytes), ("literal_gather", lg_bytes)):
+        ms_launch = prof[name][0] / max(prof[name][1], 1)
+        in_model[name] = {"gbs": nbytes / ms_launch / 1e6, "frac": nbytes / ms_launch / 1e6 / pk["hbm_gbs"],
+                          "ms": ms_launch, "bytes": nbytes}
     message_pass = None if args.skip_message_pass else message_pass_roofline(ctx, torch, pk)
 
     cpu = None
@@ -325,7 +336,7 @@ def run_ours(args):
                    "precision": precision},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "message_pass": message_pass,
-        "cpu_baseline": cpu, "sat_rate": sat_rate,
+        "message_pass_in_model": in_model, "cpu_baseline": cpu, "sat_rate": sat_rate,
     }
     print(json.dumps(line))
     if world > 1:
