@@ -94,6 +94,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(precision):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if precision != "bf16" or not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh)["fused_mlp_kernel"]["dram_bytes_per_launch"]
+
+
 def formula():
     from diffusionsat_b200 import synth
     return synth.random_3sat(N_VARS, seed=SEED_FORMULA)          # m = int(4.258 n + 58.26 n^(-2/3)) = 428
@@ -296,7 +305,7 @@ def run_ours(args):
     achieved_tf = flops / (gemm_ms / 1e3) / 1e12
     peak_tf = pk["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                "frac": achieved_tf / peak_tf, "traffic": ncu_traffic(precision), "peak_source": pk["source"] + " bf16 sustained",
                 "kernel": "sgemm128_kernel (fp32 CUDA cores)" if precision == "fp32"
                           else "fused_mlp_kernel (tcgen05 bf16, one persistent launch per MLP, 5 per round)",
                 "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_round": gemm_ms / total_ms,

@@ -1007,7 +1007,14 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     }
     CK_CUDA(c, cudaSetDevice(c->device));
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
-    release_buffers(c);
+    // same shape as before (the usual case: the same formula re-bound, or another formula of the same size):
+    // keep the activation buffers and their TMA descriptors, only the index arrays are replaced
+    const int total_graphs_new = n_graphs * n_chains;
+    const int group_new = group_graphs > 0 ? group_graphs : total_graphs_new;
+    const bool same_shape = c->has_graph && c->n == n_vars && c->m == n_clauses && c->n_graphs == n_graphs &&
+                            c->chains == n_chains && c->words == ceil_div(max_graph_vars, 64) &&
+                            c->n_groups == ceil_div(total_graphs_new, group_new);
+    if (!same_shape) release_buffers(c);
     c->n = n_vars; c->m = n_clauses; c->nnz = nnz; c->n_graphs = n_graphs; c->chains = n_chains;
     c->total_graphs = n_graphs * n_chains;
     c->group_graphs = group_graphs > 0 ? group_graphs : c->total_graphs;

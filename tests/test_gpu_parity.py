@@ -279,3 +279,42 @@ def test_cuda_diffusion_matches_reference_source(ctx, tag):
     got = unpack_assignments(packed, c["n_vars"])
     want = [O.encode_assignment(c["predictions"][i * c["n_vars"]:(i + 1) * c["n_vars"]]) for i in range(c["chains"])]
     assert got == want
+
+
+def test_uniformity_statistic_comparable_to_oracle(ctx):
+    """Sample histogram of the CUDA path vs the oracle's on a formula with 14 models (reference
+    utils/test_AllSolutions.py): same Philox noise spec on both sides, so the histograms agree up to rare
+    rounding-boundary flips, and so do their chi-square statistics against the uniform distribution
+    (reference utils/chi_square.py, diffusion_metrics.py:137)."""
+    from diffusionsat_b200.sampler import unpack_assignments
+    from diffusionsat_b200.uniformity import chi_square_vs_ideal
+    n_vars, clauses = 5, [[-1, 2], [1, -2], [-3, 4, 5]]
+    chains, steps, rounds, seed = 1500, 6, 3, 11
+    wts = H.make_weights(seed=6)
+    bind(ctx, n_vars, clauses, chains, wts, group=chains)
+    packed, is_sat, _, _ = ctx.sample(steps, rounds, seed=seed)
+    got = {}
+    for v, s in zip(unpack_assignments(packed, n_vars), is_sat):
+        if s:
+            got[v] = got.get(v, 0) + 1
+    # oracle with the identical noise streams (host restatement of the device Philox)
+    elems = np.arange(chains * n_vars)
+    uniforms = np.stack([philox.uniforms(seed, elems, t) for t in range(steps)])
+    labels = np.stack([philox.labels(seed, elems, t) for t in range(steps)])
+    normals = np.stack([np.stack([philox.normals(seed, elems, t, r) for r in range(rounds)]) for t in range(steps)])
+    graph = O.OracleGraph.copies(n_vars, clauses, chains)
+    _, final, _ = O.diffusion(steps, graph, O.weights_to_torch(wts), torch.from_numpy(uniforms),
+                              torch.from_numpy(labels.astype(np.int64)), torch.from_numpy(normals), rounds)
+    want = {}
+    for c in range(chains):
+        bits = final[c * n_vars:(c + 1) * n_vars]
+        if O._satisfiable_py([bool(b) for b in bits], clauses):
+            k = O.encode_assignment(bits)
+            want[k] = want.get(k, 0) + 1
+    models = synth.enumerate_solutions(n_vars, clauses)
+    assert set(got) <= set(models) and set(want) <= set(models)
+    differing = sum(abs(got.get(k, 0) - want.get(k, 0)) for k in models)
+    assert differing <= 0.02 * chains                      # chains that flipped on a rounding boundary
+    chi_g, _ = chi_square_vs_ideal(got, models)
+    chi_o, _ = chi_square_vs_ideal(want, models)
+    assert abs(chi_g - chi_o) <= 0.1 * max(chi_o, 1.0) + 5.0
