@@ -116,6 +116,12 @@ struct dsat_ctx {
     bool use_fused = true;
     bool use_pair = false;            // cta_group::2 whole-MLP kernels (DSAT_MLP_PAIR=1)
     bool use_smem_gather = true;
+    // panel layout of the clause-side intermediates on the fused bf16 path (contiguous gather tables):
+    // CL4P / VMSGP [Q/64][M][64] (4*clauses_loss, message to literals), CNEWb [M, F] (new clause value)
+    DevBuf<__nv_bfloat16> CL4P, VMSGP, CNEWb;
+    fm::FusedMlp fused_clause_panel;
+    bool panel_ready = false;
+    bool use_panels = false;          // measured +0.6 % at cfg2 only: opt-in (DSAT_PANELS=1)
     // TMA-staged persistent gathers (dsat_message_tma.cuh)
     CUtensorMap map_g_lit, map_g_sp, map_g_cl, map_g_ms;
     tg::GatherPlan gp_clause, gp_literal;
@@ -207,6 +213,8 @@ int ensure_buffers(dsat_ctx* c) {
 }
 
 #ifdef DSAT_WITH_TCGEN05
+static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int budget_kb);
+
 __global__ void mirror_cols_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
                                    long long rows, int cols) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,6 +315,29 @@ int ensure_tc_buffers(dsat_ctx* c) {
         ok = ok && build(FO, OP_O1, {{OP_O1, c->HO, W(OP_O1), B(OP_O1), tc::TC_LRELU},
                                      {OP_O2, DSAT_LOGIT_PAD, W(OP_O2), B(OP_O2), tc::TC_LINEAR}}, o);
         c->fused_ready = ok;
+        for (int i = 0; i < 5; ++i) { c->fused[i].map_a2 = c->fused[i].map_a; c->fused[i].p.a_split_kb = 1 << 20;
+                                      c->fused[i].p.a2_panel_rows = 0; c->fused[i].p.out0_panel_rows = 0;
+                                      c->fused[i].pp.a_split_kb = 1 << 20; c->fused[i].pp.out0_panel_rows = 0; }
+        // panel variant of the clause MLP: needs 64-wide slices on both smem gathers (see pick_slice_width)
+        c->panel_ready = false;
+        size_t b1 = 0, b2 = 0;
+        if (ok && c->n_graphs == 1 && Q == 128 && F % 64 == 0 &&
+            pick_slice_width((size_t)2 * c->n, Q, &b1, 56) == 64 && pick_slice_width((size_t)c->m, Q, &b2, 112) == 64) {
+            CK_CUDA(c, c->CL4P.alloc(Mt * Q));
+            CK_CUDA(c, c->VMSGP.alloc(Mt * Q));
+            CK_CUDA(c, c->CNEWb.alloc(Mt * F));
+            fm::FusedMlp& f = c->fused_clause_panel;
+            f = c->fused[FC];
+            f.p.out = {c->VMSGP.p, 64, 1, c->CNEWb.p, F, 1, Q};
+            f.p.out0_panel_rows = c->Mt;
+            f.p.a_split_kb = (F + Q) / 64;
+            f.p.a2_panel_rows = c->Mt;
+            if (tc::make_bf16_map(&f.map_a2, c->CL4P.p, (long long)(Q / 64) * c->Mt, 64, 64, f.p.a_box_rows) && fm::plan_fused(f)) {
+                f.p.a_split_kb = (F + Q) / 64; f.p.a2_panel_rows = c->Mt; f.p.out0_panel_rows = c->Mt;
+                f.pair_ok = false;
+                c->panel_ready = true;
+            }
+        }
     }
     {   // TMA-staged gathers: one formula per chain whose tables fit in shared memory twice
         c->tma_clause_ready = c->tma_literal_ready = false;
@@ -367,7 +398,8 @@ void release_buffers(dsat_ctx* c) {
 #ifdef DSAT_WITH_TCGEN05
     c->VROWb.release(); c->CROWb.release(); c->H1b.release(); c->H2b.release(); c->QSb.release(); c->LITb.release();
     c->CHb.release(); c->COUTb.release(); c->UOUTb.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
-    c->O1b.release();
+    c->O1b.release(); c->CL4P.release(); c->VMSGP.release(); c->CNEWb.release();
+    c->panel_ready = false;
     c->has_tc_buffers = false;
 #endif
     c->has_buffers = false;
@@ -434,6 +466,10 @@ LossScalars loss_scalars(float noise_scale) {
 static inline bool use_tc(const dsat_ctx* c) { return c->precision == DSAT_BF16 || c->precision == DSAT_BF16_UNFUSED; }
 static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p : nullptr; }
 static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : nullptr; }
+static inline bool panel_now(const dsat_ctx* c) {
+    return c->precision == DSAT_BF16 && c->fused_ready && c->use_fused && c->panel_ready && c->use_panels &&
+           c->use_smem_gather && !c->use_tma_gather && !c->use_pair;
+}
 #else
 static inline bool use_tc(const dsat_ctx*) { return false; }
 static inline __nv_bfloat16* vrow_b(dsat_ctx*) { return nullptr; }
@@ -509,6 +545,8 @@ int run_fused(dsat_ctx* c, int which, int prof_class) {
         g.smem_bytes = g.smem_bytes_pair;
         for (int l = 0; l < fm::MAX_LAYERS; ++l) g.map_w[l] = g.map_wp[l];
         CK_CUDA(c, fm2::launch_fused_pair(g, c->sm_count, c->stream));
+    } else if (which == 2 && panel_now(c)) {
+        CK_CUDA(c, fm::launch_fused(c->fused_clause_panel, c->sm_count, c->stream));
     } else {
         CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
     }
@@ -564,6 +602,7 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     size_t bytes = 0;
     const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes, 56);    // measured best at cfg2: 4 CTAs per SM
     if (!w) return false;
+    __nv_bfloat16* cl4p = (panel_now(c) && w == 64) ? c->CL4P.p : nullptr;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
     using T = __nv_bfloat16;
     const int Q = c->Q;
@@ -571,17 +610,17 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
         static bool ok = set_dyn_smem(clause_gather_smem_kernel<128>);
         if (!ok) return false;
         clause_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
-                                                                          c->CROWb.p, c->ldc(), c->F);
+                                                                          c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
     } else if (w == 64) {
         static bool ok = set_dyn_smem(clause_gather_smem_kernel<64>);
         if (!ok) return false;
         clause_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
-                                                                          c->CROWb.p, c->ldc(), c->F);
+                                                                          c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
     } else {
         static bool ok = set_dyn_smem(clause_gather_smem_kernel<32>);
         if (!ok) return false;
         clause_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
-                                                                          c->CROWb.p, c->ldc(), c->F);
+                                                                          c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
     }
     return true;
 }
@@ -613,24 +652,28 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     size_t bytes = 0;
     const int w = pick_slice_width((size_t)c->m, c->Q, &bytes, 112);
     if (!w) return false;
+    const bool pn = panel_now(c) && w == 64;
+    const __nv_bfloat16* cl4_src = pn ? c->CL4P.p : c->CROWb.p;
+    const __nv_bfloat16* msg_src = pn ? c->VMSGP.p : c->COUTb.p;
+    const long long prow = pn ? c->Mt : 0;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
     using T = __nv_bfloat16;
     const int Q = c->Q, F = c->F;
     if (w == 128) {
         static bool ok = set_dyn_smem(literal_gather_smem_kernel<128>);
         if (!ok) return false;
-        literal_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
-                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
+        literal_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F,
+                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD, prow);
     } else if (w == 64) {
         static bool ok = set_dyn_smem(literal_gather_smem_kernel<64>);
         if (!ok) return false;
-        literal_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
-                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
+        literal_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F,
+                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD, prow);
     } else {
         static bool ok = set_dyn_smem(literal_gather_smem_kernel<32>);
         if (!ok) return false;
-        literal_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F,
-                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD);
+        literal_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F,
+                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD, prow);
     }
     return true;
 }
@@ -733,7 +776,8 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
 #ifdef DSAT_WITH_TCGEN05
         else
             pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, PN_WARPS * 32, 0, c->stream>>>(
-                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUTb.p, Q + F, Q, c->CROWb.p, ldc, nullptr, 0);
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, panel_now(c) ? c->CNEWb.p : c->COUTb.p,
+                panel_now(c) ? F : Q + F, panel_now(c) ? 0 : Q, c->CROWb.p, ldc, nullptr, 0);
 #endif
     });
     if (rc) return rc;
@@ -886,6 +930,8 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e && e[0] == '0') c->use_fused = false;
         e = getenv("DSAT_MLP_PAIR");
         if (e) c->use_pair = e[0] != '0';
+        e = getenv("DSAT_PANELS");
+        if (e) c->use_panels = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
         if (e && e[0] == '0') c->use_smem_gather = false;
         e = getenv("DSAT_TMA_GATHER");

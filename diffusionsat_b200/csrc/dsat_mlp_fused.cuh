@@ -48,6 +48,9 @@ struct FmParams {
     int n_layers;
     FmLayer layer[MAX_LAYERS];
     int rows, n_tiles, a_box_rows, ah_blocks, slots, slot_bytes, two_bufs, qmaps;
+    int a_split_kb;        // k-blocks >= a_split_kb of the INPUT tile come from map_a2 (panel-major source), 1<<20 = never
+    long long a2_panel_rows;  // rows per 64-column panel of that source
+    long long out0_panel_rows;   // > 0: output columns [0, split) go to 64-column panels of this many rows (bf16)
     int stage_row;         // bytes per staged output row: 80 when every output is bf16 (64 B + pad), else 144
     int bias_total;        // floats in the shared bias array (a bf16 copy follows it)
     int epi_warps;         // 4 or 8 epilogue warps: with 8, two warps share a TMEM lane quadrant and alternate 32-column chunks
@@ -259,6 +262,7 @@ struct EpiCtx {           // loop-invariant scalars of one (tile, layer) epilogu
     int N, epi, cpar, cstep, r, lane, qmaps, stage_row;
     size_t row_first; int rows_left;
     void* ptr0; void* ptr1; int ld0, ld1, bf0, bf1, split;
+    long long out0_panel_rows;
 };
 
 template <bool HIDDEN>
@@ -278,8 +282,13 @@ __device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&ra
     const bool second = e.ptr1 != nullptr && c >= e.split;
     uint8_t* gbase = reinterpret_cast<uint8_t*>(second ? e.ptr1 : e.ptr0);
     const int is_bf16 = second ? e.bf1 : e.bf0;
-    const size_t pitch = (size_t)(second ? e.ld1 : e.ld0) * (is_bf16 ? 2 : 4);
-    const int cc = second ? c - e.split : c;
+    size_t pitch = (size_t)(second ? e.ld1 : e.ld0) * (is_bf16 ? 2 : 4);
+    int cc = second ? c - e.split : c;
+    if (!second && e.out0_panel_rows > 0) {     // panel-major bf16 output: 64-column panels of dense 128-byte rows
+        gbase += (size_t)(c >> 6) * (size_t)e.out0_panel_rows * 128;
+        pitch = 128;
+        cc = c & 63;
+    }
     const int valid = min(32, e.N - c);
     if (is_bf16 && e.epi != tc::TC_QUERY) {
         uint4 w[4];
@@ -331,8 +340,9 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint64_t* tmem_empty_
 }
 
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w0,
-                 const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, FmParams p) {
+fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                 const __grid_constant__ CUtensorMap map_w2, FmParams p) {
     using namespace tc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -396,7 +406,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (it > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((it - 1) & 1)));   // tile it-1 no longer reads AH
                 mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
                 for (int kb = 0; kb < k0_blocks; ++kb)
-                    tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
+                    if (kb < p.a_split_kb)
+                        tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
+                    else     // panel-major source: panel (kb - a_split_kb) is a dense [rows, 64] matrix
+                        tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a2, a_full, 0,
+                                    (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
                 for (int l = 0; l < n_layers; ++l) {
                     const int kbs = (p.layer[l].K + BLOCK_K - 1) / BLOCK_K;
                     const int halves = (p.layer[l].N + 255) / 256;
@@ -463,6 +477,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         e.qmaps = p.qmaps;
         e.ptr0 = p.out.ptr0; e.ptr1 = p.out.ptr1; e.ld0 = p.out.ld0; e.ld1 = p.out.ld1;
         e.bf0 = p.out.bf16_0; e.bf1 = p.out.bf16_1; e.split = p.out.split;
+        e.out0_panel_rows = p.out0_panel_rows;
         const uint32_t bias_addr0 = smem_u32(bias_s);
         int g = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -510,6 +525,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 struct FusedMlp {
     CUtensorMap map_a;
+    CUtensorMap map_a2;        // optional panel-major second source of the input tile (see FmParams::a_split_kb)
     CUtensorMap map_w[MAX_LAYERS];
     FmParams p;
     int smem_bytes;
@@ -580,7 +596,7 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         configured = true;
     }
     const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
-    fused_mlp_kernel<<<grid, 64 + 32 * f.p.epi_warps, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1],
+    fused_mlp_kernel<<<grid, 64 + 32 * f.p.epi_warps, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1],
                                                                f.map_w[f.p.n_layers > 2 ? 2 : 1], f.p);
     return cudaGetLastError();
 }
