@@ -91,3 +91,23 @@ def merge_histograms(keys: np.ndarray, counts: np.ndarray, n_bits: int, device=N
         return None
     total = dense.cpu().numpy()
     return {k: int(c) for k, c in zip(keys_to_ints(table, n_bits), total[:table.shape[0]]) if c > 0}
+
+
+def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_chains: int, n_bits: int,
+                          steps: int = 32, rounds: int = 32, seed: int = 0, group=None):
+    """One process per GPU: every rank samples its contiguous block of the `total_chains` global chains
+    (whole reference batches), then the histograms are merged on rank 0.  `make_context(local_rank)` returns a
+    ready `_lib.Context` (model set).  Returns the merged ``{int: count}`` on rank 0, ``None`` elsewhere.
+    The result does not depend on the number of ranks: noise is keyed by the global chain id."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    offset, count = shard_chains(total_chains, world, rank, multiple_of=batch_chains)
+    ctx = make_context(rank)
+    if count > 0:
+        ctx.set_graph(unit_graph, chains=count, group_graphs=batch_chains)
+        packed, is_sat, _, _ = ctx.sample(steps, rounds, seed=seed, chain_offset=offset)
+        keys, counts = local_histogram(packed, is_sat)
+    else:
+        words = -(-n_bits // 64)
+        keys, counts = np.zeros((0, words), dtype=np.uint64), np.zeros(0, dtype=np.int64)
+    return merge_histograms(keys, counts, n_bits, group=group)
