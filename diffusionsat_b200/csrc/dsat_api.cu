@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,8 @@ struct dsat_ctx {
     long long Nt = 0, Mt = 0;
     DevBuf<int> cl_rowptr, cl_lit, lit_rowptr, lit_clause, var_seg, clause_seg;
     DevBuf<float> deg_w, vdeg_w, rev_w;
+    DevBuf<int> cl_order, lit_order;     // locality orders of the output rows for the standalone segment sums
+    bool use_spmm_order = true;
 
     // activations
     bool has_buffers = false;
@@ -930,6 +933,8 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e && e[0] == '0') c->use_fused = false;
         e = getenv("DSAT_MLP_PAIR");
         if (e) c->use_pair = e[0] != '0';
+        e = getenv("DSAT_SPMM_ORDER");
+        if (e) c->use_spmm_order = e[0] != '0';
         e = getenv("DSAT_PANELS");
         if (e) c->use_panels = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
@@ -955,6 +960,7 @@ void dsat_destroy(dsat_ctx* c) {
     }
     c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
     c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release();
+    c->cl_order.release(); c->lit_order.release();
     for (auto& pm : c->prof) cudaEventDestroy(pm.ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1103,6 +1109,24 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     CK_CUDA(c, up_f(c->deg_w, deg_w));
     CK_CUDA(c, up_f(c->vdeg_w, vdeg_w));
     CK_CUDA(c, up_f(c->rev_w, rev_w));
+    {   // rows that share their first gathered row become neighbours: the warps of one CTA then hit L1
+        std::vector<int> ord(n_clauses > 0 ? n_clauses : 1, 0), key(n_clauses > 0 ? n_clauses : 1, 0);
+        for (int j = 0; j < n_clauses; ++j) {
+            ord[j] = j;
+            int mn = 2 * n_vars;
+            for (int e = cl_rowptr[j]; e < cl_rowptr[j + 1]; ++e) mn = cl_lit[e] < mn ? cl_lit[e] : mn;
+            key[j] = mn;
+        }
+        std::stable_sort(ord.begin(), ord.begin() + n_clauses, [&](int a, int b) { return key[a] < key[b]; });
+        CK_CUDA(c, up_i(c->cl_order, ord.data(), (size_t)n_clauses));
+        std::vector<int> lord(2 * n_vars), lkey(2 * n_vars);
+        for (int l = 0; l < 2 * n_vars; ++l) {
+            lord[l] = l;
+            lkey[l] = lit_rowptr[l + 1] > lit_rowptr[l] ? lit_clause[lit_rowptr[l]] : n_clauses;
+        }
+        std::stable_sort(lord.begin(), lord.end(), [&](int a, int b) { return lkey[a] < lkey[b]; });
+        CK_CUDA(c, up_i(c->lit_order, lord.data(), (size_t)2 * n_vars));
+    }
     c->has_graph = true;
     return DSAT_OK;
 }
@@ -1260,14 +1284,15 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
     const int rows_out = direction == 0 ? c->m : 2 * c->n;
     const int rows_in = direction == 0 ? 2 * c->n : c->m;
     const int grid = gather_grid((long long)chains * rows_out, c->sm_count);
+    const int* order = c->use_spmm_order ? (direction == 0 ? c->cl_order.p : c->lit_order.p) : nullptr;
     int rc = dispatch_width(c, feat, [&](auto v) {
         constexpr int V = decltype(v)::value;
         if (dtype == DSAT_BF16)
             spmm_segment_sum_kernel<V, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowptr, colidx, scale, rows_out,
-                                                                                         rows_in, chains, x_dev, y_dev);
+                                                                                         rows_in, chains, x_dev, y_dev, order);
         else
             spmm_segment_sum_kernel<V, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowptr, colidx, scale, rows_out,
-                                                                                          rows_in, chains, x_dev, y_dev);
+                                                                                          rows_in, chains, x_dev, y_dev, order);
     });
     if (rc) return rc;
     LAUNCHED(c);

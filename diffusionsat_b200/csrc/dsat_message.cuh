@@ -166,14 +166,17 @@ template <int V, bool BF16>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
 spmm_segment_sum_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
                         const float* __restrict__ scale, int rows_out, int rows_in, int chains,
-                        const void* __restrict__ Xv, void* __restrict__ Yv) {
+                        const void* __restrict__ Xv, void* __restrict__ Yv, const int* __restrict__ order) {
+    // `order` (optional): processing order of the output rows, chosen on the host so that rows handled by the warps
+    // of one CTA share gathered rows (locality in L1 instead of one L2 read per edge); results are unaffected
     constexpr int F = 32 * V;
     const int lane = threadIdx.x & 31;
     const long long total = (long long)chains * rows_out;
     const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
     const long long stride = (long long)gridDim.x * GATHER_WARPS;
     for (long long w = warp0; w < total; w += stride) {
-        const int c = (int)(w / rows_out), r = (int)(w % rows_out);
+        const int c = (int)(w / rows_out);
+        const int r = order ? __ldg(order + (int)(w % rows_out)) : (int)(w % rows_out);
         const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
         const size_t xbase = (size_t)c * rows_in;
         LaneVec<V> acc;
