@@ -14,6 +14,7 @@
 #include "dsat_common.cuh"
 #include "dsat_gemm_simt.cuh"
 #include "dsat_message.cuh"
+#include "dsat_spmm.cuh"
 #include "dsat_norm_head.cuh"
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
@@ -92,7 +93,7 @@ struct dsat_ctx {
     long long Nt = 0, Mt = 0;
     DevBuf<int> cl_rowptr, cl_lit, lit_rowptr, lit_clause, var_seg, clause_seg;
     DevBuf<float> deg_w, vdeg_w, rev_w;
-    DevBuf<int> cl_order, lit_order;     // locality orders of the output rows for the standalone segment sums
+    DevBuf<int> cl_desc, lit_desc;       // standalone segment sums: two int4 per output row in processing order (dsat_spmm.cuh)
     bool use_spmm_order = true;
 
     // activations
@@ -724,7 +725,8 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     prof_mark(c, PROF_CLAUSE_GATHER);
     rc = dispatch_width(c, Q, [&](auto v) {
         constexpr int V = decltype(v)::value;
-        const int grid = gather_grid(Mt, c->sm_count);
+        const int grid = tcp ? gather_grid(clause_gather_kernel<V, __nv_bfloat16>, Mt, GATHER_WARPS, c->sm_count)
+                             : gather_grid(clause_gather_kernel<V, float>, Mt, GATHER_WARPS, c->sm_count);
         if (!tcp)
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
@@ -756,7 +758,8 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     prof_mark(c, PROF_LITERAL_GATHER);
     rc = dispatch_width(c, Q, [&](auto v) {
         constexpr int V = decltype(v)::value;
-        const int grid = gather_grid(Nt, c->sm_count);
+        const int grid = tcp ? gather_grid(literal_gather_kernel<V, __nv_bfloat16>, Nt, GATHER_WARPS, c->sm_count)
+                             : gather_grid(literal_gather_kernel<V, float>, Nt, GATHER_WARPS, c->sm_count);
         if (!tcp)
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
@@ -960,7 +963,7 @@ void dsat_destroy(dsat_ctx* c) {
     }
     c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
     c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release();
-    c->cl_order.release(); c->lit_order.release();
+    c->cl_desc.release(); c->lit_desc.release();
     for (auto& pm : c->prof) cudaEventDestroy(pm.ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1109,23 +1112,32 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     CK_CUDA(c, up_f(c->deg_w, deg_w));
     CK_CUDA(c, up_f(c->vdeg_w, vdeg_w));
     CK_CUDA(c, up_f(c->rev_w, rev_w));
-    {   // rows that share their first gathered row become neighbours: the warps of one CTA then hit L1
-        std::vector<int> ord(n_clauses > 0 ? n_clauses : 1, 0), key(n_clauses > 0 ? n_clauses : 1, 0);
-        for (int j = 0; j < n_clauses; ++j) {
-            ord[j] = j;
-            int mn = 2 * n_vars;
-            for (int e = cl_rowptr[j]; e < cl_rowptr[j + 1]; ++e) mn = cl_lit[e] < mn ? cl_lit[e] : mn;
-            key[j] = mn;
-        }
-        std::stable_sort(ord.begin(), ord.begin() + n_clauses, [&](int a, int b) { return key[a] < key[b]; });
-        CK_CUDA(c, up_i(c->cl_order, ord.data(), (size_t)n_clauses));
-        std::vector<int> lord(2 * n_vars), lkey(2 * n_vars);
-        for (int l = 0; l < 2 * n_vars; ++l) {
-            lord[l] = l;
-            lkey[l] = lit_rowptr[l + 1] > lit_rowptr[l] ? lit_clause[lit_rowptr[l]] : n_clauses;
-        }
-        std::stable_sort(lord.begin(), lord.end(), [&](int a, int b) { return lkey[a] < lkey[b]; });
-        CK_CUDA(c, up_i(c->lit_order, lord.data(), (size_t)2 * n_vars));
+    {   // processing order of the standalone segment sums: rows that share their first gathered row become
+        // neighbours, so the warps of one CTA hit L1; each row's {index, entry range, scale} is packed into one int4
+        auto pack = [&](int rows, const int* rowptr, const int* col, const std::vector<float>& scale, int none,
+                        DevBuf<int>& dst) -> cudaError_t {
+            std::vector<int> ord(rows > 0 ? rows : 1, 0), key(rows > 0 ? rows : 1, 0);
+            for (int j = 0; j < rows; ++j) {
+                ord[j] = j;
+                int mn = none;
+                for (int e = rowptr[j]; e < rowptr[j + 1]; ++e) mn = col[e] < mn ? col[e] : mn;
+                key[j] = mn;
+            }
+            if (c->use_spmm_order)
+                std::stable_sort(ord.begin(), ord.begin() + rows, [&](int a, int b) { return key[a] < key[b]; });
+            std::vector<int> desc(8 * (size_t)(rows > 0 ? rows : 1), 0);
+            for (int p = 0; p < rows; ++p) {
+                const int j = ord[p], len = rowptr[j + 1] - rowptr[j];
+                int bits;
+                memcpy(&bits, &scale[j], sizeof(int));
+                int* d = &desc[8 * (size_t)p];
+                d[0] = j; d[1] = len; d[2] = bits; d[3] = rowptr[j];
+                for (int k = 0; k < 4; ++k) d[4 + k] = k < len ? col[rowptr[j] + k] : -1;
+            }
+            return up_i(dst, desc.data(), desc.size());
+        };
+        CK_CUDA(c, pack(n_clauses, cl_rowptr, cl_lit, rev_w, 2 * n_vars, c->cl_desc));
+        CK_CUDA(c, pack(2 * n_vars, lit_rowptr, lit_clause, deg_w, n_clauses, c->lit_desc));
     }
     c->has_graph = true;
     return DSAT_OK;
@@ -1278,22 +1290,29 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
     CK_ARG(c, x_dev && y_dev && chains > 0 && (direction == 0 || direction == 1), "dsat_spmm: bad argument");
     CK_ARG(c, dtype == DSAT_F32 || dtype == DSAT_BF16, "dsat_spmm: dtype must be f32 or bf16");
     CK_CUDA(c, cudaSetDevice(c->device));
-    const int* rowptr = direction == 0 ? c->cl_rowptr.p : c->lit_rowptr.p;
+    const int4* rowdesc = reinterpret_cast<const int4*>(direction == 0 ? c->cl_desc.p : c->lit_desc.p);
     const int* colidx = direction == 0 ? c->cl_lit.p : c->lit_clause.p;
-    const float* scale = direction == 0 ? c->rev_w.p : c->deg_w.p;
     const int rows_out = direction == 0 ? c->m : 2 * c->n;
     const int rows_in = direction == 0 ? 2 * c->n : c->m;
-    const int grid = gather_grid((long long)chains * rows_out, c->sm_count);
-    const int* order = c->use_spmm_order ? (direction == 0 ? c->cl_order.p : c->lit_order.p) : nullptr;
-    int rc = dispatch_width(c, feat, [&](auto v) {
-        constexpr int V = decltype(v)::value;
-        if (dtype == DSAT_BF16)
-            spmm_segment_sum_kernel<V, true><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowptr, colidx, scale, rows_out,
-                                                                                         rows_in, chains, x_dev, y_dev, order);
-        else
-            spmm_segment_sum_kernel<V, false><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowptr, colidx, scale, rows_out,
-                                                                                          rows_in, chains, x_dev, y_dev, order);
-    });
+    auto launch = [&](auto kernel, int row_bytes) {
+        const int rows_per_block = GATHER_WARPS * (row_bytes >= 512 ? 1 : 512 / row_bytes);
+        const int grid = gather_grid(kernel, (long long)chains * rows_out, rows_per_block, c->sm_count);
+        kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowdesc, colidx, rows_out, rows_in, chains, x_dev, y_dev);
+    };
+    int rc = DSAT_OK;
+    const int row_bytes = feat * (dtype == DSAT_BF16 ? 2 : 4);
+    if (feat != 64 && feat != 128 && feat != 256) {
+        c->err = "feature width must be 64, 128 or 256";
+        rc = DSAT_ERR_UNSUPPORTED;
+    } else if (dtype == DSAT_BF16) {
+        if (row_bytes == 128) launch(spmm_rows_kernel<128, true>, 128);
+        else if (row_bytes == 256) launch(spmm_rows_kernel<256, true>, 256);
+        else launch(spmm_rows_kernel<512, true>, 512);
+    } else {
+        if (row_bytes == 256) launch(spmm_rows_kernel<256, false>, 256);
+        else if (row_bytes == 512) launch(spmm_rows_kernel<512, false>, 512);
+        else launch(spmm_rows_kernel<1024, false>, 1024);
+    }
     if (rc) return rc;
     LAUNCHED(c);
     return DSAT_OK;

@@ -29,6 +29,27 @@ struct UnitGraphDev {
 
 constexpr int GATHER_WARPS = 8;
 
+// Position of a warp in the flattened (chain, row) space of a grid-stride kernel.  The stride is split into
+// (chains, rows) once, so a step costs two adds and a compare instead of a 64-bit division per row (which made
+// the short-row kernels issue-bound: ~60 % issue-slot use for four memory operations per row).
+struct RowCursor {
+    int c, pos;           // chain, row position inside the chain
+    int step_c, step_pos; // the grid stride, decomposed
+};
+__device__ __forceinline__ RowCursor row_cursor(long long first, long long stride, int rows) {
+    RowCursor k;
+    k.c = (int)(first / rows);
+    k.pos = (int)(first - (long long)k.c * rows);
+    k.step_c = (int)(stride / rows);
+    k.step_pos = (int)(stride - (long long)k.step_c * rows);
+    return k;
+}
+__device__ __forceinline__ void row_cursor_step(RowCursor& k, int rows) {
+    k.c += k.step_c;
+    k.pos += k.step_pos;
+    if (k.pos >= rows) { k.pos -= rows; ++k.c; }
+}
+
 // ------------------------------------------------------------------------------ clause side
 // For clause j of chain c:
 //   cmsg[j] = rev_w[j] * sum_{lit in j} LIT[var(lit)][sign(lit)*Q : +Q]
@@ -43,11 +64,10 @@ clause_gather_kernel(UnitGraphDev g, int chains,
                      T* __restrict__ OUT, int ld_out, int out_off) {
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
-    const long long total = (long long)chains * g.m;
-    const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
-    const long long stride = (long long)gridDim.x * GATHER_WARPS;
-    for (long long w = warp0; w < total; w += stride) {
-        const int c = (int)(w / g.m), j = (int)(w % g.m);
+    RowCursor cur = row_cursor((long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5),
+                               (long long)gridDim.x * GATHER_WARPS, g.m);
+    for (; cur.c < chains; row_cursor_step(cur, g.m)) {
+        const int c = cur.c, j = cur.pos;
         const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
         const size_t vbase = (size_t)c * g.n;
         LaneVec<V> acc_l, acc_s;
@@ -105,11 +125,10 @@ literal_gather_kernel(UnitGraphDev g, int chains,
                       T* __restrict__ OUT, int ld_out, int out_off) {
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
-    const long long total = (long long)chains * g.n;
-    const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
-    const long long stride = (long long)gridDim.x * GATHER_WARPS;
-    for (long long w = warp0; w < total; w += stride) {
-        const int c = (int)(w / g.n), v = (int)(w % g.n);
+    RowCursor cur = row_cursor((long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5),
+                               (long long)gridDim.x * GATHER_WARPS, g.n);
+    for (; cur.c < chains; row_cursor_step(cur, g.n)) {
+        const int c = cur.c, v = cur.pos;
         const size_t cbase = (size_t)c * g.m;
         LaneVec<V> s4[2], ms[2];
 #pragma unroll
@@ -158,68 +177,16 @@ literal_gather_kernel(UnitGraphDev g, int chains,
     }
 }
 
-// --------------------------------------------------------------------- standalone segment sums
-// Y[c, r, :] = scale[r] * sum_{e in row r} X[c, col(e), :]   on caller buffers, fp32 or bf16 storage.
-// dir 0: clause <- literal (X rows are literal codes: [2n, F] per chain, i.e. the [n, 2F] layout);
-// dir 1: literal <- clause (X rows are clauses: [m, F] per chain).
-template <int V, bool BF16>
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
-spmm_segment_sum_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                        const float* __restrict__ scale, int rows_out, int rows_in, int chains,
-                        const void* __restrict__ Xv, void* __restrict__ Yv, const int* __restrict__ order) {
-    // `order` (optional): processing order of the output rows, chosen on the host so that rows handled by the warps
-    // of one CTA share gathered rows (locality in L1 instead of one L2 read per edge); results are unaffected
-    constexpr int F = 32 * V;
-    const int lane = threadIdx.x & 31;
-    const long long total = (long long)chains * rows_out;
-    const long long warp0 = (long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);
-    const long long stride = (long long)gridDim.x * GATHER_WARPS;
-    for (long long w = warp0; w < total; w += stride) {
-        const int c = (int)(w / rows_out);
-        const int r = order ? __ldg(order + (int)(w % rows_out)) : (int)(w % rows_out);
-        const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
-        const size_t xbase = (size_t)c * rows_in;
-        LaneVec<V> acc;
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
-        int e = e0;
-        for (; e + 4 <= e1; e += 4) {
-            size_t i0 = xbase + __ldg(colidx + e), i1 = xbase + __ldg(colidx + e + 1);
-            size_t i2 = xbase + __ldg(colidx + e + 2), i3 = xbase + __ldg(colidx + e + 3);
-            LaneVec<V> x0, x1, x2, x3;
-            if constexpr (BF16) {
-                const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(Xv);
-                x0 = lane_load_bf16<V>(X + i0 * F, lane); x1 = lane_load_bf16<V>(X + i1 * F, lane);
-                x2 = lane_load_bf16<V>(X + i2 * F, lane); x3 = lane_load_bf16<V>(X + i3 * F, lane);
-            } else {
-                const float* X = reinterpret_cast<const float*>(Xv);
-                x0 = lane_load<V>(X + i0 * F, lane); x1 = lane_load<V>(X + i1 * F, lane);
-                x2 = lane_load<V>(X + i2 * F, lane); x3 = lane_load<V>(X + i3 * F, lane);
-            }
-#pragma unroll
-            for (int i = 0; i < V; ++i) acc.v[i] = (((acc.v[i] + x0.v[i]) + x1.v[i]) + x2.v[i]) + x3.v[i];
-        }
-        for (; e < e1; ++e) {
-            size_t i0 = xbase + __ldg(colidx + e);
-            LaneVec<V> x0;
-            if constexpr (BF16) x0 = lane_load_bf16<V>(reinterpret_cast<const __nv_bfloat16*>(Xv) + i0 * F, lane);
-            else x0 = lane_load<V>(reinterpret_cast<const float*>(Xv) + i0 * F, lane);
-#pragma unroll
-            for (int i = 0; i < V; ++i) acc.v[i] += x0.v[i];
-        }
-        const float s = __ldg(scale + r);
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc.v[i] *= s;
-        const size_t yrow = (size_t)c * rows_out + r;
-        if constexpr (BF16) lane_store_bf16<V>(reinterpret_cast<__nv_bfloat16*>(Yv) + yrow * F, lane, acc);
-        else lane_store<V>(reinterpret_cast<float*>(Yv) + yrow * F, lane, acc);
-    }
-}
-
-inline int gather_grid(long long total_rows, int sm_count) {
-    // grid-stride kernels: a multiple of the SM count (8 resident CTAs of 256 threads per SM, 4 waves)
-    long long blocks = (total_rows + GATHER_WARPS - 1) / GATHER_WARPS;
-    const long long cap = (long long)sm_count * 8 * 4;
+// Grid of a grid-stride gather kernel: exactly one resident wave (occupancy x SM count).  More blocks than fit at
+// once would make every later wave sweep all chains again (block b strides over the whole row range), so each
+// chain's gathered table would be fetched from HBM once per wave instead of once (measured 2.7x DRAM reads).
+template <typename Kernel>
+inline int gather_grid(Kernel kernel, long long total_rows, int rows_per_block, int sm_count) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GATHER_WARPS * 32, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    long long blocks = (total_rows + rows_per_block - 1) / rows_per_block;
+    const long long cap = (long long)sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     return (int)(blocks < 1 ? 1 : blocks);
 }
