@@ -44,6 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd += ["-DDSAT_WITH_TCGEN05"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    cmd += os.environ.get("DSAT_NVCC_FLAGS", "").split()      # e.g. -DDSAT_GATHER_TRACE for one-off phase timing
     cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:

@@ -93,8 +93,12 @@ struct dsat_ctx {
     long long Nt = 0, Mt = 0;
     DevBuf<int> cl_rowptr, cl_lit, lit_rowptr, lit_clause, var_seg, clause_seg;
     DevBuf<float> deg_w, vdeg_w, rev_w;
+    DevBuf<int> var_order;               // variables by descending degree (literal-side gather)
+    DevBuf<unsigned short> cl_idx16, lit_idx16;   // 16-bit adjacency blocks for the shared-memory gathers (dsat_message.cuh)
+    int cl_idx16_vecs = 0, lit_idx16_vecs = 0, cl_col_off = 0, lit_col_off = 0, lit_ord_off = 0;
     DevBuf<int> cl_desc, lit_desc;       // standalone segment sums: two int4 per output row in processing order (dsat_spmm.cuh)
     bool use_spmm_order = true;
+    bool use_idx16 = true;               // stage the 16-bit adjacency in the shared-memory gathers (DSAT_IDX16=0 disables)
 
     // activations
     bool has_buffers = false;
@@ -167,6 +171,11 @@ UnitGraphDev graph_view(const dsat_ctx* c) {
     g.lit_rowptr = c->lit_rowptr.p; g.lit_clause = c->lit_clause.p;
     g.var_seg = c->var_seg.p; g.clause_seg = c->clause_seg.p;
     g.deg_w = c->deg_w.p; g.vdeg_w = c->vdeg_w.p; g.rev_w = c->rev_w.p;
+    g.var_order = c->var_order.p;
+    g.cl_idx16 = c->cl_idx16_vecs ? c->cl_idx16.p : nullptr;
+    g.lit_idx16 = c->lit_idx16_vecs ? c->lit_idx16.p : nullptr;
+    g.cl_idx16_vecs = c->cl_idx16_vecs; g.lit_idx16_vecs = c->lit_idx16_vecs;
+    g.cl_col_off = c->cl_col_off; g.lit_col_off = c->lit_col_off; g.lit_ord_off = c->lit_ord_off;
     return g;
 }
 
@@ -577,6 +586,14 @@ static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int bud
     return 0;
 }
 
+// staging the 16-bit adjacency next to the tables is worth it only if it does not cost a resident CTA
+static bool idx_fits(size_t table_bytes, int idx_vecs) {
+    if (idx_vecs <= 0) return false;
+    const size_t sm_bytes = 227 * 1024, reserved = 1024, with_idx = table_bytes + (size_t)idx_vecs * 16;
+    if (with_idx + reserved > sm_bytes) return false;
+    return sm_bytes / (with_idx + reserved) == sm_bytes / (table_bytes + reserved);
+}
+
 template <typename K>
 static bool set_dyn_smem(K kernel) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
@@ -608,25 +625,17 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     if (!w) return false;
     __nv_bfloat16* cl4p = (panel_now(c) && w == 64) ? c->CL4P.p : nullptr;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
-    using T = __nv_bfloat16;
     const int Q = c->Q;
-    if (w == 128) {
-        static bool ok = set_dyn_smem(clause_gather_smem_kernel<128>);
-        if (!ok) return false;
-        clause_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
-                                                                          c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
-    } else if (w == 64) {
-        static bool ok = set_dyn_smem(clause_gather_smem_kernel<64>);
-        if (!ok) return false;
-        clause_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
-                                                                          c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
-    } else {
-        static bool ok = set_dyn_smem(clause_gather_smem_kernel<32>);
-        if (!ok) return false;
-        clause_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q,
-                                                                          c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
-    }
-    return true;
+    const bool si = c->use_idx16 && idx_fits(bytes, g.cl_idx16_vecs);
+    const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
+    auto launch = [&](auto kernel) -> bool {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
+        return true;
+    };
+    if (w == 128) return si ? launch(clause_gather_smem_kernel<128, true>) : launch(clause_gather_smem_kernel<128, false>);
+    if (w == 64) return si ? launch(clause_gather_smem_kernel<64, true>) : launch(clause_gather_smem_kernel<64, false>);
+    return si ? launch(clause_gather_smem_kernel<32, true>) : launch(clause_gather_smem_kernel<32, false>);
 }
 
 bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
@@ -661,25 +670,18 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     const __nv_bfloat16* msg_src = pn ? c->VMSGP.p : c->COUTb.p;
     const long long prow = pn ? c->Mt : 0;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
-    using T = __nv_bfloat16;
     const int Q = c->Q, F = c->F;
-    if (w == 128) {
-        static bool ok = set_dyn_smem(literal_gather_smem_kernel<128>);
-        if (!ok) return false;
-        literal_gather_smem_kernel<128><<<grid, 512, bytes, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F,
-                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD, prow);
-    } else if (w == 64) {
-        static bool ok = set_dyn_smem(literal_gather_smem_kernel<64>);
-        if (!ok) return false;
-        literal_gather_smem_kernel<64><<<grid, 512, bytes, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F,
-                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD, prow);
-    } else {
-        static bool ok = set_dyn_smem(literal_gather_smem_kernel<32>);
-        if (!ok) return false;
-        literal_gather_smem_kernel<32><<<grid, 512, bytes, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F,
-                                                                           c->QSb.p, 3 * Q, c->VROWb.p, c->ldv(), F + DSAT_AUX_PAD, prow);
-    }
-    return true;
+    const bool si = c->use_idx16 && idx_fits(bytes, g.lit_idx16_vecs);
+    const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
+    auto launch = [&](auto kernel) -> bool {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F, c->QSb.p, 3 * Q, c->VROWb.p,
+                                               c->ldv(), F + DSAT_AUX_PAD, prow);
+        return true;
+    };
+    if (w == 128) return si ? launch(literal_gather_smem_kernel<128, true>) : launch(literal_gather_smem_kernel<128, false>);
+    if (w == 64) return si ? launch(literal_gather_smem_kernel<64, true>) : launch(literal_gather_smem_kernel<64, false>);
+    return si ? launch(literal_gather_smem_kernel<32, true>) : launch(literal_gather_smem_kernel<32, false>);
 }
 #endif
 
@@ -938,6 +940,8 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e) c->use_pair = e[0] != '0';
         e = getenv("DSAT_SPMM_ORDER");
         if (e) c->use_spmm_order = e[0] != '0';
+        e = getenv("DSAT_IDX16");
+        if (e) c->use_idx16 = e[0] != '0';
         e = getenv("DSAT_PANELS");
         if (e) c->use_panels = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
@@ -962,7 +966,8 @@ void dsat_destroy(dsat_ctx* c) {
 #endif
     }
     c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
-    c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release();
+    c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release(); c->var_order.release();
+    c->cl_idx16.release(); c->lit_idx16.release(); c->cl_idx16_vecs = c->lit_idx16_vecs = 0;
     c->cl_desc.release(); c->lit_desc.release();
     for (auto& pm : c->prof) cudaEventDestroy(pm.ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1111,6 +1116,41 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     CK_CUDA(c, up_i(c->clause_seg, clause_seg, n_graphs + 1));
     CK_CUDA(c, up_f(c->deg_w, deg_w));
     CK_CUDA(c, up_f(c->vdeg_w, vdeg_w));
+    {
+        std::vector<int> vord(n_vars > 0 ? n_vars : 1, 0);
+        for (int v = 0; v < n_vars; ++v) vord[v] = v;
+        std::stable_sort(vord.begin(), vord.begin() + n_vars, [&](int a, int b) {
+            return lit_rowptr[2 * a + 2] - lit_rowptr[2 * a] > lit_rowptr[2 * b + 2] - lit_rowptr[2 * b];
+        });
+        CK_CUDA(c, up_i(c->var_order, vord.data(), (size_t)n_vars));
+        // 16-bit adjacency blocks (sections padded to 16 bytes)
+        c->cl_idx16_vecs = c->lit_idx16_vecs = 0;
+        if (nnz < 65536 && 2 * n_vars < 65536 && n_clauses < 65536 && n_vars > 0 && n_clauses > 0) {
+            auto pad8 = [](size_t x) { return (x + 7) / 8 * 8; };
+            std::vector<unsigned short> blk;
+            auto put = [&](const int* src, size_t cnt) {
+                const size_t at = blk.size();
+                blk.resize(at + pad8(cnt), 0);
+                for (size_t i = 0; i < cnt; ++i) blk[at + i] = (unsigned short)src[i];
+                return (int)at;
+            };
+            auto upload = [&](DevBuf<unsigned short>& dst) -> cudaError_t {
+                cudaError_t e = dst.alloc(blk.size());
+                if (e != cudaSuccess) return e;
+                return dsat_memcpy_sync(dst.p, blk.data(), blk.size() * sizeof(unsigned short), cudaMemcpyHostToDevice);
+            };
+            put(cl_rowptr, (size_t)n_clauses + 1);
+            c->cl_col_off = put(cl_lit, (size_t)nnz);
+            CK_CUDA(c, upload(c->cl_idx16));
+            c->cl_idx16_vecs = (int)(blk.size() / 8);
+            blk.clear();
+            put(lit_rowptr, (size_t)2 * n_vars + 1);
+            c->lit_col_off = put(lit_clause, (size_t)nnz);
+            c->lit_ord_off = put(vord.data(), (size_t)n_vars);
+            CK_CUDA(c, upload(c->lit_idx16));
+            c->lit_idx16_vecs = (int)(blk.size() / 8);
+        }
+    }
     CK_CUDA(c, up_f(c->rev_w, rev_w));
     {   // processing order of the standalone segment sums: rows that share their first gathered row become
         // neighbours, so the warps of one CTA hit L1; each row's {index, entry range, scale} is packed into one int4

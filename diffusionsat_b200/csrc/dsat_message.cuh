@@ -25,6 +25,14 @@ struct UnitGraphDev {
     const float* deg_w;                 // [2n]  rsqrt(max(deg(lit),1))
     const float* vdeg_w;                // [n]   rsqrt(max(deg(+v)+deg(-v),1))   (the reference's factor 4 is carried by cl4)
     const float* rev_w;                 // [m]   rsqrt(max(|clause|,1))
+    const int* var_order;               // [n]   variables by descending degree (rows of one warp pass get similar lengths)
+    // 16-bit copies of the adjacency for the shared-memory gathers (null when a count does not fit 16 bits):
+    //   cl_idx16  = [cl_rowptr (m+1) | cl_lit (nnz)],  lit_idx16 = [lit_rowptr (2n+1) | lit_clause (nnz) | var_order (n)]
+    // each section starts on a 16-byte boundary; *_vecs = length in 16-byte units
+    const unsigned short* cl_idx16;
+    const unsigned short* lit_idx16;
+    int cl_idx16_vecs, lit_idx16_vecs;
+    int cl_col_off, lit_col_off, lit_ord_off;      // section starts, in elements
 };
 
 constexpr int GATHER_WARPS = 8;
@@ -235,6 +243,36 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return w;
 }
 
+// streamed 16-byte load that does not allocate in L1: with ~220 KB of the SM carved out as shared memory only a few
+// KB of L1 remain, and they should keep the adjacency (read by every CTA) rather than rows that are used once
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// asynchronous 16-byte global -> shared copy (LDGSTS, L2 only): no register round trip, so a thread can have all of
+// its pieces in flight at once instead of eight
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_rows_async(T* __restrict__ dst, const T* __restrict__ src, int rows, int ld_src,
+                                                 int width, int tid, int nthreads) {
+    const int vec_per_row = width * (int)sizeof(T) / 16;
+    const int total = rows * vec_per_row;
+    for (int i = tid; i < total; i += nthreads) {
+        const int r = i / vec_per_row, k = i % vec_per_row;
+        cp_async16(reinterpret_cast<uint4*>(dst + (size_t)r * width) + k, reinterpret_cast<const uint4*>(src + (size_t)r * ld_src) + k);
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void stage_rows(T* __restrict__ dst, const T* __restrict__ src, int rows, int ld_src,
                                            int width, int tid, int nthreads) {
@@ -246,7 +284,7 @@ __device__ __forceinline__ void stage_rows(T* __restrict__ dst, const T* __restr
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = i0 + u * nthreads;
-            if (i < total) a[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(i / vec_per_row) * ld_src) + i % vec_per_row);
+            if (i < total) a[u] = ldg_stream(reinterpret_cast<const uint4*>(src + (size_t)(i / vec_per_row) * ld_src) + i % vec_per_row);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -257,7 +295,7 @@ __device__ __forceinline__ void stage_rows(T* __restrict__ dst, const T* __restr
 }
 
 // clause side: tables LIT[2n][W] and SP[2n][W] of the chain's slice (row = literal code 2*var+sign)
-template <int W>
+template <int W, bool SI>
 __global__ void __launch_bounds__(1024)
 clause_gather_smem_kernel(UnitGraphDev g, int Q,
                           const __nv_bfloat16* __restrict__ LIT, int ld_lit,
@@ -270,44 +308,41 @@ clause_gather_smem_kernel(UnitGraphDev g, int Q,
     extern __shared__ __align__(16) uint8_t gsm[];
     T* t_lit = reinterpret_cast<T*>(gsm);
     T* t_sp = t_lit + (size_t)2 * g.n * W;
+    // SI: the adjacency is staged too (16-bit).  Read from global it costs an L2 round trip per entry, because the
+    // shared-memory carve-out leaves almost no L1, and that chain of dependent loads dominated the gather phase.
+    const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(t_sp + (size_t)2 * g.n * W);
     const int chain = blockIdx.x, slice = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int sub = lane / LPR, li = lane % LPR;
     const size_t vbase = (size_t)chain * g.n;
-    {   // stage both tables: 4 independent 16-byte loads per table in flight per thread
+    {   // stage both tables with asynchronous copies (all pieces of a thread in flight at once)
         const int total = 2 * g.n * LPR;                    // (variable, sign, 16-byte piece)
-        constexpr int U = 4;
-        for (int i0 = tid; i0 < total; i0 += U * blockDim.x) {
-            uint4 a[U], b[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < total) {
-                    const int code = i / LPR, k = i % LPR, v = code >> 1, sgn = code & 1;
-                    a[u] = __ldg(reinterpret_cast<const uint4*>(LIT + (vbase + v) * ld_lit + sgn * Q + slice * W) + k);
-                    b[u] = __ldg(reinterpret_cast<const uint4*>(SP + (vbase + v) * ld_sp + sp_off + sgn * Q + slice * W) + k);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * blockDim.x;
-                if (i < total) {
-                    const int code = i / LPR, k = i % LPR;
-                    reinterpret_cast<uint4*>(t_lit + (size_t)code * W)[k] = a[u];
-                    reinterpret_cast<uint4*>(t_sp + (size_t)code * W)[k] = b[u];
-                }
-            }
+        for (int i = tid; i < total; i += blockDim.x) {
+            const int code = i / LPR, k = i % LPR, v = code >> 1, sgn = code & 1;
+            cp_async16(reinterpret_cast<uint4*>(t_lit + (size_t)code * W) + k,
+                       reinterpret_cast<const uint4*>(LIT + (vbase + v) * ld_lit + sgn * Q + slice * W) + k);
+            cp_async16(reinterpret_cast<uint4*>(t_sp + (size_t)code * W) + k,
+                       reinterpret_cast<const uint4*>(SP + (vbase + v) * ld_sp + sp_off + sgn * Q + slice * W) + k);
         }
     }
+    if constexpr (SI) {
+        uint4* d = reinterpret_cast<uint4*>(const_cast<unsigned short*>(s_idx));
+        for (int i = tid; i < g.cl_idx16_vecs; i += blockDim.x) d[i] = __ldg(reinterpret_cast<const uint4*>(g.cl_idx16) + i);
+    }
+    cp_async_wait_all();
     __syncthreads();
     for (int j0 = warp * RPW; j0 < g.m; j0 += nwarps * RPW) {
         const int j = j0 + sub;
         const bool live = j < g.m;
-        const int e0 = live ? __ldg(g.cl_rowptr + j) : 0, e1 = live ? __ldg(g.cl_rowptr + j + 1) : 0;
+        int e0 = 0, e1 = 0;
+        if (live) {
+            if constexpr (SI) { e0 = s_idx[j]; e1 = s_idx[j + 1]; }
+            else { e0 = __ldg(g.cl_rowptr + j); e1 = __ldg(g.cl_rowptr + j + 1); }
+        }
         Acc8 al, as;
         acc8_zero(al); acc8_zero(as);
         for (int e = e0; e < e1; ++e) {
-            const int code = __ldg(g.cl_lit + e);
+            const int code = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
             acc8_add(al, reinterpret_cast<const uint4*>(t_lit + (size_t)code * W)[li]);
             acc8_add(as, reinterpret_cast<const uint4*>(t_sp + (size_t)code * W)[li]);
         }
@@ -325,7 +360,7 @@ clause_gather_smem_kernel(UnitGraphDev g, int Q,
 }
 
 // literal side: tables CL4[m][W] and MSG[m][W] of the chain's slice
-template <int W>
+template <int W, bool SI>
 __global__ void __launch_bounds__(1024)
 literal_gather_smem_kernel(UnitGraphDev g, int Q,
                            const __nv_bfloat16* __restrict__ CL4, int ld_cl, int cl_off,
@@ -338,29 +373,62 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
     extern __shared__ __align__(16) uint8_t gsm[];
     T* t_cl = reinterpret_cast<T*>(gsm);
     T* t_ms = t_cl + (size_t)g.m * W;
+    const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(t_ms + (size_t)g.m * W);   // see clause side
     const int chain = blockIdx.x, slice = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int sub = lane / LPR, li = lane % LPR;
     const size_t cbase = (size_t)chain * g.m;
+#ifdef DSAT_GATHER_TRACE
+    const long long t_start = clock64();
+#endif
     if (panel_rows > 0) {
-        stage_rows<T>(t_cl, CL4 + ((size_t)slice * panel_rows + cbase) * 64, g.m, 64, W, tid, blockDim.x);
-        stage_rows<T>(t_ms, MSG + ((size_t)slice * panel_rows + cbase) * 64, g.m, 64, W, tid, blockDim.x);
+        stage_rows_async<T>(t_cl, CL4 + ((size_t)slice * panel_rows + cbase) * 64, g.m, 64, W, tid, blockDim.x);
+        stage_rows_async<T>(t_ms, MSG + ((size_t)slice * panel_rows + cbase) * 64, g.m, 64, W, tid, blockDim.x);
     } else {
-        stage_rows<T>(t_cl, CL4 + cbase * ld_cl + cl_off + slice * W, g.m, ld_cl, W, tid, blockDim.x);
-        stage_rows<T>(t_ms, MSG + cbase * ld_msg + slice * W, g.m, ld_msg, W, tid, blockDim.x);
+        stage_rows_async<T>(t_cl, CL4 + cbase * ld_cl + cl_off + slice * W, g.m, ld_cl, W, tid, blockDim.x);
+        stage_rows_async<T>(t_ms, MSG + cbase * ld_msg + slice * W, g.m, ld_msg, W, tid, blockDim.x);
     }
+    if constexpr (SI) {
+        uint4* d = reinterpret_cast<uint4*>(const_cast<unsigned short*>(s_idx));
+        for (int i = tid; i < g.lit_idx16_vecs; i += blockDim.x) d[i] = __ldg(reinterpret_cast<const uint4*>(g.lit_idx16) + i);
+    }
+    cp_async_wait_all();
+#ifdef DSAT_GATHER_TRACE
+    const long long t_staged = clock64();
+#endif
     __syncthreads();
+#ifdef DSAT_GATHER_TRACE
+    const long long t_sync = clock64();
+#endif
+    // variables are taken in order of descending degree: the RPW rows of a pass then have similar entry counts (a
+    // pass runs for its longest row), and the heaviest passes are dealt first
     for (int v0 = warp * RPW; v0 < g.n; v0 += nwarps * RPW) {
-        const int v = v0 + sub;
-        const bool live = v < g.n;
+        const bool live = v0 + sub < g.n;
+        int v = 0;
+        if (live) v = SI ? (int)s_idx[g.lit_ord_off + v0 + sub] : __ldg(g.var_order + v0 + sub);
         Acc8 s4[2], ms[2];
 #pragma unroll
         for (int sgn = 0; sgn < 2; ++sgn) {
             acc8_zero(s4[sgn]); acc8_zero(ms[sgn]);
             const int code = 2 * v + sgn;
-            const int e0 = live ? __ldg(g.lit_rowptr + code) : 0, e1 = live ? __ldg(g.lit_rowptr + code + 1) : 0;
-            for (int e = e0; e < e1; ++e) {
-                const int j = __ldg(g.lit_clause + e);
+            int e0 = 0, e1 = 0;
+            if (live) {
+                if constexpr (SI) { e0 = s_idx[code]; e1 = s_idx[code + 1]; }
+                else { e0 = __ldg(g.lit_rowptr + code); e1 = __ldg(g.lit_rowptr + code + 1); }
+            }
+            int e = e0;
+            for (; e + 2 <= e1; e += 2) {
+                const int j0 = SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e);
+                const int j1 = SI ? (int)s_idx[g.lit_col_off + e + 1] : __ldg(g.lit_clause + e + 1);
+                const uint4 a0 = reinterpret_cast<const uint4*>(t_cl + (size_t)j0 * W)[li];
+                const uint4 b0 = reinterpret_cast<const uint4*>(t_ms + (size_t)j0 * W)[li];
+                const uint4 a1 = reinterpret_cast<const uint4*>(t_cl + (size_t)j1 * W)[li];
+                const uint4 b1 = reinterpret_cast<const uint4*>(t_ms + (size_t)j1 * W)[li];
+                acc8_add(s4[sgn], a0); acc8_add(ms[sgn], b0);
+                acc8_add(s4[sgn], a1); acc8_add(ms[sgn], b1);
+            }
+            if (e < e1) {
+                const int j = SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e);
                 acc8_add(s4[sgn], reinterpret_cast<const uint4*>(t_cl + (size_t)j * W)[li]);
                 acc8_add(ms[sgn], reinterpret_cast<const uint4*>(t_ms + (size_t)j * W)[li]);
             }
@@ -385,6 +453,11 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
             reinterpret_cast<uint4*>(dst + 2 * Q)[li] = pack8(ln);
         }
     }
+#ifdef DSAT_GATHER_TRACE
+    if (slice == 0 && (chain == 1500 || chain == 3000) && (tid == 0 || tid == 511))
+        printf("literal gather chain %d tid %d: stage %lld  wait %lld  gather %lld cycles\n", chain, tid, t_staged - t_start,
+               t_sync - t_staged, clock64() - t_sync);
+#endif
 }
 
 }  // namespace dsat
