@@ -13,7 +13,8 @@ Differences that are deliberate and documented in DESIGN.md:
 * several reference batches run in one launch; they are consumed batch by batch in order, with the
   reference's stop rules (exactly ``n`` SAT samples; abort below 0.5 % SAT rate), so the returned
   histogram does not depend on how many batches a launch holds;
-* ``model_path`` is a ``.npz`` from :func:`diffusionsat_b200.weights.save_weights`; a missing file prints
+* ``model_path`` is the reference's TensorFlow checkpoint directory (read without TensorFlow,
+  :mod:`diffusionsat_b200.tf_checkpoint`) or a ``.npz`` from :func:`diffusionsat_b200.weights.save_weights`; a missing file prints
   "Checkpoint not found!" and continues with seeded random weights, as the reference does.
 """
 

@@ -13,8 +13,9 @@ Input column order of each first layer (what the kernels' weight re-packing reli
 * ``update_gate``: ``[variables_grad(Q) | v1(F+9) | loss_pos(Q) | loss_neg(Q)]`` (``:277``)
 * ``variables_output``: ``variables(F)`` (``:283``)
 
-Checkpoint import from TensorFlow object-graph files is not available offline; ``model_path`` is a
-``.npz`` written by :func:`save_weights`.
+``model_path`` is either a ``.npz`` written by :func:`save_weights` or a TensorFlow checkpoint directory /
+prefix as the reference writes it (read without TensorFlow by :mod:`diffusionsat_b200.tf_checkpoint`,
+SURVEY.md section 8f item 1).
 """
 
 from __future__ import annotations
@@ -102,9 +103,14 @@ def save_weights(path: str, weights: QuerySATWeights) -> None:
 
 
 def load_weights(path: str) -> QuerySATWeights:
-    """Load a ``.npz`` (a directory is searched for the newest ``*.npz``). Raises
+    """Load a ``.npz`` (a directory is searched for the newest ``*.npz``) or a TensorFlow checkpoint
+    (directory with a ``checkpoint`` state file / ``*.index``, or a ``ckpt-N`` prefix). Raises
     ``FileNotFoundError`` when nothing is there; the caller decides about random init, as the
     reference does (``satuniformity/DiffusionSampler.py:221-225``)."""
+    from . import tf_checkpoint
+    if not (os.path.isdir(path) and any(f.endswith(".npz") for f in os.listdir(path))) and not path.endswith(".npz") \
+            and tf_checkpoint.is_tf_checkpoint(path):
+        return tf_checkpoint.load_querysat_weights(path)
     if os.path.isdir(path):
         cands = sorted((os.path.getmtime(os.path.join(path, f)), os.path.join(path, f))
                        for f in os.listdir(path) if f.endswith(".npz"))
