@@ -87,6 +87,22 @@ def _graph_ids(membership, count):
     return ids, shape[0]
 
 
+def is_graph_sat(predictions, adj_indices, adj_shape, clause_graph_ids, n_graphs):
+    """Per-graph 0/1 flags: every clause of the graph has a true literal under ``round(sigmoid(logits))``
+    (reference ``utils/sat.py:165-180``; ``tf.round`` is half-to-even, so the bit is ``sigmoid > 0.5`` strictly)."""
+    n, m = adj_shape[0] // 2, adj_shape[1]
+    z = np.asarray(predictions, dtype=np.float32).reshape(n)
+    bits = ((np.float32(1.0) / (np.float32(1.0) + np.exp(-z, dtype=np.float32))) > np.float32(0.5)).astype(np.float32)
+    literals = np.concatenate([bits, 1.0 - bits])
+    clause_sat = np.zeros(m, dtype=np.float32)
+    np.add.at(clause_sat, adj_indices[:, 1], literals[adj_indices[:, 0]])
+    clause_sat = np.clip(clause_sat, 0.0, 1.0)
+    sat_in_g = np.zeros(n_graphs, dtype=np.float32)
+    np.add.at(sat_in_g, clause_graph_ids, clause_sat)
+    total_in_g = np.bincount(clause_graph_ids, minlength=n_graphs).astype(np.float32)
+    return np.clip(sat_in_g + 1.0 - total_in_g, 0.0, 1.0)
+
+
 class QuerySAT:
     def __init__(self, optimizer=None, feature_maps=128, msg_layers=3, vote_layers=3, train_rounds=32,
                  test_rounds=64, query_maps=128, supervised=True, trial=None, *, weights: QuerySATWeights = None,
@@ -169,7 +185,32 @@ class QuerySAT:
         return {"steps_taken": step, "loss": loss, "prediction": predictions[:, 0]}
 
     def predict_step(self, adj_matrix, clauses_graph, variables_graph, solutions=None):
-        predictions, loss, step = self.call(adj_matrix, clauses_graph, variables_graph, training=False)
+        """Reference ``:424-451``: one call, or ``prediction_tries`` calls where every graph keeps the logits of the
+        first try that satisfied it (graphs never solved end with zeros, as in the reference)."""
+        if self.prediction_tries == 1:
+            predictions, loss, step = self.call(adj_matrix, clauses_graph, variables_graph, training=False)
+        else:
+            idx, shape = _coo(adj_matrix)
+            n, m = shape[0] // 2, shape[1]
+            vg, n_graphs = _graph_ids(variables_graph, n)
+            cg, _ = _graph_ids(clauses_graph, m)
+            final = np.zeros((n, 1), dtype=np.float32)
+            solved = np.zeros(n_graphs, dtype=np.float32)
+            for _ in range(self.prediction_tries):
+                predictions, loss, step = self.call(adj_matrix, clauses_graph, variables_graph, training=False)
+                sat = np.clip(is_graph_sat(predictions, idx, shape, cg, n_graphs) - solved, 0.0, 1.0)   # newly solved
+                final += predictions * sat[vg][:, None]
+                solved = solved + sat
+            predictions = final
+        return {"steps_taken": step, "loss": loss, "prediction": predictions[:, 0]}
+
+    def plot_step(self, adj_matrix, clauses_graph, variables_graph, solutions, noise_scale):
+        """Reference ``:453-465``: a call at a given noise level with the solutions as labels."""
+        labels = solutions.flat_values if hasattr(solutions, "flat_values") else solutions
+        labels = labels.numpy() if hasattr(labels, "numpy") else labels
+        labels = np.concatenate([np.asarray(x).reshape(-1) for x in labels]) if isinstance(labels, (list, tuple)) else labels
+        predictions, loss, step = self.call(adj_matrix, clauses_graph, variables_graph, training=False, labels=labels,
+                                            noise_scale=noise_scale)
         return {"steps_taken": step, "loss": loss, "prediction": predictions[:, 0]}
 
     def get_config(self):

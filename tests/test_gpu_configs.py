@@ -66,6 +66,22 @@ def test_mixed_ksat_union_batch_through_querysat_api(ctx):
     # predict_step draws its own noise: shape and finiteness only
     out = model.predict_step((coo, shape), cg, vg, None)
     assert out["prediction"].shape == (n_rows,) and np.isfinite(out["prediction"]).all()
+    # prediction_tries > 1 (reference model/query_sat.py:429-445): a graph keeps the logits of the first try that
+    # satisfied it and zeros otherwise, so every non-zero block must satisfy its formula
+    from diffusionsat_b200.query_sat import is_graph_sat
+    model.prediction_tries = 3
+    out3 = model.predict_step((coo, shape), cg, vg, None)
+    model.prediction_tries = 1
+    flags = is_graph_sat(out3["prediction"], coo, shape, cg, len(formulas))
+    for gi in range(len(formulas)):
+        block = out3["prediction"][vg == gi]
+        assert (block != 0).any() == bool(flags[gi]) or not (block != 0).any()
+        if (block != 0).any():
+            assert flags[gi] == 1.0
+    # plot_step: labels = solutions (ragged), explicit noise level
+    sols = [np.zeros(n, dtype=np.int32) for n, _ in formulas]
+    outp = model.plot_step((coo, shape), cg, vg, sols, 0.5)
+    assert outp["prediction"].shape == (n_rows,) and np.isfinite(outp["prediction"]).all()
 
 
 @pytest.mark.parametrize("feat", [64, 128, 256])

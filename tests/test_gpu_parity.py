@@ -248,6 +248,12 @@ def test_sampler_end_to_end(ctx, tmp_path):
     sampler2 = DiffusionSampler(str(wpath), str(cnf), context=ctx, chains_per_launch=2048, seed=3,
                                 max_nodes_per_batch=130)
     assert sampler2.samples(100) == hist
+    # model_path as the reference's TensorFlow checkpoint directory (read without TensorFlow): same weights, same histogram
+    from diffusionsat_b200.tf_checkpoint import save_querysat_checkpoint
+    save_querysat_checkpoint(str(tmp_path / "tf_model"), H.make_weights(seed=2), step=5)
+    sampler3 = DiffusionSampler(str(tmp_path / "tf_model"), str(cnf), context=ctx, chains_per_launch=512, seed=3,
+                                max_nodes_per_batch=130)
+    assert sampler3.samples(100) == hist
 
 
 # ---------------------------------------------------------------- against the reference's own source

@@ -148,3 +148,27 @@ def test_union_graph_and_reference_coo_roundtrip():
         np.testing.assert_array_equal(getattr(back, name), getattr(union, name))
     og = O.OracleGraph.from_formulas(formulas)
     assert list(zip(og.lit_row.tolist(), og.clause.tolist())) == [tuple(p) for p in coo.tolist()]
+
+
+def test_is_graph_sat_matches_clause_by_clause_check():
+    """Host restatement of reference utils/sat.py:165-180 against a literal-by-literal evaluation."""
+    from diffusionsat_b200 import graph as G, synth
+    from diffusionsat_b200.query_sat import is_graph_sat
+    rng = np.random.default_rng(0)
+    formulas = [synth.random_ksat_mixed(int(rng.integers(3, 12)), int(rng.integers(2, 20)), seed=s) for s in range(6)]
+    formulas.append((3, [[1], [-1]]))                              # unsatisfiable
+    formulas.append((2, [[1, 2], []]))                             # empty clause is never satisfied
+    union = G.build_union_graph(formulas)
+    coo, shape = union.reference_coo(1)
+    vg = np.repeat(np.arange(len(formulas)), [n for n, _ in formulas])
+    cg = np.repeat(np.arange(len(formulas)), [len(c) for _, c in formulas])
+    for trial in range(5):
+        logits = rng.standard_normal(union.n_vars).astype(np.float32)
+        logits[rng.integers(0, union.n_vars)] = 0.0                # sigmoid == 0.5 rounds to 0 (half to even)
+        got = is_graph_sat(logits, coo, shape, cg, len(formulas))
+        off = 0
+        for gi, (n, clauses) in enumerate(formulas):
+            bits = logits[off:off + n] > 0
+            ok = all(any((bits[abs(l) - 1] if l > 0 else not bits[abs(l) - 1]) for l in c) for c in clauses)
+            assert got[gi] == float(ok), (trial, gi)
+            off += n
