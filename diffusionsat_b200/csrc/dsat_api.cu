@@ -302,6 +302,10 @@ int ensure_tc_buffers(dsat_ctx* c) {
                 if (!tc::make_bf16_map(&f.map_wp[i], l.w, l.n, K64, K64, f.p.layer[i].box_rows / 2)) return false;
                 ++i;
             }
+            {   // input ring per MLP: DSAT_A_RING is a bit mask over (query, literal, clause, update, output)
+                static const int mask = getenv("DSAT_A_RING") ? atoi(getenv("DSAT_A_RING")) : 0x1d;
+                f.stream_input = ((mask >> which) & 1) != 0;
+            }
             if (!fm::plan_fused(f)) return false;
             f.pair_ok = fm2::pair_supported(f) && f.pp.slots >= 2;
             return true;

@@ -12,6 +12,9 @@
 //                   the two halves, so the first layer of tile i+1 accumulates while tile i's output drains
 //   warps           0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue (lane quadrant = warp%4)
 //
+//                   input ring  : (a_slots > 0) the 64-column blocks of the input tile stream through their own ring
+//                                 instead of resting in AH, so the next tile's input is fetched while this tile's
+//                                 later layers and epilogues still run (AH then holds hidden activations only)
 // mbarriers:  a_full (TMA->MMA, per tile)      ah_free (MMA->TMA, AH may take the next input tile)
 //             ring full/empty (TMA<->MMA)       tmem_full[buf] (MMA->epilogue)   tmem_empty[buf] (epilogue->MMA)
 //             h_full (epilogue->MMA, hidden activations of a layer are in shared memory)
@@ -33,7 +36,8 @@ constexpr int AH_BLOCK_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB: 128 rows x 
 constexpr int TMEM_COLS = 512;
 constexpr int STAGE_ROW = 128 + 16;                        // bytes per staged row (one 32-column fp32 chunk + pad)
 constexpr int STAGE_BYTES = 4 * 32 * STAGE_ROW;            // four epilogue warps
-constexpr int BAR_BYTES = 256;
+constexpr int BAR_BYTES = 512;
+constexpr int MAX_A_SLOTS = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct FmLayer {
@@ -48,6 +52,7 @@ struct FmParams {
     int n_layers;
     FmLayer layer[MAX_LAYERS];
     int rows, n_tiles, a_box_rows, ah_blocks, slots, slot_bytes, two_bufs, qmaps;
+    int a_slots;           // > 0: layer 0's A operand streams through an input ring of that many 16 KB blocks
     int a_split_kb;        // k-blocks >= a_split_kb of the INPUT tile come from map_a2 (panel-major source), 1<<20 = never
     long long a2_panel_rows;  // rows per 64-column panel of that source
     long long out0_panel_rows;   // > 0: output columns [0, split) go to 64-column panels of this many rows (bf16)
@@ -347,7 +352,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* ah = smem;
-    uint8_t* ring = smem + (size_t)p.ah_blocks * AH_BLOCK_BYTES;
+    uint8_t* a_ring = smem + (size_t)p.ah_blocks * AH_BLOCK_BYTES;
+    uint8_t* ring = a_ring + (size_t)p.a_slots * AH_BLOCK_BYTES;
     uint8_t* stage_all = ring + (size_t)p.slots * p.slot_bytes;
     uint8_t* tail = stage_all + (size_t)p.epi_warps * 32 * p.stage_row;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
@@ -357,7 +363,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint64_t* tmem_empty = a_full + 5;                 // [2]
     uint64_t* ring_full = a_full + 7;                  // [MAX_SLOTS]
     uint64_t* ring_empty = a_full + 7 + MAX_SLOTS;     // [MAX_SLOTS]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 7 + 2 * MAX_SLOTS);
+    uint64_t* a_ring_full = a_full + 7 + 2 * MAX_SLOTS;                  // [MAX_A_SLOTS]
+    uint64_t* a_ring_empty = a_ring_full + MAX_A_SLOTS;                  // [MAX_A_SLOTS]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ring_empty + MAX_A_SLOTS);
     float* bias_s = reinterpret_cast<float*>(tail + BAR_BYTES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -373,6 +381,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_init(h_full, epi_threads);
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], epi_threads); }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+        for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_ring_full[s], 1); mbar_init(&a_ring_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
@@ -401,39 +410,52 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (lane == 0) {   // ================================ TMA producer
             const int k0_blocks = (p.layer[0].K + BLOCK_K - 1) / BLOCK_K;
             int slot = 0; uint32_t phase = 0;
+            int aslot = 0; uint32_t aphase = 0;
             int it = 0;
+            auto load_a_block = [&](uint8_t* dst, uint64_t* bar, int kb, int tile) {
+                if (kb < p.a_split_kb)
+                    tma_load_2d(dst, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
+                else         // panel-major source: panel (kb - a_split_kb) is a dense [rows, 64] matrix
+                    tma_load_2d(dst, &map_a2, bar, 0, (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
+            };
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                if (it > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((it - 1) & 1)));   // tile it-1 no longer reads AH
-                mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
-                for (int kb = 0; kb < k0_blocks; ++kb)
-                    if (kb < p.a_split_kb)
-                        tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
-                    else     // panel-major source: panel (kb - a_split_kb) is a dense [rows, 64] matrix
-                        tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a2, a_full, 0,
-                                    (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
+                if (p.a_slots == 0) {
+                    if (it > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((it - 1) & 1)));   // tile it-1 no longer reads AH
+                    mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
+                    for (int kb = 0; kb < k0_blocks; ++kb) load_a_block(ah + (size_t)kb * AH_BLOCK_BYTES, a_full, kb, tile);
+                }
                 for (int l = 0; l < n_layers; ++l) {
                     const int kbs = (p.layer[l].K + BLOCK_K - 1) / BLOCK_K;
                     const int halves = (p.layer[l].N + 255) / 256;
-                    for (int kb = 0; kb < kbs; ++kb)
+                    for (int kb = 0; kb < kbs; ++kb) {
+                        if (l == 0 && p.a_slots > 0) {     // input block kb of this tile into the input ring
+                            DSAT_TIMED_WAIT(w0, mbar_wait(&a_ring_empty[aslot], aphase ^ 1));
+                            mbar_expect_tx(&a_ring_full[aslot], (uint32_t)p.a_box_rows * (BLOCK_K * 2));
+                            load_a_block(a_ring + (size_t)aslot * AH_BLOCK_BYTES, &a_ring_full[aslot], kb, tile);
+                            if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+                        }
                         for (int h = 0; h < halves; ++h) {
                             DSAT_TIMED_WAIT(w1, mbar_wait(&ring_empty[slot], phase ^ 1));
                             mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[l].box_rows * (BLOCK_K * 2));
                             tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K, h * 256);
                             if (++slot == p.slots) { slot = 0; phase ^= 1; }
                         }
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ================================ MMA issuer
             int slot = 0; uint32_t phase = 0;
+            int aslot = 0; uint32_t aphase = 0;
             int it = 0, g = 0, hcount = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
                 for (int l = 0; l < n_layers; ++l, ++g) {
                     const int buf = p.two_bufs ? (g & 1) : 0;
                     const int use = p.two_bufs ? (g >> 1) : g;
                     DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_empty[buf], (uint32_t)((use & 1) ^ 1)));   // accumulator drained
-                    if (l == 0) DSAT_TIMED_WAIT(w1, mbar_wait(a_full, (uint32_t)(it & 1)));
+                    const bool streamed = l == 0 && p.a_slots > 0;
+                    if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, mbar_wait(a_full, (uint32_t)(it & 1))); }
                     else { DSAT_TIMED_WAIT(w2, mbar_wait(h_full, (uint32_t)(hcount & 1))); ++hcount; }
                     tcgen05_fence_after();
                     const int K = p.layer[l].K, N = p.layer[l].N;
@@ -441,7 +463,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int halves = (N + 255) / 256;
                     const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
                     for (int kb = 0; kb < kbs; ++kb) {
-                        const uint64_t da = make_smem_desc_sw128(smem_u32(ah + (size_t)kb * AH_BLOCK_BYTES));
+                        if (streamed) { DSAT_TIMED_WAIT(w1, mbar_wait(&a_ring_full[aslot], aphase)); tcgen05_fence_after(); }
+                        const uint64_t da = make_smem_desc_sw128(smem_u32(streamed ? a_ring + (size_t)aslot * AH_BLOCK_BYTES
+                                                                                   : ah + (size_t)kb * AH_BLOCK_BYTES));
                         const int ksteps = min(BLOCK_K / 16, (K - kb * BLOCK_K + 15) / 16);
                         for (int h = 0; h < halves; ++h) {
                             const int bn = min(256, N - h * 256);
@@ -458,9 +482,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
                             if (++slot == p.slots) { slot = 0; phase ^= 1; }
                         }
+                        if (streamed) {
+                            tcgen05_commit(&a_ring_empty[aslot]);
+                            if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+                        }
                     }
                     tcgen05_commit(&tmem_full[buf]);
-                    if (l == n_layers - 1) tcgen05_commit(ah_free);
+                    if (l == n_layers - 1 && p.a_slots == 0) tcgen05_commit(ah_free);
                 }
             }
         }
@@ -534,6 +562,7 @@ struct FusedMlp {
     FmParams pp;
     int smem_bytes_pair;
     bool pair_ok;
+    bool stream_input = false;      // request the input ring (FmParams::a_slots), set before plan_fused
 };
 
 // shared-memory plan; returns false when the MLP does not fit
@@ -542,6 +571,7 @@ inline bool plan_fused(FusedMlp& f) {
     int blocks = (p.layer[0].K + 63) / 64;
     int bias_total = 0, max_box = 0;
     p.two_bufs = 1;
+    p.a_slots = 0;
     for (int l = 0; l < p.n_layers; ++l) {
         if (l + 1 < p.n_layers) blocks = max(blocks, (p.layer[l].N + 63) / 64);
         p.layer[l].bias_off = bias_total;
@@ -566,7 +596,32 @@ inline bool plan_fused(FusedMlp& f) {
         const bool all_bf16 = p.out.bf16_0 && (p.out.ptr1 == nullptr || p.out.bf16_1) && last.epi != tc::TC_QUERY;
         p.stage_row = all_bf16 ? 80 : STAGE_ROW;
     }
+    p.a_slots = 0;
     p.epi_warps = 4;
+    if (f.stream_input && p.n_layers > 1) {
+        // streamed input: AH keeps hidden activations only; the input gets its own ring (as deep as fits next to two
+        // weight slots and eight epilogue warps, at most two tiles' worth)
+        int h_blocks = 1;
+        for (int l = 0; l + 1 < p.n_layers; ++l) h_blocks = max(h_blocks, (p.layer[l].N + 63) / 64);
+        const int k0_blocks = (p.layer[0].K + 63) / 64;
+        for (int ew : {8, 4}) {
+            const int fixed = 1024 + h_blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 6;
+            int a_slots = (SMEM_LIMIT - fixed) / AH_BLOCK_BYTES;
+            if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
+            if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
+            if (a_slots >= 2 && a_slots >= (k0_blocks + 1) / 2) {
+                p.a_slots = a_slots;
+                p.epi_warps = ew;
+                p.ah_blocks = h_blocks;
+                const int base = fixed - 2 * p.slot_bytes + a_slots * AH_BLOCK_BYTES;
+                for (int slots = MAX_SLOTS; slots >= 2; --slots)
+                    if (base + slots * p.slot_bytes <= SMEM_LIMIT) { p.slots = slots; f.smem_bytes = base + slots * p.slot_bytes; break; }
+                f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs; f.pp.ah_blocks = blocks;
+                for (int l = 0; l < p.n_layers; ++l) f.pp.layer[l].bias_off = p.layer[l].bias_off;
+                return true;
+            }
+        }
+    }
     for (int ew : {8, 4}) {     // prefer 8 epilogue warps when two ring slots still fit
         if (1024 + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 6 <= SMEM_LIMIT) {
             p.epi_warps = ew;
