@@ -344,6 +344,7 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint64_t* tmem_empty_
     if (!HIDDEN && !released) { tc::tcgen05_fence_before(); mbar_arrive(tmem_empty_bar); }
 }
 
+template <bool TIMING>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
@@ -371,9 +372,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int epi_threads = 32 * p.epi_warps;
     const CUtensorMap* map_w[MAX_LAYERS] = {&map_w0, &map_w1, &map_w2};
-    const bool timing = p.prof != nullptr && blockIdx.x == 0;
+    const bool timing = TIMING && p.prof != nullptr && blockIdx.x == 0;   // TIMING = false strips every counter
     const long long t_kernel0 = timing ? clock64() : 0;
-    long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0;
+    long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0, w7 = 0;
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
@@ -445,7 +446,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {   // ================================ MMA issuer
+        {                  // ================================ MMA issuer: the whole warp runs the loop converged, lane 0 issues
+            const uint32_t leader = lane == 0;
             int slot = 0; uint32_t phase = 0;
             int aslot = 0; uint32_t aphase = 0;
             int it = 0, g = 0, hcount = 0;
@@ -462,6 +464,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
                     const int halves = (N + 255) / 256;
                     const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+                    const long long t_kb0 = timing ? clock64() : 0;
                     for (int kb = 0; kb < kbs; ++kb) {
                         if (streamed) { DSAT_TIMED_WAIT(w1, mbar_wait(&a_ring_full[aslot], aphase)); tcgen05_fence_after(); }
                         const uint64_t da = make_smem_desc_sw128(smem_u32(streamed ? a_ring + (size_t)aslot * AH_BLOCK_BYTES
@@ -474,21 +477,30 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                             tcgen05_fence_after();
                             const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
                             const long long t_i0 = timing ? clock64() : 0;
-                            for (int k = 0; k < ksteps; ++k)
-                                umma_bf16(acc + (uint32_t)(h * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                          (kb | k) != 0);
+                            const uint32_t acc_h = acc + (uint32_t)(h * 256);
+                            if (ksteps == BLOCK_K / 16) {       // 16 bf16 = 32 bytes along K: +2 in the (>>4) address field
+                                umma_bf16_if(leader, acc_h, da, db, idesc, kb != 0);
+                                umma_bf16_if(leader, acc_h, da + 2, db + 2, idesc, 1);
+                                umma_bf16_if(leader, acc_h, da + 4, db + 4, idesc, 1);
+                                umma_bf16_if(leader, acc_h, da + 6, db + 6, idesc, 1);
+                            } else {
+                                for (int k = 0; k < ksteps; ++k)
+                                    umma_bf16_if(leader, acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            }
                             const long long t_i1 = timing ? clock64() : 0;
-                            tcgen05_commit(&ring_empty[slot]);
+                            tcgen05_commit_if(leader, &ring_empty[slot]);
                             if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
                             if (++slot == p.slots) { slot = 0; phase ^= 1; }
                         }
                         if (streamed) {
-                            tcgen05_commit(&a_ring_empty[aslot]);
+                            tcgen05_commit_if(leader, &a_ring_empty[aslot]);
                             if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
                         }
                     }
-                    tcgen05_commit(&tmem_full[buf]);
-                    if (l == n_layers - 1 && p.a_slots == 0) tcgen05_commit(ah_free);
+                    const long long t_kb1 = timing ? clock64() : 0;
+                    tcgen05_commit_if(leader, &tmem_full[buf]);
+                    if (l == n_layers - 1 && p.a_slots == 0) tcgen05_commit_if(leader, ah_free);
+                    if (timing) { w6 += t_kb1 - t_kb0; w7 += clock64() - t_kb1; }
                 }
             }
         }
@@ -540,10 +552,10 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         // [5] h_full wait [6] ring_full wait; epilogue warp 2: [7] tmem_full wait [8] hidden epilogues [9] final epilogues
         const long long total = clock64() - t_kernel0;
         if (warp == 0) { p.prof[0] = total; p.prof[1] = w0; p.prof[2] = w1; }
-        if (warp == 1) { p.prof[3] = w0; p.prof[4] = w1; p.prof[5] = w2; p.prof[6] = w3; p.prof[10] = total; p.prof[12] = w4; p.prof[13] = w5; }
-        if (warp == 2) { p.prof[7] = w0; p.prof[8] = w1; p.prof[9] = w2; p.prof[11] = total; p.prof[14] = w3; p.prof[15] = w4; }
+        if (warp == 1) { p.prof[3] = w0; p.prof[4] = w1; p.prof[5] = w2; p.prof[6] = w3; p.prof[10] = total; p.prof[12] = w4; p.prof[13] = w5; p.prof[14] = w6; p.prof[15] = w7; }
+        if (warp == 2) { p.prof[7] = w0; p.prof[8] = w1; p.prof[9] = w2; p.prof[11] = total; }
     }
-    (void)w4; (void)w5;
+    (void)w4; (void)w5; (void)w6; (void)w7;
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
@@ -646,13 +658,19 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
     if (f.p.rows <= 0) return cudaSuccess;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fused_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
-    fused_mlp_kernel<<<grid, 64 + 32 * f.p.epi_warps, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1],
-                                                               f.map_w[f.p.n_layers > 2 ? 2 : 1], f.p);
+    const unsigned threads = 64 + 32 * f.p.epi_warps;
+    const CUtensorMap& w2 = f.map_w[f.p.n_layers > 2 ? 2 : 1];
+    if (f.p.prof)   // instrumented build of the same kernel (dsat_profile_fused)
+        fused_mlp_kernel<true><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], w2, f.p);
+    else
+        fused_mlp_kernel<false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], w2, f.p);
     return cudaGetLastError();
 }
 

@@ -12,4 +12,4 @@ for w in range(5):
     tiles = {0: chains * 100, 1: chains * 100, 2: chains * len(cl), 3: chains * 100, 4: chains * 100}[w] / 128 / 148
     print("%-8s total %8d cyc (%.0f cyc/tile) | producer: ah_free %4.1f%% ring_empty %4.1f%% | mma: tmem_empty %4.1f%% a_full %4.1f%% h_full %4.1f%% ring_full %4.1f%% | epi: tmem_full %4.1f%% hidden %4.1f%% final %4.1f%%"
           % (names[w], tot, tot / tiles, 100 * c[1] / tot, 100 * c[2] / tot, 100 * c[3] / tot, 100 * c[4] / tot, 100 * c[5] / tot,
-             100 * c[6] / tot, 100 * c[7] / tot, 100 * c[8] / tot, 100 * c[9] / tot), "| mma issue %4.1f%% commit %4.1f%% | epi: ld wait %4.1f%% process %4.1f%%" % (100 * c[12] / tot, 100 * c[13] / tot, 100 * c[14] / tot, 100 * c[15] / tot))
+             100 * c[6] / tot, 100 * c[7] / tot, 100 * c[8] / tot, 100 * c[9] / tot), "| mma issue %4.1f%% commit %4.1f%% | mma k-loop total %4.1f%% tile commit %4.1f%%" % (100 * c[12] / tot, 100 * c[13] / tot, 100 * c[14] / tot, 100 * c[15] / tot))
