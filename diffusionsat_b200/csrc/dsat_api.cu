@@ -292,6 +292,7 @@ int ensure_tc_buffers(dsat_ctx* c) {
             f.p.a_box_rows = c->a_box_rows[a_op];
             f.p.qmaps = Q;
             f.p.prof = nullptr;
+            f.p.dbg = getenv("DSAT_FM_DEBUG") ? atoi(getenv("DSAT_FM_DEBUG")) : 0;   // timing experiments only, results are garbage
             f.p.out = out;
             int i = 0;
             for (const L& l : layers) {
@@ -305,6 +306,8 @@ int ensure_tc_buffers(dsat_ctx* c) {
             {   // input ring per MLP: DSAT_A_RING is a bit mask over (query, literal, clause, update, output)
                 static const int mask = getenv("DSAT_A_RING") ? atoi(getenv("DSAT_A_RING")) : 0x1d;
                 f.stream_input = ((mask >> which) & 1) != 0;
+                static const int pp_mask = getenv("DSAT_PING_PONG") ? atoi(getenv("DSAT_PING_PONG")) : 0x1f;
+                f.ping_pong = ((pp_mask >> which) & 1) != 0;
             }
             if (!fm::plan_fused(f)) return false;
             f.pair_ok = fm2::pair_supported(f) && f.pp.slots >= 2;

@@ -76,27 +76,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// Predicated forms for a warp that runs its issue loop converged (all 32 lanes execute the same control flow, only
-// the lane with issue != 0 issues).  Inside an `if (lane == 0)` region the compiler has to wrap every uniform-register
+// Forms for a warp that runs its issue loop converged (all 32 lanes execute the same control flow, the lane picked
+// by elect.sync issues).  Inside an `if (lane == 0)` region the compiler has to wrap every uniform-register
 // operand of UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, and that single thread's instruction
 // stream was the critical path of the fused MLP kernels (~560 cycles of overhead per four MMAs).
-__device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p, q;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "setp.ne.b32 q, %5, 0;\n"
+        "elect.sync _|q, 0xffffffff;\n"
         "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tcgen05_commit_if(uint32_t issue, uint64_t* bar) {
+__device__ __forceinline__ void tcgen05_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n"
         ".reg .pred q;\n"
-        "setp.ne.b32 q, %1, 0;\n"
+        "elect.sync _|q, 0xffffffff;\n"
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(issue) : "memory");
+        "}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):

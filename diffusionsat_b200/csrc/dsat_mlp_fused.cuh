@@ -15,6 +15,10 @@
 //                   input ring  : (a_slots > 0) the 64-column blocks of the input tile stream through their own ring
 //                                 instead of resting in AH, so the next tile's input is fetched while this tile's
 //                                 later layers and epilogues still run (AH then holds hidden activations only)
+//                   ping-pong   : (pp) two tiles are in flight, tile parity s owns accumulator half s and hidden region
+//                                 H[s]; the MMA warp issues L1(A) L1(B) L2(A) L2(B) ..., so every epilogue of one tile
+//                                 runs under an MMA phase of the other (the final epilogue stages through its own,
+//                                 by then dead, H[s])
 // mbarriers:  a_full (TMA->MMA, per tile)      ah_free (MMA->TMA, AH may take the next input tile)
 //             ring full/empty (TMA<->MMA)       tmem_full[buf] (MMA->epilogue)   tmem_empty[buf] (epilogue->MMA)
 //             h_full (epilogue->MMA, hidden activations of a layer are in shared memory)
@@ -52,6 +56,9 @@ struct FmParams {
     int n_layers;
     FmLayer layer[MAX_LAYERS];
     int rows, n_tiles, a_box_rows, ah_blocks, slots, slot_bytes, two_bufs, qmaps;
+    int dbg;               // experiments only (DSAT_FM_DEBUG): bit 0 = epilogues do no work (results are garbage)
+    int pp;                // ping-pong: two tiles in flight (needs a_slots > 0 and two_bufs)
+    int stage_in_h;        // pp: the output staging of a tile aliases its hidden region
     int a_slots;           // > 0: layer 0's A operand streams through an input ring of that many 16 KB blocks
     int a_split_kb;        // k-blocks >= a_split_kb of the INPUT tile come from map_a2 (panel-major source), 1<<20 = never
     long long a2_panel_rows;  // rows per 64-column panel of that source
@@ -268,6 +275,7 @@ struct EpiCtx {           // loop-invariant scalars of one (tile, layer) epilogu
     size_t row_first; int rows_left;
     void* ptr0; void* ptr1; int ld0, ld1, bf0, bf1, split;
     long long out0_panel_rows;
+    bool skip;
 };
 
 template <bool HIDDEN>
@@ -329,6 +337,10 @@ __device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&ra
 template <bool HIDDEN>
 __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint64_t* tmem_empty_bar) {
     bool released = false;
+    if (e.skip) {          // timing experiment: hand everything back without touching the accumulator
+        if (!HIDDEN) { tc::tcgen05_fence_before(); mbar_arrive(tmem_empty_bar); }
+        return;
+    }
 #pragma unroll 1
     for (int c = 32 * e.cpar; c < e.N; c += e.cstep) {
         uint32_t ra[32];
@@ -353,18 +365,19 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* ah = smem;
-    uint8_t* a_ring = smem + (size_t)p.ah_blocks * AH_BLOCK_BYTES;
+    const size_t h_bytes = (size_t)p.ah_blocks * AH_BLOCK_BYTES;          // one AH / hidden region
+    uint8_t* a_ring = smem + (p.pp ? 2 : 1) * h_bytes;
     uint8_t* ring = a_ring + (size_t)p.a_slots * AH_BLOCK_BYTES;
     uint8_t* stage_all = ring + (size_t)p.slots * p.slot_bytes;
-    uint8_t* tail = stage_all + (size_t)p.epi_warps * 32 * p.stage_row;
+    uint8_t* tail = stage_all + (p.stage_in_h ? 0 : (size_t)p.epi_warps * 32 * p.stage_row);
     uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
     uint64_t* ah_free = a_full + 1;
-    uint64_t* h_full = a_full + 2;
-    uint64_t* tmem_full = a_full + 3;                  // [2]
-    uint64_t* tmem_empty = a_full + 5;                 // [2]
-    uint64_t* ring_full = a_full + 7;                  // [MAX_SLOTS]
-    uint64_t* ring_empty = a_full + 7 + MAX_SLOTS;     // [MAX_SLOTS]
-    uint64_t* a_ring_full = a_full + 7 + 2 * MAX_SLOTS;                  // [MAX_A_SLOTS]
+    uint64_t* h_full = a_full + 2;                     // [2]
+    uint64_t* tmem_full = a_full + 4;                  // [2]
+    uint64_t* tmem_empty = a_full + 6;                 // [2]
+    uint64_t* ring_full = a_full + 8;                  // [MAX_SLOTS]
+    uint64_t* ring_empty = a_full + 8 + MAX_SLOTS;     // [MAX_SLOTS]
+    uint64_t* a_ring_full = a_full + 8 + 2 * MAX_SLOTS;                  // [MAX_A_SLOTS]
     uint64_t* a_ring_empty = a_ring_full + MAX_A_SLOTS;                  // [MAX_A_SLOTS]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ring_empty + MAX_A_SLOTS);
     float* bias_s = reinterpret_cast<float*>(tail + BAR_BYTES);
@@ -379,8 +392,11 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         mbar_init(ah_free, 1);
-        mbar_init(h_full, epi_threads);
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], epi_threads); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&h_full[b], epi_threads);
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], epi_threads);
+        }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
         for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_ring_full[s], 1); mbar_init(&a_ring_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -406,103 +422,127 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_layers = p.n_layers;
+    // This CTA's tiles are blockIdx.x + j * gridDim.x, j < nt.  All three roles walk the same sequence of
+    // (tile, layer) steps: tile by tile, or (pp) in groups of two tiles with the layers interleaved
+    // L1(A) L1(B) L2(A) L2(B) ...  For step (j, l) with s = j & 1 inside its group:
+    //   pp    : accumulator half s, hidden region s, both used once per layer and group
+    //   else  : accumulator half alternates per step when every layer fits 256 columns, one hidden region
+    const int nt = blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int group = p.pp ? 2 : 1;
+    struct Step { int tile, buf, use, hidx, hcnt; };
+    auto make_step = [&](int j0, int s, int l) {
+        Step st;
+        const int j = j0 + s;
+        st.tile = (int)blockIdx.x + j * (int)gridDim.x;
+        if (p.pp) {
+            st.buf = s; st.use = (j0 >> 1) * n_layers + l;
+            st.hidx = s; st.hcnt = (j0 >> 1) * (n_layers - 1) + (l - 1);
+        } else {
+            const int g = j * n_layers + l;
+            st.buf = p.two_bufs ? (g & 1) : 0; st.use = p.two_bufs ? (g >> 1) : g;
+            st.hidx = 0; st.hcnt = j * (n_layers - 1) + (l - 1);
+        }
+        return st;
+    };
 
     if (warp == 0) {
         if (lane == 0) {   // ================================ TMA producer
             const int k0_blocks = (p.layer[0].K + BLOCK_K - 1) / BLOCK_K;
             int slot = 0; uint32_t phase = 0;
             int aslot = 0; uint32_t aphase = 0;
-            int it = 0;
             auto load_a_block = [&](uint8_t* dst, uint64_t* bar, int kb, int tile) {
                 if (kb < p.a_split_kb)
                     tma_load_2d(dst, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
                 else         // panel-major source: panel (kb - a_split_kb) is a dense [rows, 64] matrix
                     tma_load_2d(dst, &map_a2, bar, 0, (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
             };
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                if (p.a_slots == 0) {
-                    if (it > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((it - 1) & 1)));   // tile it-1 no longer reads AH
-                    mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
-                    for (int kb = 0; kb < k0_blocks; ++kb) load_a_block(ah + (size_t)kb * AH_BLOCK_BYTES, a_full, kb, tile);
-                }
-                for (int l = 0; l < n_layers; ++l) {
-                    const int kbs = (p.layer[l].K + BLOCK_K - 1) / BLOCK_K;
-                    const int halves = (p.layer[l].N + 255) / 256;
-                    for (int kb = 0; kb < kbs; ++kb) {
-                        if (l == 0 && p.a_slots > 0) {     // input block kb of this tile into the input ring
-                            DSAT_TIMED_WAIT(w0, mbar_wait(&a_ring_empty[aslot], aphase ^ 1));
-                            mbar_expect_tx(&a_ring_full[aslot], (uint32_t)p.a_box_rows * (BLOCK_K * 2));
-                            load_a_block(a_ring + (size_t)aslot * AH_BLOCK_BYTES, &a_ring_full[aslot], kb, tile);
-                            if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+            for (int j0 = 0; j0 < nt; j0 += group)
+                for (int l = 0; l < n_layers; ++l)
+                    for (int s = 0; s < group; ++s) {
+                        if (j0 + s >= nt) continue;
+                        const int j = j0 + s, tile = (int)blockIdx.x + j * (int)gridDim.x;
+                        if (l == 0 && p.a_slots == 0) {      // whole input tile into AH
+                            if (j > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((j - 1) & 1)));   // tile j-1 no longer reads AH
+                            mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
+                            for (int kb = 0; kb < k0_blocks; ++kb) load_a_block(ah + (size_t)kb * AH_BLOCK_BYTES, a_full, kb, tile);
                         }
-                        for (int h = 0; h < halves; ++h) {
-                            DSAT_TIMED_WAIT(w1, mbar_wait(&ring_empty[slot], phase ^ 1));
-                            mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[l].box_rows * (BLOCK_K * 2));
-                            tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K, h * 256);
-                            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+                        const int kbs = (p.layer[l].K + BLOCK_K - 1) / BLOCK_K;
+                        const int halves = (p.layer[l].N + 255) / 256;
+                        for (int kb = 0; kb < kbs; ++kb) {
+                            if (l == 0 && p.a_slots > 0) {     // input block kb of this tile into the input ring
+                                DSAT_TIMED_WAIT(w0, mbar_wait(&a_ring_empty[aslot], aphase ^ 1));
+                                mbar_expect_tx(&a_ring_full[aslot], (uint32_t)p.a_box_rows * (BLOCK_K * 2));
+                                load_a_block(a_ring + (size_t)aslot * AH_BLOCK_BYTES, &a_ring_full[aslot], kb, tile);
+                                if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+                            }
+                            for (int h = 0; h < halves; ++h) {
+                                DSAT_TIMED_WAIT(w1, mbar_wait(&ring_empty[slot], phase ^ 1));
+                                mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[l].box_rows * (BLOCK_K * 2));
+                                tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K, h * 256);
+                                if (++slot == p.slots) { slot = 0; phase ^= 1; }
+                            }
                         }
                     }
-                }
-            }
         }
     } else if (warp == 1) {
-        {                  // ================================ MMA issuer: the whole warp runs the loop converged, lane 0 issues
-            const uint32_t leader = lane == 0;
+        {                  // ================================ MMA issuer: the whole warp runs the loop converged, one lane issues
             int slot = 0; uint32_t phase = 0;
             int aslot = 0; uint32_t aphase = 0;
-            int it = 0, g = 0, hcount = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-                for (int l = 0; l < n_layers; ++l, ++g) {
-                    const int buf = p.two_bufs ? (g & 1) : 0;
-                    const int use = p.two_bufs ? (g >> 1) : g;
-                    DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_empty[buf], (uint32_t)((use & 1) ^ 1)));   // accumulator drained
-                    const bool streamed = l == 0 && p.a_slots > 0;
-                    if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, mbar_wait(a_full, (uint32_t)(it & 1))); }
-                    else { DSAT_TIMED_WAIT(w2, mbar_wait(h_full, (uint32_t)(hcount & 1))); ++hcount; }
-                    tcgen05_fence_after();
-                    const int K = p.layer[l].K, N = p.layer[l].N;
-                    const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
-                    const int halves = (N + 255) / 256;
-                    const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
-                    const long long t_kb0 = timing ? clock64() : 0;
-                    for (int kb = 0; kb < kbs; ++kb) {
-                        if (streamed) { DSAT_TIMED_WAIT(w1, mbar_wait(&a_ring_full[aslot], aphase)); tcgen05_fence_after(); }
-                        const uint64_t da = make_smem_desc_sw128(smem_u32(streamed ? a_ring + (size_t)aslot * AH_BLOCK_BYTES
-                                                                                   : ah + (size_t)kb * AH_BLOCK_BYTES));
-                        const int ksteps = min(BLOCK_K / 16, (K - kb * BLOCK_K + 15) / 16);
-                        for (int h = 0; h < halves; ++h) {
-                            const int bn = min(256, N - h * 256);
-                            const uint32_t idesc = make_idesc_bf16(BLOCK_M, bn);
-                            DSAT_TIMED_WAIT(w3, mbar_wait(&ring_full[slot], phase));
-                            tcgen05_fence_after();
-                            const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
-                            const long long t_i0 = timing ? clock64() : 0;
-                            const uint32_t acc_h = acc + (uint32_t)(h * 256);
-                            if (ksteps == BLOCK_K / 16) {       // 16 bf16 = 32 bytes along K: +2 in the (>>4) address field
-                                umma_bf16_if(leader, acc_h, da, db, idesc, kb != 0);
-                                umma_bf16_if(leader, acc_h, da + 2, db + 2, idesc, 1);
-                                umma_bf16_if(leader, acc_h, da + 4, db + 4, idesc, 1);
-                                umma_bf16_if(leader, acc_h, da + 6, db + 6, idesc, 1);
-                            } else {
-                                for (int k = 0; k < ksteps; ++k)
-                                    umma_bf16_if(leader, acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int j0 = 0; j0 < nt; j0 += group)
+                for (int l = 0; l < n_layers; ++l)
+                    for (int s = 0; s < group; ++s) {
+                        if (j0 + s >= nt) continue;
+                        const Step st = make_step(j0, s, l);
+                        const int j = j0 + s;
+                        DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_empty[st.buf], (uint32_t)((st.use & 1) ^ 1)));   // accumulator drained
+                        const bool streamed = l == 0 && p.a_slots > 0;
+                        if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, mbar_wait(a_full, (uint32_t)(j & 1))); }
+                        else DSAT_TIMED_WAIT(w2, mbar_wait(&h_full[st.hidx], (uint32_t)(st.hcnt & 1)));
+                        tcgen05_fence_after();
+                        const int K = p.layer[l].K, N = p.layer[l].N;
+                        const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
+                        const int halves = (N + 255) / 256;
+                        const uint32_t acc = tmem_base + (uint32_t)(st.buf * 256);
+                        const uint8_t* a_src = ah + (size_t)st.hidx * h_bytes;
+                        const long long t_kb0 = timing ? clock64() : 0;
+                        for (int kb = 0; kb < kbs; ++kb) {
+                            // (no tcgen05 fence after the ring waits: TMA writes and MMA reads are both async-proxy accesses
+                            //  ordered by the mbarrier; the fences that matter are the per-step ones above)
+                            if (streamed) { DSAT_TIMED_WAIT(w1, mbar_wait(&a_ring_full[aslot], aphase)); }
+                            const uint64_t da = make_smem_desc_sw128(smem_u32(streamed ? a_ring + (size_t)aslot * AH_BLOCK_BYTES
+                                                                                       : a_src + (size_t)kb * AH_BLOCK_BYTES));
+                            const int ksteps = min(BLOCK_K / 16, (K - kb * BLOCK_K + 15) / 16);
+                            for (int h = 0; h < halves; ++h) {
+                                const int bn = min(256, N - h * 256);
+                                const uint32_t idesc = make_idesc_bf16(BLOCK_M, bn);
+                                DSAT_TIMED_WAIT(w3, mbar_wait(&ring_full[slot], phase));
+                                const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
+                                const long long t_i0 = timing ? clock64() : 0;
+                                const uint32_t acc_h = acc + (uint32_t)(h * 256);
+                                if (ksteps == BLOCK_K / 16) {       // 16 bf16 = 32 bytes along K: +2 in the (>>4) address field
+                                    umma_bf16_elect(acc_h, da, db, idesc, kb != 0);
+                                    umma_bf16_elect(acc_h, da + 2, db + 2, idesc, 1);
+                                    umma_bf16_elect(acc_h, da + 4, db + 4, idesc, 1);
+                                    umma_bf16_elect(acc_h, da + 6, db + 6, idesc, 1);
+                                } else {
+                                    for (int k = 0; k < ksteps; ++k)
+                                        umma_bf16_elect(acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                                }
+                                const long long t_i1 = timing ? clock64() : 0;
+                                tcgen05_commit_elect(&ring_empty[slot]);
+                                if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
+                                if (++slot == p.slots) { slot = 0; phase ^= 1; }
                             }
-                            const long long t_i1 = timing ? clock64() : 0;
-                            tcgen05_commit_if(leader, &ring_empty[slot]);
-                            if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
-                            if (++slot == p.slots) { slot = 0; phase ^= 1; }
+                            if (streamed) {
+                                tcgen05_commit_elect(&a_ring_empty[aslot]);
+                                if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+                            }
                         }
-                        if (streamed) {
-                            tcgen05_commit_if(leader, &a_ring_empty[aslot]);
-                            if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
-                        }
+                        const long long t_kb1 = timing ? clock64() : 0;
+                        tcgen05_commit_elect(&tmem_full[st.buf]);
+                        if (l == n_layers - 1 && p.a_slots == 0) tcgen05_commit_elect(ah_free);
+                        if (timing) { w6 += t_kb1 - t_kb0; w7 += clock64() - t_kb1; }
                     }
-                    const long long t_kb1 = timing ? clock64() : 0;
-                    tcgen05_commit_if(leader, &tmem_full[buf]);
-                    if (l == n_layers - 1 && p.a_slots == 0) tcgen05_commit_if(leader, ah_free);
-                    if (timing) { w6 += t_kb1 - t_kb0; w7 += clock64() - t_kb1; }
-                }
-            }
         }
     } else {               // ================================ epilogue warps (4 or 8)
         const int quad = warp & 3;
@@ -512,40 +552,41 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         e.cpar = (warp - 2) >> 2;                          // which 32-column chunks of the quadrant this warp takes
         e.cstep = 32 * (p.epi_warps >> 2);
         e.stage_row = p.stage_row;
-        e.stage_addr = smem_u32(stage_all) + (uint32_t)(warp - 2) * (32 * p.stage_row);
-        e.ah_addr = smem_u32(ah);
         e.qmaps = p.qmaps;
+        e.skip = (p.dbg & 1) != 0;
         e.ptr0 = p.out.ptr0; e.ptr1 = p.out.ptr1; e.ld0 = p.out.ld0; e.ld1 = p.out.ld1;
         e.bf0 = p.out.bf16_0; e.bf1 = p.out.bf16_1; e.split = p.out.split;
         e.out0_panel_rows = p.out0_panel_rows;
         const uint32_t bias_addr0 = smem_u32(bias_s);
-        int g = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            e.row_first = (size_t)tile * BLOCK_M + quad * 32;
-            e.rows_left = p.rows - (int)e.row_first;
-            for (int l = 0; l < n_layers; ++l, ++g) {
-                const int buf = p.two_bufs ? (g & 1) : 0;
-                const int use = p.two_bufs ? (g >> 1) : g;
-                e.N = p.layer[l].N; e.epi = p.layer[l].epi;
-                e.bl_addr = bias_addr0 + 4u * (uint32_t)p.layer[l].bias_off;
-                e.blb_addr = bias_addr0 + 4u * (uint32_t)p.bias_total + 2u * (uint32_t)p.layer[l].bias_off;
-                e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
-                DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_full[buf], (uint32_t)(use & 1)));
-                tcgen05_fence_after();
-                const long long t_epi0 = timing ? clock64() : 0;
-                if (l + 1 < n_layers) {
-                    epi_drain<true>(e, &tmem_empty[buf]);
-                    tcgen05_fence_before();
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the MMA (async proxy)
-                    mbar_arrive(&tmem_empty[buf]);
-                    mbar_arrive(h_full);
-                    if (timing) w1 += clock64() - t_epi0;
-                } else {
-                    epi_drain<false>(e, &tmem_empty[buf]);
-                    if (timing) w2 += clock64() - t_epi0;
+        const uint32_t stage_off = (uint32_t)(warp - 2) * (32 * p.stage_row);
+        for (int j0 = 0; j0 < nt; j0 += group)
+            for (int l = 0; l < n_layers; ++l)
+                for (int s = 0; s < group; ++s) {
+                    if (j0 + s >= nt) continue;
+                    const Step st = make_step(j0, s, l);
+                    e.row_first = (size_t)st.tile * BLOCK_M + quad * 32;
+                    e.rows_left = p.rows - (int)e.row_first;
+                    e.ah_addr = smem_u32(ah + (size_t)st.hidx * h_bytes);
+                    e.stage_addr = (p.stage_in_h ? e.ah_addr : smem_u32(stage_all)) + stage_off;
+                    e.N = p.layer[l].N; e.epi = p.layer[l].epi;
+                    e.bl_addr = bias_addr0 + 4u * (uint32_t)p.layer[l].bias_off;
+                    e.blb_addr = bias_addr0 + 4u * (uint32_t)p.bias_total + 2u * (uint32_t)p.layer[l].bias_off;
+                    e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st.buf * 256);
+                    DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_full[st.buf], (uint32_t)(st.use & 1)));
+                    tcgen05_fence_after();
+                    const long long t_epi0 = timing ? clock64() : 0;
+                    if (l + 1 < n_layers) {
+                        epi_drain<true>(e, &tmem_empty[st.buf]);
+                        tcgen05_fence_before();
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the MMA (async proxy)
+                        mbar_arrive(&tmem_empty[st.buf]);
+                        mbar_arrive(&h_full[st.hidx]);
+                        if (timing) w1 += clock64() - t_epi0;
+                    } else {
+                        epi_drain<false>(e, &tmem_empty[st.buf]);
+                        if (timing) w2 += clock64() - t_epi0;
+                    }
                 }
-            }
-        }
     }
     if (timing && lane == 0 && (warp == 0 || warp == 1 || warp == 2)) {
         // [0] kernel cycles; producer: [1] ah_free wait [2] ring_empty wait; MMA: [3] tmem_empty wait [4] a_full wait
@@ -575,6 +616,7 @@ struct FusedMlp {
     int smem_bytes_pair;
     bool pair_ok;
     bool stream_input = false;      // request the input ring (FmParams::a_slots), set before plan_fused
+    bool ping_pong = false;         // request two tiles in flight (FmParams::pp); needs stream_input
 };
 
 // shared-memory plan; returns false when the MLP does not fit
@@ -584,6 +626,8 @@ inline bool plan_fused(FusedMlp& f) {
     int bias_total = 0, max_box = 0;
     p.two_bufs = 1;
     p.a_slots = 0;
+    p.pp = 0;
+    p.stage_in_h = 0;
     for (int l = 0; l < p.n_layers; ++l) {
         if (l + 1 < p.n_layers) blocks = max(blocks, (p.layer[l].N + 63) / 64);
         p.layer[l].bias_off = bias_total;
@@ -616,6 +660,28 @@ inline bool plan_fused(FusedMlp& f) {
         int h_blocks = 1;
         for (int l = 0; l + 1 < p.n_layers; ++l) h_blocks = max(h_blocks, (p.layer[l].N + 63) / 64);
         const int k0_blocks = (p.layer[0].K + 63) / 64;
+        auto finish_pair_plan = [&]() {
+            f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs; f.pp.ah_blocks = blocks;
+            for (int l = 0; l < p.n_layers; ++l) f.pp.layer[l].bias_off = p.layer[l].bias_off;
+        };
+        if (f.ping_pong && p.two_bufs) {
+            // two tiles in flight: two hidden regions; a tile's output staging aliases its own hidden region when it fits
+            for (int ew : {8, 4}) {
+                const int h_bytes = h_blocks * AH_BLOCK_BYTES, stage_bytes = ew * 32 * p.stage_row;
+                const int in_h = stage_bytes <= h_bytes;
+                const int fixed = 1024 + 2 * h_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 6;
+                int a_slots = (SMEM_LIMIT - fixed - 2 * p.slot_bytes) / AH_BLOCK_BYTES;
+                if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
+                if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
+                if (SMEM_LIMIT - fixed - 2 * p.slot_bytes < 0 || a_slots < 2) continue;
+                p.pp = 1; p.stage_in_h = in_h; p.a_slots = a_slots; p.epi_warps = ew; p.ah_blocks = h_blocks;
+                const int base = fixed + a_slots * AH_BLOCK_BYTES;
+                for (int slots = MAX_SLOTS; slots >= 2; --slots)
+                    if (base + slots * p.slot_bytes <= SMEM_LIMIT) { p.slots = slots; f.smem_bytes = base + slots * p.slot_bytes; break; }
+                finish_pair_plan();
+                return true;
+            }
+        }
         for (int ew : {8, 4}) {
             const int fixed = 1024 + h_blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 6;
             int a_slots = (SMEM_LIMIT - fixed) / AH_BLOCK_BYTES;
