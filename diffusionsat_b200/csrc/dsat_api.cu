@@ -310,6 +310,10 @@ int ensure_tc_buffers(dsat_ctx* c) {
                 f.ping_pong = ((pp_mask >> which) & 1) != 0;
             }
             if (!fm::plan_fused(f)) return false;
+            if (getenv("DSAT_PLAN_LOG"))
+                fprintf(stderr, "[dsat] fused mlp %d: smem %d B (pad %d), hidden blocks %d x%d, input ring %d, weight ring %d x %d B, "
+                        "epilogue warps %d, ping-pong %d, staging in hidden %d\n", which, f.smem_bytes, f.p.smem_pad, f.p.ah_blocks,
+                        f.p.pp ? 2 : 1, f.p.a_slots, f.p.slots, f.p.slot_bytes, f.p.epi_warps, f.p.pp, f.p.stage_in_h);
             f.pair_ok = fm2::pair_supported(f) && f.pp.slots >= 2;
             return true;
         };

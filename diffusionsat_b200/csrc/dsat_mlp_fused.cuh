@@ -64,7 +64,8 @@ struct FmParams {
     long long a2_panel_rows;  // rows per 64-column panel of that source
     long long out0_panel_rows;   // > 0: output columns [0, split) go to 64-column panels of this many rows (bf16)
     int stage_row;         // bytes per staged output row: 80 when every output is bf16 (64 B + pad), else 144
-    int bias_total;        // floats in the shared bias array (a bf16 copy follows it)
+    int bias_total;        // floats in the shared bias array
+    int smem_pad;          // bytes the plan reserved for aligning the dynamic shared memory base to 1024
     int epi_warps;         // 4 or 8 epilogue warps: with 8, two warps share a TMEM lane quadrant and alternate 32-column chunks
     TcOut out;
     long long* prof;       // optional [16] cycle counters of CTA 0 (wait/work breakdown), nullptr = off
@@ -270,7 +271,7 @@ __device__ __forceinline__ void store_chunk_coalesced(uint8_t* stage, int lane, 
 
 
 struct EpiCtx {           // loop-invariant scalars of one (tile, layer) epilogue, all in registers
-    uint32_t lane_addr, ah_addr, bl_addr, blb_addr, stage_addr;
+    uint32_t lane_addr, ah_addr, bl_addr, stage_addr;
     int N, epi, cpar, cstep, r, lane, qmaps, stage_row;
     size_t row_first; int rows_left;
     void* ptr0; void* ptr1; int ld0, ld1, bf0, bf1, split;
@@ -362,8 +363,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                  const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, FmParams p) {
     using namespace tc;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if ((int)(smem - smem_raw) > p.smem_pad) __trap();     // the plan assumed a better aligned base (dyn_smem_pad)
     uint8_t* ah = smem;
     const size_t h_bytes = (size_t)p.ah_blocks * AH_BLOCK_BYTES;          // one AH / hidden region
     uint8_t* a_ring = smem + (p.pp ? 2 : 1) * h_bytes;
@@ -412,9 +414,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp >= 2) {
         for (int l = 0; l < p.n_layers; ++l)
             for (int i = threadIdx.x - 64; i < p.layer[l].N; i += epi_threads) {
-                const float b = __ldg(p.layer[l].bias + i);
-                bias_s[p.layer[l].bias_off + i] = b;
-                reinterpret_cast<__nv_bfloat16*>(bias_s + p.bias_total)[p.layer[l].bias_off + i] = __float2bfloat16_rn(b);
+                bias_s[p.layer[l].bias_off + i] = __ldg(p.layer[l].bias + i);
             }
     }
     tcgen05_fence_before();
@@ -519,17 +519,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                                 const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
                                 const long long t_i0 = timing ? clock64() : 0;
                                 const uint32_t acc_h = acc + (uint32_t)(h * 256);
-                                if (ksteps == BLOCK_K / 16) {       // 16 bf16 = 32 bytes along K: +2 in the (>>4) address field
-                                    umma_bf16_elect(acc_h, da, db, idesc, kb != 0);
-                                    umma_bf16_elect(acc_h, da + 2, db + 2, idesc, 1);
-                                    umma_bf16_elect(acc_h, da + 4, db + 4, idesc, 1);
-                                    umma_bf16_elect(acc_h, da + 6, db + 6, idesc, 1);
+                                if (ksteps == BLOCK_K / 16) {       // full K block: four MMAs and the slot's commit in one go
+                                    umma_bf16_kblock_commit_elect(acc_h, da, db, idesc, kb != 0, &ring_empty[slot]);
                                 } else {
                                     for (int k = 0; k < ksteps; ++k)
                                         umma_bf16_elect(acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                                    tcgen05_commit_elect(&ring_empty[slot]);
                                 }
                                 const long long t_i1 = timing ? clock64() : 0;
-                                tcgen05_commit_elect(&ring_empty[slot]);
                                 if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
                                 if (++slot == p.slots) { slot = 0; phase ^= 1; }
                             }
@@ -570,7 +567,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     e.stage_addr = (p.stage_in_h ? e.ah_addr : smem_u32(stage_all)) + stage_off;
                     e.N = p.layer[l].N; e.epi = p.layer[l].epi;
                     e.bl_addr = bias_addr0 + 4u * (uint32_t)p.layer[l].bias_off;
-                    e.blb_addr = bias_addr0 + 4u * (uint32_t)p.bias_total + 2u * (uint32_t)p.layer[l].bias_off;
                     e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st.buf * 256);
                     DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_full[st.buf], (uint32_t)(st.use & 1)));
                     tcgen05_fence_after();
@@ -619,10 +615,33 @@ struct FusedMlp {
     bool ping_pong = false;         // request two tiles in flight (FmParams::pp); needs stream_input
 };
 
+// Dynamic shared memory has to start on a 1024-byte boundary (SWIZZLE_128B atoms).  The base is that well aligned in
+// practice; a one-off probe checks it so that the plans do not have to give up 1 KB (the clause MLP's ping-pong plan
+// fits with a few hundred bytes to spare).  The kernel traps if a base ever needs more than the planned pad.
+__global__ void smem_base_probe_kernel(unsigned* out) {
+    extern __shared__ __align__(1024) uint8_t probe_raw[];
+    *out = tc::smem_u32(probe_raw);
+}
+inline int dyn_smem_pad() {
+    static int pad = -1;
+    if (pad >= 0) return pad;
+    pad = 1024;
+    unsigned* dev = nullptr;
+    unsigned host = 1;
+    if (cudaMalloc(&dev, sizeof(unsigned)) != cudaSuccess) return pad;
+    cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    smem_base_probe_kernel<<<1, 1, SMEM_LIMIT>>>(dev);
+    if (cudaMemcpy(&host, dev, sizeof(unsigned), cudaMemcpyDeviceToHost) == cudaSuccess && (host & 1023u) == 0) pad = 0;
+    cudaFree(dev);
+    return pad;
+}
+
 // shared-memory plan; returns false when the MLP does not fit
 inline bool plan_fused(FusedMlp& f) {
     FmParams& p = f.p;
     int blocks = (p.layer[0].K + 63) / 64;
+    const int pad = dyn_smem_pad();
+    p.smem_pad = pad;
     int bias_total = 0, max_box = 0;
     p.two_bufs = 1;
     p.a_slots = 0;
@@ -644,7 +663,7 @@ inline bool plan_fused(FusedMlp& f) {
     f.pp.slot_bytes = (max_box / 2 * BLOCK_K * 2 + 1023) / 1024 * 1024;
     f.pp.slots = 0;
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * f.pp.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 6;
+        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * f.pp.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 4;
         if (total <= SMEM_LIMIT) { f.pp.slots = slots; f.smem_bytes_pair = total; break; }
     }
     {
@@ -669,7 +688,7 @@ inline bool plan_fused(FusedMlp& f) {
             for (int ew : {8, 4}) {
                 const int h_bytes = h_blocks * AH_BLOCK_BYTES, stage_bytes = ew * 32 * p.stage_row;
                 const int in_h = stage_bytes <= h_bytes;
-                const int fixed = 1024 + 2 * h_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 6;
+                const int fixed = pad + 2 * h_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4;
                 int a_slots = (SMEM_LIMIT - fixed - 2 * p.slot_bytes) / AH_BLOCK_BYTES;
                 if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
                 if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
@@ -683,7 +702,7 @@ inline bool plan_fused(FusedMlp& f) {
             }
         }
         for (int ew : {8, 4}) {
-            const int fixed = 1024 + h_blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 6;
+            const int fixed = pad + h_blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 4;
             int a_slots = (SMEM_LIMIT - fixed) / AH_BLOCK_BYTES;
             if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
             if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
@@ -701,14 +720,14 @@ inline bool plan_fused(FusedMlp& f) {
         }
     }
     for (int ew : {8, 4}) {     // prefer 8 epilogue warps when two ring slots still fit
-        if (1024 + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 6 <= SMEM_LIMIT) {
+        if (pad + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 4 <= SMEM_LIMIT) {
             p.epi_warps = ew;
             break;
         }
     }
     f.pp.epi_warps = 4;
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + p.epi_warps * 32 * p.stage_row + BAR_BYTES + bias_total * 6;
+        const int total = pad + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + p.epi_warps * 32 * p.stage_row + BAR_BYTES + bias_total * 4;
         if (total <= SMEM_LIMIT) {
             p.slots = slots;
             f.pp.ah_blocks = p.ah_blocks; f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs;
