@@ -794,7 +794,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
 #ifdef DSAT_WITH_TCGEN05
         else
-            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, PN_WARPS * 32, 0, c->stream>>>(
+            pairnorm_bf16_kernel<32 * V><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, panel_now(c) ? c->CNEWb.p : c->COUTb.p,
                 panel_now(c) ? F : Q + F, panel_now(c) ? 0 : Q, c->CROWb.p, ldc, nullptr, 0);
 #endif
@@ -828,7 +828,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
 #ifdef DSAT_WITH_TCGEN05
         else
-            pairnorm_kernel<V, __nv_bfloat16, __nv_bfloat16><<<grid, PN_WARPS * 32, 0, c->stream>>>(
+            pairnorm_bf16_kernel<32 * V><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUTb.p, F, 0, c->VROWb.p, ldv, c->SPREb.p, F);
 #endif
     });

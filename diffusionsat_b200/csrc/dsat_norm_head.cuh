@@ -121,6 +121,106 @@ __device__ __forceinline__ float bernoulli_kl(float pa, float pb) {
     return t1 + t2;
 }
 
+// bf16 storage on both sides (tensor-core path): a lane moves 16 bytes = 8 features, so a row takes F/8 lanes and a
+// warp load covers 32/(F/8) rows: half as many memory instructions per byte as the generic kernel's 8-byte lanes, and
+// PN_UNROLL row groups in flight give twice the bytes in flight per warp.  Same arithmetic (fp32), different summation
+// order than the generic kernel.
+template <int F>
+__global__ void __launch_bounds__(PN_WARPS * 32)
+pairnorm_bf16_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
+                     const __nv_bfloat16* __restrict__ SRC, int ld_src, int src_off,
+                     __nv_bfloat16* __restrict__ STATE, int ld_state,
+                     __nv_bfloat16* __restrict__ PRE, int ld_pre) {
+    constexpr int LPR = F / 8, RPW = 32 / LPR, GROUP = PN_WARPS * RPW;     // rows covered by one load of the whole CTA
+    __shared__ float red[PN_WARPS][F];
+    __shared__ float mean_s[F];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
+    for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
+        const int chain = gid / n_graphs_unit, lg = gid % n_graphs_unit;
+        const size_t base = (size_t)chain * rows_per_chain;
+        const size_t r0 = base + __ldg(seg + lg), r1 = base + __ldg(seg + lg + 1);
+        const float wgt = 1.0f / (float)(r1 - r0);
+        float sum[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+        // (loop bounds are warp-uniform: the row of a lane is rb + sub, guarded by rr < r1)
+        for (size_t rb = r0 + warp * RPW; rb < r1; rb += (size_t)PN_UNROLL * GROUP) {
+            const size_t r = rb + sub;
+            uint4 x[PN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PN_UNROLL; ++u) {
+                const size_t rr = r + (size_t)u * GROUP;
+                x[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (rr < r1) x[u] = __ldg(reinterpret_cast<const uint4*>(SRC + rr * ld_src + src_off) + li);
+            }
+#pragma unroll
+            for (int u = 0; u < PN_UNROLL; ++u) {
+                float v[8];
+                unpack8(x[u], v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sum[i] += v[i] * wgt;
+            }
+        }
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], off);
+        if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp][li * 8 + i] = sum[i];
+        }
+        __syncthreads();
+        for (int col = tid; col < F; col += PN_WARPS * 32) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < PN_WARPS; ++w) s += red[w][col];
+            mean_s[col] = s;
+        }
+        __syncthreads();
+        float mean[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mean[i] = mean_s[li * 8 + i];
+        for (size_t rb = r0 + warp * RPW; rb < r1; rb += (size_t)PN_UNROLL * GROUP) {
+            const size_t r = rb + sub;
+            uint4 x[PN_UNROLL], old[PN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PN_UNROLL; ++u) {
+                const size_t rr = r + (size_t)u * GROUP;
+                x[u] = make_uint4(0u, 0u, 0u, 0u); old[u] = x[u];
+                if (rr < r1) {
+                    x[u] = __ldg(reinterpret_cast<const uint4*>(SRC + rr * ld_src + src_off) + li);
+                    old[u] = reinterpret_cast<const uint4*>(STATE + rr * ld_state)[li];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PN_UNROLL; ++u) {
+                const size_t rr = r + (size_t)u * GROUP;
+                float v[8], o[8], nw[8], carried[8];
+                unpack8(x[u], v);
+                unpack8(old[u], o);
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[i] -= mean[i]; ss += v[i] * v[i]; }
+#pragma unroll
+                for (int off = LPR / 2; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                const float inv = rsqrtf(ss / (float)F + 1.0e-6f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    nw[i] = __fadd_rn(__fmul_rn(v[i] * inv, 0.25f), __fmul_rn(0.1f, o[i]));
+                    carried[i] = __fadd_rn(__fmul_rn(nw[i], 0.2f), __fmul_rn(nw[i], 0.8f));
+                }
+                if (rr < r1) {
+                    if (PRE) reinterpret_cast<uint4*>(PRE + rr * ld_pre)[li] = pack8(nw);
+                    reinterpret_cast<uint4*>(STATE + rr * ld_state)[li] = pack8(carried);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
 __device__ __forceinline__ int graph_clauses_unsat(const UnitGraphDev& g, int lg, size_t rowbase,
                                                    const unsigned char* bits, int tid, int nthreads) {
     int unsat = 0;
