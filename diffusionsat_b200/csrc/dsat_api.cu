@@ -19,7 +19,6 @@
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
 #include "dsat_mlp_fused.cuh"
-#include "dsat_mlp_pair.cuh"
 #include "dsat_message_tma.cuh"
 #endif
 
@@ -122,7 +121,6 @@ struct dsat_ctx {
     fm::FusedMlp fused[5];
     bool fused_ready = false;
     bool use_fused = true;
-    bool use_pair = false;            // cta_group::2 whole-MLP kernels (DSAT_MLP_PAIR=1)
     bool use_smem_gather = true;
     // panel layout of the clause-side intermediates on the fused bf16 path (contiguous gather tables):
     // CL4P / VMSGP [Q/64][M][64] (4*clauses_loss, message to literals), CNEWb [M, F] (new clause value)
@@ -308,13 +306,14 @@ int ensure_tc_buffers(dsat_ctx* c) {
                 f.stream_input = ((mask >> which) & 1) != 0;
                 static const int pp_mask = getenv("DSAT_PING_PONG") ? atoi(getenv("DSAT_PING_PONG")) : 0x1f;
                 f.ping_pong = ((pp_mask >> which) & 1) != 0;
+                static const int pair_mask = getenv("DSAT_PAIR_MODE") ? atoi(getenv("DSAT_PAIR_MODE")) : 0;
+                f.pair_mode = ((pair_mask >> which) & 1) != 0;
             }
             if (!fm::plan_fused(f)) return false;
             if (getenv("DSAT_PLAN_LOG"))
                 fprintf(stderr, "[dsat] fused mlp %d: smem %d B (pad %d), hidden blocks %d x%d, input ring %d, weight ring %d x %d B, "
-                        "epilogue warps %d, ping-pong %d, staging in hidden %d\n", which, f.smem_bytes, f.p.smem_pad, f.p.ah_blocks,
-                        f.p.pp ? 2 : 1, f.p.a_slots, f.p.slots, f.p.slot_bytes, f.p.epi_warps, f.p.pp, f.p.stage_in_h);
-            f.pair_ok = fm2::pair_supported(f) && f.pp.slots >= 2;
+                        "epilogue warps %d, ping-pong %d, staging in hidden %d, cta pair %d\n", which, f.smem_bytes, f.p.smem_pad, f.p.ah_blocks,
+                        f.p.pp ? 2 : 1, f.p.a_slots, f.p.slots, f.p.slot_bytes, f.p.epi_warps, f.p.pp, f.p.stage_in_h, f.p.pair);
             return true;
         };
         auto W = [&](int op) { return (const __nv_bfloat16*)c->ops[op].w_bf16.p; };
@@ -340,8 +339,7 @@ int ensure_tc_buffers(dsat_ctx* c) {
                                      {OP_O2, DSAT_LOGIT_PAD, W(OP_O2), B(OP_O2), tc::TC_LINEAR}}, o);
         c->fused_ready = ok;
         for (int i = 0; i < 5; ++i) { c->fused[i].map_a2 = c->fused[i].map_a; c->fused[i].p.a_split_kb = 1 << 20;
-                                      c->fused[i].p.a2_panel_rows = 0; c->fused[i].p.out0_panel_rows = 0;
-                                      c->fused[i].pp.a_split_kb = 1 << 20; c->fused[i].pp.out0_panel_rows = 0; }
+                                      c->fused[i].p.a2_panel_rows = 0; c->fused[i].p.out0_panel_rows = 0; }
         // panel variant of the clause MLP: needs 64-wide slices on both smem gathers (see pick_slice_width)
         c->panel_ready = false;
         size_t b1 = 0, b2 = 0;
@@ -358,7 +356,6 @@ int ensure_tc_buffers(dsat_ctx* c) {
             f.p.a2_panel_rows = c->Mt;
             if (tc::make_bf16_map(&f.map_a2, c->CL4P.p, (long long)(Q / 64) * c->Mt, 64, 64, f.p.a_box_rows) && fm::plan_fused(f)) {
                 f.p.a_split_kb = (F + Q) / 64; f.p.a2_panel_rows = c->Mt; f.p.out0_panel_rows = c->Mt;
-                f.pair_ok = false;
                 c->panel_ready = true;
             }
         }
@@ -492,7 +489,7 @@ static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p
 static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : nullptr; }
 static inline bool panel_now(const dsat_ctx* c) {
     return c->precision == DSAT_BF16 && c->fused_ready && c->use_fused && c->panel_ready && c->use_panels &&
-           c->use_smem_gather && !c->use_tma_gather && !c->use_pair;
+           c->use_smem_gather && !c->use_tma_gather;
 }
 #else
 static inline bool use_tc(const dsat_ctx*) { return false; }
@@ -563,13 +560,7 @@ int run_linear_tc(dsat_ctx* c, int op, long long rows, int epi, void* p0, int ld
 #ifdef DSAT_WITH_TCGEN05
 int run_fused(dsat_ctx* c, int which, int prof_class) {
     prof_mark(c, prof_class);
-    if (c->use_pair && c->fused[which].pair_ok) {
-        fm::FusedMlp g = c->fused[which];
-        g.p = g.pp;
-        g.smem_bytes = g.smem_bytes_pair;
-        for (int l = 0; l < fm::MAX_LAYERS; ++l) g.map_w[l] = g.map_wp[l];
-        CK_CUDA(c, fm2::launch_fused_pair(g, c->sm_count, c->stream));
-    } else if (which == 2 && panel_now(c)) {
+    if (which == 2 && panel_now(c)) {
         CK_CUDA(c, fm::launch_fused(c->fused_clause_panel, c->sm_count, c->stream));
     } else {
         CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
@@ -947,8 +938,6 @@ int dsat_create(int device, dsat_ctx** out) {
     {   // A/B switches for measurements: DSAT_FUSED_MLP=0, DSAT_SMEM_GATHER=0
         const char* e = getenv("DSAT_FUSED_MLP");
         if (e && e[0] == '0') c->use_fused = false;
-        e = getenv("DSAT_MLP_PAIR");
-        if (e) c->use_pair = e[0] != '0';
         e = getenv("DSAT_SPMM_ORDER");
         if (e) c->use_spmm_order = e[0] != '0';
         e = getenv("DSAT_IDX16");

@@ -110,6 +110,88 @@ __device__ __forceinline__ void umma_bf16_kblock_commit_elect(uint32_t tmem_d, u
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(slot_free_bar)) : "memory");
 }
+// ---- CTA-pair forms (cluster of 2, tcgen05 cta_group::2): the leader CTA (cluster rank 0) issues MMAs with M = 256
+// that read A and B from both CTAs' shared memory (same offsets) and write each CTA's 128 accumulator rows into its own
+// tensor memory.  Barriers the leader's issue warp waits on live in the leader's shared memory and are arrived on
+// remotely (mapa + shared::cluster addressing); barriers that producers / epilogues wait on are per CTA and are
+// signalled by the leader's multicast commits.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {   // shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_expect_tx_at(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_at(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_scope(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_CS:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE_CS;\n"
+        "bra WAIT_LOOP_CS;\n"
+        "WAIT_DONE_CS:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion is signalled on a barrier given by its shared::cluster address
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_elect_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs once all prior MMAs completed
+__device__ __forceinline__ void tcgen05_commit_elect_cg2(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        ".reg .b16 m;\n"
+        "mov.b16 m, 3;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n"
+        "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_kblock_commit_elect_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                                  uint32_t accumulate_first, uint64_t* slot_free_bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        ".reg .b16 m;\n"
+        "mov.b16 m, 3;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
+        "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(slot_free_bar)) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }

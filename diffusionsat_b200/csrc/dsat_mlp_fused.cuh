@@ -32,7 +32,6 @@ using tc::TcOut;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int THREADS = 192;                 // 2 + 4 warps (pair kernel); the single-CTA kernel runs 2 + epi_warps warps
 constexpr int MAX_THREADS = 320;
 constexpr int MAX_LAYERS = 3;
 constexpr int MAX_SLOTS = 8;
@@ -57,8 +56,10 @@ struct FmParams {
     FmLayer layer[MAX_LAYERS];
     int rows, n_tiles, a_box_rows, ah_blocks, slots, slot_bytes, two_bufs, qmaps;
     int dbg;               // experiments only (DSAT_FM_DEBUG): bit 0 = epilogues do no work (results are garbage)
+    int pair;              // CTA-pair mode (cluster of 2, cta_group::2): host-side flag, the kernel is a separate instantiation
     int pp;                // ping-pong: two tiles in flight (needs a_slots > 0 and two_bufs)
-    int stage_in_h;        // pp: the output staging of a tile aliases its hidden region
+    int stage_in_h;        // the output staging of a tile aliases its (by then dead) hidden region, at byte offset stage_off
+    int stage_off;
     int a_slots;           // > 0: layer 0's A operand streams through an input ring of that many 16 KB blocks
     int a_split_kb;        // k-blocks >= a_split_kb of the INPUT tile come from map_a2 (panel-major source), 1<<20 = never
     long long a2_panel_rows;  // rows per 64-column panel of that source
@@ -335,11 +336,18 @@ __device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&ra
 // Drain one accumulator: software pipeline, the tcgen05.ld of the next chunk is in flight while this one is
 // processed.  For the last layer the accumulator is handed back (tmem_empty) as soon as this warp's last TMEM
 // read has landed; for hidden layers the caller arrives after the shared-memory stores are fenced.
-template <bool HIDDEN>
-__device__ __forceinline__ void epi_drain(const EpiCtx& e, uint64_t* tmem_empty_bar) {
+// barrier arrive by shared-memory address: this CTA's barrier, or (PAIR) the leader CTA's through shared::cluster
+template <bool PAIR>
+__device__ __forceinline__ void arrive_addr(uint32_t addr) {
+    if constexpr (PAIR) tc::mbar_arrive_at(addr);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+template <bool HIDDEN, bool PAIR>
+__device__ __forceinline__ void epi_drain(const EpiCtx& e, uint32_t tmem_empty_addr) {
     bool released = false;
     if (e.skip) {          // timing experiment: hand everything back without touching the accumulator
-        if (!HIDDEN) { tc::tcgen05_fence_before(); mbar_arrive(tmem_empty_bar); }
+        if (!HIDDEN) { tc::tcgen05_fence_before(); arrive_addr<PAIR>(tmem_empty_addr); }
         return;
     }
 #pragma unroll 1
@@ -349,15 +357,15 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint64_t* tmem_empty_
         tmem_ld_wait(ra);
         if (!HIDDEN && c + e.cstep >= e.N) {     // last TMEM read of this warp: hand the accumulator back early
             tc::tcgen05_fence_before();
-            mbar_arrive(tmem_empty_bar);
+            arrive_addr<PAIR>(tmem_empty_addr);
             released = true;
         }
         epi_process<HIDDEN>(e, ra, c);
     }
-    if (!HIDDEN && !released) { tc::tcgen05_fence_before(); mbar_arrive(tmem_empty_bar); }
+    if (!HIDDEN && !released) { tc::tcgen05_fence_before(); arrive_addr<PAIR>(tmem_empty_addr); }
 }
 
-template <bool TIMING>
+template <bool TIMING, bool PAIR>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
@@ -391,16 +399,22 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const long long t_kernel0 = timing ? clock64() : 0;
     long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0, w7 = 0;
 
+    // PAIR (launched as clusters of 2): rank 0 leads.  "full"-type barriers (waited on by the leader's issue warp) count
+    // one arrival per CTA / per epilogue thread of both CTAs; "empty"-type and tmem_full barriers are local and get one
+    // arrival from the leader's multicast commit.
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const bool leader = rank == 0;
+    constexpr int NC = PAIR ? 2 : 1;
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, NC);
         mbar_init(ah_free, 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&h_full[b], epi_threads);
+            mbar_init(&h_full[b], NC * epi_threads);
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], epi_threads);
+            mbar_init(&tmem_empty[b], NC * epi_threads);
         }
-        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-        for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_ring_full[s], 1); mbar_init(&a_ring_empty[s], 1); }
+        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], NC); mbar_init(&ring_empty[s], 1); }
+        for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_ring_full[s], NC); mbar_init(&a_ring_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
@@ -408,8 +422,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     if (warp >= 2) {
         for (int l = 0; l < p.n_layers; ++l)
@@ -419,21 +438,32 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();              // both CTAs' barriers exist before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_layers = p.n_layers;
+    auto wait = [&](uint64_t* bar, uint32_t parity) {
+        if constexpr (PAIR) mbar_wait_cluster_scope(bar, parity); else mbar_wait(bar, parity);
+    };
+    // address of the barrier the leader's issue warp waits on (this CTA's own one when not paired)
+    auto at_leader = [&](uint64_t* bar) -> uint32_t { return PAIR ? mapa_rank(smem_u32(bar), 0) : smem_u32(bar); };
     // This CTA's tiles are blockIdx.x + j * gridDim.x, j < nt.  All three roles walk the same sequence of
     // (tile, layer) steps: tile by tile, or (pp) in groups of two tiles with the layers interleaved
     // L1(A) L1(B) L2(A) L2(B) ...  For step (j, l) with s = j & 1 inside its group:
     //   pp    : accumulator half s, hidden region s, both used once per layer and group
     //   else  : accumulator half alternates per step when every layer fits 256 columns, one hidden region
-    const int nt = blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // work units: 128-row tiles of this CTA, or (PAIR) 256-row macro tiles of the pair, of which this CTA owns half
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
+    const int nt = unit0 < n_units ? (n_units - unit0 + unit_stride - 1) / unit_stride : 0;
+    auto tile_of = [&](int j) { const int u = unit0 + j * unit_stride; return PAIR ? 2 * u + (int)rank : u; };
     const int group = p.pp ? 2 : 1;
     struct Step { int tile, buf, use, hidx, hcnt; };
     auto make_step = [&](int j0, int s, int l) {
         Step st;
         const int j = j0 + s;
-        st.tile = (int)blockIdx.x + j * (int)gridDim.x;
+        st.tile = tile_of(j);
         if (p.pp) {
             st.buf = s; st.use = (j0 >> 1) * n_layers + l;
             st.hidx = s; st.hcnt = (j0 >> 1) * (n_layers - 1) + (l - 1);
@@ -450,54 +480,70 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int k0_blocks = (p.layer[0].K + BLOCK_K - 1) / BLOCK_K;
             int slot = 0; uint32_t phase = 0;
             int aslot = 0; uint32_t aphase = 0;
+            auto load_2d = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+                if constexpr (PAIR) tma_load_2d_cg2(dst, map, at_leader(bar), c0, c1); else tma_load_2d(dst, map, bar, c0, c1);
+            };
+            auto expect = [&](uint64_t* bar, uint32_t bytes) {
+                if constexpr (PAIR) mbar_expect_tx_at(at_leader(bar), bytes); else mbar_expect_tx(bar, bytes);
+            };
             auto load_a_block = [&](uint8_t* dst, uint64_t* bar, int kb, int tile) {
                 if (kb < p.a_split_kb)
-                    tma_load_2d(dst, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
+                    load_2d(dst, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
                 else         // panel-major source: panel (kb - a_split_kb) is a dense [rows, 64] matrix
-                    tma_load_2d(dst, &map_a2, bar, 0, (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
+                    load_2d(dst, &map_a2, bar, 0, (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
             };
             for (int j0 = 0; j0 < nt; j0 += group)
                 for (int l = 0; l < n_layers; ++l)
                     for (int s = 0; s < group; ++s) {
                         if (j0 + s >= nt) continue;
-                        const int j = j0 + s, tile = (int)blockIdx.x + j * (int)gridDim.x;
+                        const int j = j0 + s, tile = tile_of(j);
                         if (l == 0 && p.a_slots == 0) {      // whole input tile into AH
-                            if (j > 0) DSAT_TIMED_WAIT(w0, mbar_wait(ah_free, (uint32_t)((j - 1) & 1)));   // tile j-1 no longer reads AH
-                            mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
+                            if (j > 0) DSAT_TIMED_WAIT(w0, wait(ah_free, (uint32_t)((j - 1) & 1)));   // tile j-1 no longer reads AH
+                            expect(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
                             for (int kb = 0; kb < k0_blocks; ++kb) load_a_block(ah + (size_t)kb * AH_BLOCK_BYTES, a_full, kb, tile);
                         }
                         const int kbs = (p.layer[l].K + BLOCK_K - 1) / BLOCK_K;
                         const int halves = (p.layer[l].N + 255) / 256;
                         for (int kb = 0; kb < kbs; ++kb) {
                             if (l == 0 && p.a_slots > 0) {     // input block kb of this tile into the input ring
-                                DSAT_TIMED_WAIT(w0, mbar_wait(&a_ring_empty[aslot], aphase ^ 1));
-                                mbar_expect_tx(&a_ring_full[aslot], (uint32_t)p.a_box_rows * (BLOCK_K * 2));
+                                DSAT_TIMED_WAIT(w0, wait(&a_ring_empty[aslot], aphase ^ 1));
+                                expect(&a_ring_full[aslot], (uint32_t)p.a_box_rows * (BLOCK_K * 2));
                                 load_a_block(a_ring + (size_t)aslot * AH_BLOCK_BYTES, &a_ring_full[aslot], kb, tile);
                                 if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
                             }
                             for (int h = 0; h < halves; ++h) {
-                                DSAT_TIMED_WAIT(w1, mbar_wait(&ring_empty[slot], phase ^ 1));
-                                mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[l].box_rows * (BLOCK_K * 2));
-                                tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K, h * 256);
+                                DSAT_TIMED_WAIT(w1, wait(&ring_empty[slot], phase ^ 1));
+                                if constexpr (PAIR) {     // this CTA's half of the weight block: rows [h*256 + rank*bn/2, +bn/2) of W^T
+                                    const int bn = min(256, p.layer[l].N - h * 256);
+                                    expect(&ring_full[slot], (uint32_t)(bn / 2) * (BLOCK_K * 2));
+                                    load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K,
+                                            h * 256 + (int)rank * (bn / 2));
+                                } else {
+                                    expect(&ring_full[slot], (uint32_t)p.layer[l].box_rows * (BLOCK_K * 2));
+                                    load_2d(ring + (size_t)slot * p.slot_bytes, map_w[l], &ring_full[slot], kb * BLOCK_K, h * 256);
+                                }
                                 if (++slot == p.slots) { slot = 0; phase ^= 1; }
                             }
                         }
                     }
         }
     } else if (warp == 1) {
-        {                  // ================================ MMA issuer: the whole warp runs the loop converged, one lane issues
+        if (leader) {      // ================================ MMA issuer: the whole warp runs the loop converged, one lane issues
             int slot = 0; uint32_t phase = 0;
             int aslot = 0; uint32_t aphase = 0;
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (PAIR) tcgen05_commit_elect_cg2(bar); else tcgen05_commit_elect(bar);
+            };
             for (int j0 = 0; j0 < nt; j0 += group)
                 for (int l = 0; l < n_layers; ++l)
                     for (int s = 0; s < group; ++s) {
                         if (j0 + s >= nt) continue;
                         const Step st = make_step(j0, s, l);
                         const int j = j0 + s;
-                        DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_empty[st.buf], (uint32_t)((st.use & 1) ^ 1)));   // accumulator drained
+                        DSAT_TIMED_WAIT(w0, wait(&tmem_empty[st.buf], (uint32_t)((st.use & 1) ^ 1)));   // accumulator drained
                         const bool streamed = l == 0 && p.a_slots > 0;
-                        if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, mbar_wait(a_full, (uint32_t)(j & 1))); }
-                        else DSAT_TIMED_WAIT(w2, mbar_wait(&h_full[st.hidx], (uint32_t)(st.hcnt & 1)));
+                        if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, wait(a_full, (uint32_t)(j & 1))); }
+                        else DSAT_TIMED_WAIT(w2, wait(&h_full[st.hidx], (uint32_t)(st.hcnt & 1)));
                         tcgen05_fence_after();
                         const int K = p.layer[l].K, N = p.layer[l].N;
                         const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
@@ -508,36 +554,39 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int kb = 0; kb < kbs; ++kb) {
                             // (no tcgen05 fence after the ring waits: TMA writes and MMA reads are both async-proxy accesses
                             //  ordered by the mbarrier; the fences that matter are the per-step ones above)
-                            if (streamed) { DSAT_TIMED_WAIT(w1, mbar_wait(&a_ring_full[aslot], aphase)); }
+                            if (streamed) { DSAT_TIMED_WAIT(w1, wait(&a_ring_full[aslot], aphase)); }
                             const uint64_t da = make_smem_desc_sw128(smem_u32(streamed ? a_ring + (size_t)aslot * AH_BLOCK_BYTES
                                                                                        : a_src + (size_t)kb * AH_BLOCK_BYTES));
                             const int ksteps = min(BLOCK_K / 16, (K - kb * BLOCK_K + 15) / 16);
                             for (int h = 0; h < halves; ++h) {
                                 const int bn = min(256, N - h * 256);
-                                const uint32_t idesc = make_idesc_bf16(BLOCK_M, bn);
-                                DSAT_TIMED_WAIT(w3, mbar_wait(&ring_full[slot], phase));
+                                const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, bn);
+                                DSAT_TIMED_WAIT(w3, wait(&ring_full[slot], phase));
                                 const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
                                 const long long t_i0 = timing ? clock64() : 0;
                                 const uint32_t acc_h = acc + (uint32_t)(h * 256);
                                 if (ksteps == BLOCK_K / 16) {       // full K block: four MMAs and the slot's commit in one go
-                                    umma_bf16_kblock_commit_elect(acc_h, da, db, idesc, kb != 0, &ring_empty[slot]);
+                                    if constexpr (PAIR) umma_bf16_kblock_commit_elect_cg2(acc_h, da, db, idesc, kb != 0, &ring_empty[slot]);
+                                    else umma_bf16_kblock_commit_elect(acc_h, da, db, idesc, kb != 0, &ring_empty[slot]);
                                 } else {
-                                    for (int k = 0; k < ksteps; ++k)
-                                        umma_bf16_elect(acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                                    tcgen05_commit_elect(&ring_empty[slot]);
+                                    for (int k = 0; k < ksteps; ++k) {
+                                        if constexpr (PAIR) umma_bf16_elect_cg2(acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                                        else umma_bf16_elect(acc_h, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                                    }
+                                    commit(&ring_empty[slot]);
                                 }
                                 const long long t_i1 = timing ? clock64() : 0;
                                 if (timing) { w4 += t_i1 - t_i0; w5 += clock64() - t_i1; }
                                 if (++slot == p.slots) { slot = 0; phase ^= 1; }
                             }
                             if (streamed) {
-                                tcgen05_commit_elect(&a_ring_empty[aslot]);
+                                commit(&a_ring_empty[aslot]);
                                 if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
                             }
                         }
                         const long long t_kb1 = timing ? clock64() : 0;
-                        tcgen05_commit_elect(&tmem_full[st.buf]);
-                        if (l == n_layers - 1 && p.a_slots == 0) tcgen05_commit_elect(ah_free);
+                        commit(&tmem_full[st.buf]);
+                        if (l == n_layers - 1 && p.a_slots == 0) commit(ah_free);
                         if (timing) { w6 += t_kb1 - t_kb0; w7 += clock64() - t_kb1; }
                     }
         }
@@ -564,22 +613,28 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     e.row_first = (size_t)st.tile * BLOCK_M + quad * 32;
                     e.rows_left = p.rows - (int)e.row_first;
                     e.ah_addr = smem_u32(ah + (size_t)st.hidx * h_bytes);
-                    e.stage_addr = (p.stage_in_h ? e.ah_addr : smem_u32(stage_all)) + stage_off;
+                    e.stage_addr = (p.stage_in_h ? e.ah_addr + (uint32_t)p.stage_off : smem_u32(stage_all)) + stage_off;
                     e.N = p.layer[l].N; e.epi = p.layer[l].epi;
                     e.bl_addr = bias_addr0 + 4u * (uint32_t)p.layer[l].bias_off;
                     e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st.buf * 256);
-                    DSAT_TIMED_WAIT(w0, mbar_wait(&tmem_full[st.buf], (uint32_t)(st.use & 1)));
+                    DSAT_TIMED_WAIT(w0, wait(&tmem_full[st.buf], (uint32_t)(st.use & 1)));
                     tcgen05_fence_after();
                     const long long t_epi0 = timing ? clock64() : 0;
+                    const uint32_t empty_addr = at_leader(&tmem_empty[st.buf]);
                     if (l + 1 < n_layers) {
-                        epi_drain<true>(e, &tmem_empty[st.buf]);
+                        epi_drain<true, PAIR>(e, empty_addr);
                         tcgen05_fence_before();
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the MMA (async proxy)
-                        mbar_arrive(&tmem_empty[st.buf]);
-                        mbar_arrive(&h_full[st.hidx]);
+                        // st.shared -> visible to the MMA (async proxy); the leader's MMA also reads the peer's shared memory
+                        if constexpr (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
+                        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        arrive_addr<PAIR>(empty_addr);
+                        arrive_addr<PAIR>(at_leader(&h_full[st.hidx]));
                         if (timing) w1 += clock64() - t_epi0;
                     } else {
-                        epi_drain<false>(e, &tmem_empty[st.buf]);
+                        epi_drain<false, PAIR>(e, empty_addr);
+                        // staging inside the hidden region: no epilogue warp may start writing the next hidden activations
+                        // there while another one still reads back its staged output (named barrier of the epilogue warps)
+                        if (p.stage_in_h) asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
                         if (timing) w2 += clock64() - t_epi0;
                     }
                 }
@@ -593,10 +648,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (warp == 2) { p.prof[7] = w0; p.prof[8] = w1; p.prof[9] = w2; p.prof[11] = total; }
     }
     (void)w4; (void)w5; (void)w6; (void)w7;
+    tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();              // the leader's MMAs may still read this CTA's shared memory
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -606,13 +664,10 @@ struct FusedMlp {
     CUtensorMap map_w[MAX_LAYERS];
     FmParams p;
     int smem_bytes;
-    // CTA-pair variant (dsat_mlp_pair.cuh): weight maps with half-height boxes, its own ring plan
-    CUtensorMap map_wp[MAX_LAYERS];
-    FmParams pp;
-    int smem_bytes_pair;
-    bool pair_ok;
+    CUtensorMap map_wp[MAX_LAYERS];     // weight maps with half-height boxes (CTA-pair mode: each CTA loads half a block)
     bool stream_input = false;      // request the input ring (FmParams::a_slots), set before plan_fused
     bool ping_pong = false;         // request two tiles in flight (FmParams::pp); needs stream_input
+    bool pair_mode = false;         // request the CTA-pair instantiation: half-height weight slots (map_wp), clusters of 2
 };
 
 // Dynamic shared memory has to start on a 1024-byte boundary (SWIZZLE_128B atoms).  The base is that well aligned in
@@ -647,6 +702,7 @@ inline bool plan_fused(FusedMlp& f) {
     p.a_slots = 0;
     p.pp = 0;
     p.stage_in_h = 0;
+    p.stage_off = 0;
     for (int l = 0; l < p.n_layers; ++l) {
         if (l + 1 < p.n_layers) blocks = max(blocks, (p.layer[l].N + 63) / 64);
         p.layer[l].bias_off = bias_total;
@@ -656,16 +712,15 @@ inline bool plan_fused(FusedMlp& f) {
     }
     p.ah_blocks = blocks;
     p.bias_total = bias_total;
-    p.slot_bytes = (max_box * BLOCK_K * 2 + 1023) / 1024 * 1024;
-    p.n_tiles = ceil_div(p.rows, BLOCK_M);
-    // pair variant: each CTA holds half of every weight block, so slots are half as large
-    f.pp = p;
-    f.pp.slot_bytes = (max_box / 2 * BLOCK_K * 2 + 1023) / 1024 * 1024;
-    f.pp.slots = 0;
-    for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = 1024 + blocks * AH_BLOCK_BYTES + slots * f.pp.slot_bytes + STAGE_BYTES + BAR_BYTES + bias_total * 4;
-        if (total <= SMEM_LIMIT) { f.pp.slots = slots; f.smem_bytes_pair = total; break; }
+    // CTA pair: needs equal weight halves per MMA (N <= 256, or a multiple of 256) and at least one full macro tile
+    bool pair = f.pair_mode && p.rows > BLOCK_M;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const int N = p.layer[l].N;
+        if (N % 16 || (N > 256 && N % 256)) pair = false;
     }
+    p.pair = pair ? 1 : 0;
+    p.slot_bytes = ((pair ? max_box / 2 : max_box) * BLOCK_K * 2 + 1023) / 1024 * 1024;
+    p.n_tiles = ceil_div(p.rows, BLOCK_M);
     {
         const FmLayer& last = p.layer[p.n_layers - 1];
         const bool all_bf16 = p.out.bf16_0 && (p.out.ptr1 == nullptr || p.out.bf16_1) && last.epi != tc::TC_QUERY;
@@ -679,25 +734,23 @@ inline bool plan_fused(FusedMlp& f) {
         int h_blocks = 1;
         for (int l = 0; l + 1 < p.n_layers; ++l) h_blocks = max(h_blocks, (p.layer[l].N + 63) / 64);
         const int k0_blocks = (p.layer[0].K + 63) / 64;
-        auto finish_pair_plan = [&]() {
-            f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs; f.pp.ah_blocks = blocks;
-            for (int l = 0; l < p.n_layers; ++l) f.pp.layer[l].bias_off = p.layer[l].bias_off;
-        };
         if (f.ping_pong && p.two_bufs) {
             // two tiles in flight: two hidden regions; a tile's output staging aliases its own hidden region when it fits
             for (int ew : {8, 4}) {
                 const int h_bytes = h_blocks * AH_BLOCK_BYTES, stage_bytes = ew * 32 * p.stage_row;
                 const int in_h = stage_bytes <= h_bytes;
                 const int fixed = pad + 2 * h_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4;
-                int a_slots = (SMEM_LIMIT - fixed - 2 * p.slot_bytes) / AH_BLOCK_BYTES;
+                // weight slots to reserve before the input ring gets the rest: four half-height ones in pair mode
+                int w_min = p.pair ? 4 : 2;
+                if (SMEM_LIMIT - fixed - w_min * p.slot_bytes < 2 * AH_BLOCK_BYTES) w_min = 2;
+                int a_slots = (SMEM_LIMIT - fixed - w_min * p.slot_bytes) / AH_BLOCK_BYTES;
                 if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
                 if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
-                if (SMEM_LIMIT - fixed - 2 * p.slot_bytes < 0 || a_slots < 2) continue;
+                if (SMEM_LIMIT - fixed - w_min * p.slot_bytes < 0 || a_slots < 2) continue;
                 p.pp = 1; p.stage_in_h = in_h; p.a_slots = a_slots; p.epi_warps = ew; p.ah_blocks = h_blocks;
                 const int base = fixed + a_slots * AH_BLOCK_BYTES;
                 for (int slots = MAX_SLOTS; slots >= 2; --slots)
                     if (base + slots * p.slot_bytes <= SMEM_LIMIT) { p.slots = slots; f.smem_bytes = base + slots * p.slot_bytes; break; }
-                finish_pair_plan();
                 return true;
             }
         }
@@ -713,25 +766,28 @@ inline bool plan_fused(FusedMlp& f) {
                 const int base = fixed - 2 * p.slot_bytes + a_slots * AH_BLOCK_BYTES;
                 for (int slots = MAX_SLOTS; slots >= 2; --slots)
                     if (base + slots * p.slot_bytes <= SMEM_LIMIT) { p.slots = slots; f.smem_bytes = base + slots * p.slot_bytes; break; }
-                f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs; f.pp.ah_blocks = blocks;
-                for (int l = 0; l < p.n_layers; ++l) f.pp.layer[l].bias_off = p.layer[l].bias_off;
                 return true;
             }
         }
     }
+    // Resident-input mode.  The final epilogue may stage through the part of AH above the input blocks: the hidden
+    // activations there are dead once the last layer's MMAs have completed, the next tile's input only overwrites the
+    // first k0 blocks, and the next hidden epilogue comes after this one in the same warps' program order.
+    const int k0_blocks_res = (p.layer[0].K + 63) / 64;
     for (int ew : {8, 4}) {     // prefer 8 epilogue warps when two ring slots still fit
-        if (pad + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 4 <= SMEM_LIMIT) {
+        const int stage_bytes = ew * 32 * p.stage_row;
+        const int in_h = p.n_layers > 1 && (blocks - k0_blocks_res) * AH_BLOCK_BYTES >= stage_bytes;
+        if (pad + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4 <= SMEM_LIMIT) {
             p.epi_warps = ew;
+            p.stage_in_h = in_h;
+            p.stage_off = in_h ? k0_blocks_res * AH_BLOCK_BYTES : 0;
             break;
         }
     }
-    f.pp.epi_warps = 4;
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = pad + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + p.epi_warps * 32 * p.stage_row + BAR_BYTES + bias_total * 4;
+        const int total = pad + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + (p.stage_in_h ? 0 : p.epi_warps * 32 * p.stage_row) + BAR_BYTES + bias_total * 4;
         if (total <= SMEM_LIMIT) {
             p.slots = slots;
-            f.pp.ah_blocks = p.ah_blocks; f.pp.n_tiles = p.n_tiles; f.pp.two_bufs = p.two_bufs;
-            for (int l = 0; l < p.n_layers; ++l) f.pp.layer[l].bias_off = p.layer[l].bias_off;
             f.smem_bytes = total;
             return true;
         }
@@ -743,19 +799,32 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
     if (f.p.rows <= 0) return cudaSuccess;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fused_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
     const unsigned threads = 64 + 32 * f.p.epi_warps;
-    const CUtensorMap& w2 = f.map_w[f.p.n_layers > 2 ? 2 : 1];
+    const int last = f.p.n_layers > 2 ? 2 : 1;
+    if (f.p.pair) {     // clusters of two CTAs, one 256-row macro tile per pair and pass; weight maps with half-height boxes
+        const int n_macro = (f.p.n_tiles + 1) / 2;
+        const int pairs = n_macro < sm_count / 2 ? n_macro : sm_count / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)f.smem_bytes; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (f.p.prof) return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<true, true>, f.map_a, f.map_a2, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
+        return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<false, true>, f.map_a, f.map_a2, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
+    }
+    const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
     if (f.p.prof)   // instrumented build of the same kernel (dsat_profile_fused)
-        fused_mlp_kernel<true><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], w2, f.p);
+        fused_mlp_kernel<true, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
     else
-        fused_mlp_kernel<false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], w2, f.p);
+        fused_mlp_kernel<false, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
     return cudaGetLastError();
 }
 
