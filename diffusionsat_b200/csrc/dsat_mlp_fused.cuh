@@ -755,14 +755,23 @@ inline bool plan_fused(FusedMlp& f) {
             }
         }
         for (int ew : {8, 4}) {
-            const int fixed = pad + h_blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + ew * 32 * p.stage_row + BAR_BYTES + bias_total * 4;
+            // one tile at a time: the final epilogue can still stage through the (dead) hidden region; three weight slots
+            // are reserved before the input ring takes the rest
+            const int stage_bytes = ew * 32 * p.stage_row;
+            const int in_h = stage_bytes <= h_blocks * AH_BLOCK_BYTES;
+            int w_min = 3;
+            int fixed = pad + h_blocks * AH_BLOCK_BYTES + w_min * p.slot_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4;
+            if (SMEM_LIMIT - fixed < 2 * AH_BLOCK_BYTES) { fixed -= p.slot_bytes; w_min = 2; }
             int a_slots = (SMEM_LIMIT - fixed) / AH_BLOCK_BYTES;
             if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
             if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
+            fixed -= (w_min - 2) * p.slot_bytes;          // `fixed` below counts two weight slots
             if (a_slots >= 2 && a_slots >= (k0_blocks + 1) / 2) {
                 p.a_slots = a_slots;
                 p.epi_warps = ew;
                 p.ah_blocks = h_blocks;
+                p.stage_in_h = in_h;
+                p.stage_off = 0;
                 const int base = fixed - 2 * p.slot_bytes + a_slots * AH_BLOCK_BYTES;
                 for (int slots = MAX_SLOTS; slots >= 2; --slots)
                     if (base + slots * p.slot_bytes <= SMEM_LIMIT) { p.slots = slots; f.smem_bytes = base + slots * p.slot_bytes; break; }
