@@ -94,6 +94,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_RESTORE_STDOUT = lambda: None
+
+
 def ncu_traffic(precision):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
     path = os.path.join(ROOT, "profiles", "r1_traffic.json")
@@ -165,7 +168,8 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "TensorFlow 2.4 / TFP 0.12 are not installable offline; this is the torch-CPU oracle port of the reference path",
     }
-    print(json.dumps(line))
+    _RESTORE_STDOUT()
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -347,7 +351,8 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "message_pass": message_pass,
         "message_pass_in_model": in_model, "cpu_baseline": cpu, "sat_rate": sat_rate,
     }
-    print(json.dumps(line))
+    _RESTORE_STDOUT()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -363,6 +368,15 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-message-pass", action="store_true")
     args = ap.parse_args()
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner under torchrun, for one) write there too, so
+    # file descriptor 1 points at stderr while the benchmark runs and is restored for the final print.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _RESTORE_STDOUT
+    def _RESTORE_STDOUT():
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
