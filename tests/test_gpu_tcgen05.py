@@ -82,10 +82,13 @@ def test_bf16_sampler_runs_and_is_deterministic(ctx):
         assert (v in models) == bool(s)          # the SAT flag is exact integer work in both precisions
 
 
-def test_fused_mlp_kernels_match_per_layer_kernels(ctx):
+@pytest.mark.parametrize("chains", [7, 600])
+def test_fused_mlp_kernels_match_per_layer_kernels(ctx, chains):
     """One kernel per MLP (hidden activations in shared memory) against one kernel per Dense layer:
-    same bf16 rounding points, same accumulation order -> logits agree to fp32 round-off."""
-    n_vars, chains, rounds = 100, 7, 3
+    same bf16 rounding points, same accumulation order -> logits agree to fp32 round-off.
+    7 chains: at most one 128-row tile per CTA; 600 chains: 3-4 variable tiles and 13-14 clause tiles per CTA, i.e.
+    the persistent loop, the input ring wrap-around and the ping-pong pairing with odd and even tile counts."""
+    n_vars, rounds = 100, 3
     _, clauses = synth.random_3sat(n_vars, seed=4)
     wts = H.make_weights(seed=9)
     n_rows = n_vars * chains
@@ -94,11 +97,28 @@ def test_fused_mlp_kernels_match_per_layer_kernels(ctx):
     ctx.set_model(wts)
     ctx.set_graph(G.build_unit_graph(n_vars, clauses), chains=chains, group_graphs=0)
     out = {}
-    for name, code in (("fused", _lib.BF16), ("per_layer", 2)):
+    for name, code in (("fused", _lib.BF16), ("per_layer", 2), ("fp32", _lib.F32)):
         ctx.set_precision(code)
         ctx.debug_begin(0.5, noisy, noise["labels"])
         for r in range(rounds):
             ctx.debug_round(r, noise["normals"][r])
         out[name] = (ctx.debug_read("LOGITS").copy(), ctx.debug_read("SPRE").copy(), ctx.debug_read("CROW")[:, :128].copy())
     for a, b in zip(out["fused"], out["per_layer"]):
-        assert H.rel_err(a, b) < 5e-2      # two bf16 realisations (leaky relu on packed bf16 pairs vs fp32); same bound as against the oracle
+        # two bf16 realisations (leaky relu on packed bf16 pairs vs fp32); same bound as against the oracle.  The
+        # maximum over 100x more elements sits further out in the tail of the rounding noise, so the large case bounds
+        # the maximum at 1e-1 and the rms error at 2e-2: a misplaced or stale tile would be an O(1) error
+        assert H.rel_err(a, b) < (5e-2 if chains < 100 else 1e-1)
+        scale = max(float(np.sqrt(np.mean(b.astype(np.float64) ** 2))), 1e-12)
+        err2 = ((a.astype(np.float64) - b) ** 2).mean(axis=1)
+        assert float(np.sqrt(err2.mean())) / scale < 3.5e-2             # typical: 2e-2 after three rounds
+        pad = (-len(err2)) % 128
+        tiles = np.sqrt(np.pad(err2, (0, pad)).reshape(-1, 128).mean(axis=1)) / scale
+        assert tiles.max() < 1e-1                                         # every 128-row tile on its own
+    # and against the fp32 parity path (SIMT GEMMs, general gather kernels, generic PairNorm): independent kernels all
+    # the way, so this also covers the shared-memory gathers and the bf16 PairNorm at a size with many chains per SM
+    for a, b in zip(out["fused"], out["fp32"]):
+        scale = max(float(np.sqrt(np.mean(b.astype(np.float64) ** 2))), 1e-12)
+        err2 = ((a.astype(np.float64) - b) ** 2).mean(axis=1)
+        assert float(np.sqrt(err2.mean())) / scale < 5e-2
+        pad = (-len(err2)) % 128
+        assert (np.sqrt(np.pad(err2, (0, pad)).reshape(-1, 128).mean(axis=1)) / scale).max() < 1.5e-1
