@@ -19,7 +19,6 @@
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
 #include "dsat_mlp_fused.cuh"
-#include "dsat_message_tma.cuh"
 #endif
 
 using namespace dsat;
@@ -122,17 +121,6 @@ struct dsat_ctx {
     bool fused_ready = false;
     bool use_fused = true;
     bool use_smem_gather = true;
-    // panel layout of the clause-side intermediates on the fused bf16 path (contiguous gather tables):
-    // CL4P / VMSGP [Q/64][M][64] (4*clauses_loss, message to literals), CNEWb [M, F] (new clause value)
-    DevBuf<__nv_bfloat16> CL4P, VMSGP, CNEWb;
-    fm::FusedMlp fused_clause_panel;
-    bool panel_ready = false;
-    bool use_panels = false;          // measured +0.6 % at cfg2 only: opt-in (DSAT_PANELS=1)
-    // TMA-staged persistent gathers (dsat_message_tma.cuh)
-    CUtensorMap map_g_lit, map_g_sp, map_g_cl, map_g_ms;
-    tg::GatherPlan gp_clause, gp_literal;
-    bool tma_clause_ready = false, tma_literal_ready = false;
-    bool use_tma_gather = false;     // measured slightly slower than the cooperative-load staging at cfg2: opt-in (DSAT_TMA_GATHER=1)
 #endif
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
@@ -340,48 +328,6 @@ int ensure_tc_buffers(dsat_ctx* c) {
         ok = ok && build(FO, OP_O1, {{OP_O1, c->HO, W(OP_O1), B(OP_O1), tc::TC_LRELU},
                                      {OP_O2, DSAT_LOGIT_PAD, W(OP_O2), B(OP_O2), tc::TC_LINEAR}}, o);
         c->fused_ready = ok;
-        for (int i = 0; i < 5; ++i) { c->fused[i].map_a2 = c->fused[i].map_a; c->fused[i].p.a_split_kb = 1 << 20;
-                                      c->fused[i].p.a2_panel_rows = 0; c->fused[i].p.out0_panel_rows = 0; }
-        // panel variant of the clause MLP: needs 64-wide slices on both smem gathers (see pick_slice_width)
-        c->panel_ready = false;
-        size_t b1 = 0, b2 = 0;
-        if (ok && c->n_graphs == 1 && Q == 128 && F % 64 == 0 &&
-            pick_slice_width((size_t)2 * c->n, Q, &b1, 56) == 64 && pick_slice_width((size_t)c->m, Q, &b2, 112) == 64) {
-            CK_CUDA(c, c->CL4P.alloc(Mt * Q));
-            CK_CUDA(c, c->VMSGP.alloc(Mt * Q));
-            CK_CUDA(c, c->CNEWb.alloc(Mt * F));
-            fm::FusedMlp& f = c->fused_clause_panel;
-            f = c->fused[FC];
-            f.p.out = {c->VMSGP.p, 64, 1, c->CNEWb.p, F, 1, Q};
-            f.p.out0_panel_rows = c->Mt;
-            f.p.a_split_kb = (F + Q) / 64;
-            f.p.a2_panel_rows = c->Mt;
-            if (tc::make_bf16_map(&f.map_a2, c->CL4P.p, (long long)(Q / 64) * c->Mt, 64, 64, f.p.a_box_rows) && fm::plan_fused(f)) {
-                f.p.a_split_kb = (F + Q) / 64; f.p.a2_panel_rows = c->Mt; f.p.out0_panel_rows = c->Mt;
-                c->panel_ready = true;
-            }
-        }
-    }
-    {   // TMA-staged gathers: one formula per chain whose tables fit in shared memory twice
-        c->tma_clause_ready = c->tma_literal_ready = false;
-        if (c->n_graphs == 1 && 2 * Q <= 256) {
-            tg::GatherPlan& gc = c->gp_clause;
-            gc.width = 2 * Q; gc.slices = 1;
-            gc.boxes = (c->n + 255) / 256;
-            gc.box_rows = (c->n + gc.boxes - 1) / gc.boxes;
-            gc.table_bytes = gc.boxes * gc.box_rows * gc.width * 2;
-            gc.smem_bytes = 4 * gc.table_bytes + 64 + 128;
-            if (gc.smem_bytes <= 226 * 1024 &&
-                tc::make_bf16_map_plain(&c->map_g_lit, c->LITb.p, c->Nt, 2 * Q, 2 * Q, 2 * Q, gc.box_rows) &&
-                tc::make_bf16_map_plain(&c->map_g_sp, c->QSb.p + Q, c->Nt, 2 * Q, 3 * Q, 2 * Q, gc.box_rows))
-                c->tma_clause_ready = true;
-        }
-        if (c->n_graphs == 1 && tg::plan_gather(c->m, Q, 128, &c->gp_literal)) {
-            const tg::GatherPlan& gl = c->gp_literal;
-            if (tc::make_bf16_map_plain(&c->map_g_cl, c->CROWb.p + F + Q, c->Mt, Q, c->ldc(), gl.width, gl.box_rows) &&
-                tc::make_bf16_map_plain(&c->map_g_ms, c->COUTb.p, c->Mt, Q, Q + F, gl.width, gl.box_rows))
-                c->tma_literal_ready = true;
-        }
     }
     c->has_tc_buffers = true;
     return DSAT_OK;
@@ -421,8 +367,7 @@ void release_buffers(dsat_ctx* c) {
 #ifdef DSAT_WITH_TCGEN05
     c->VROWb.release(); c->CROWb.release(); c->H1b.release(); c->H2b.release(); c->QSb.release(); c->LITb.release();
     c->CHb.release(); c->COUTb.release(); c->UOUTb.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
-    c->O1b.release(); c->CL4P.release(); c->VMSGP.release(); c->CNEWb.release();
-    c->panel_ready = false;
+    c->O1b.release();
     c->has_tc_buffers = false;
 #endif
     c->has_buffers = false;
@@ -489,10 +434,6 @@ LossScalars loss_scalars(float noise_scale) {
 static inline bool use_tc(const dsat_ctx* c) { return c->precision == DSAT_BF16 || c->precision == DSAT_BF16_UNFUSED; }
 static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p : nullptr; }
 static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : nullptr; }
-static inline bool panel_now(const dsat_ctx* c) {
-    return c->precision == DSAT_BF16 && c->fused_ready && c->use_fused && c->panel_ready && c->use_panels &&
-           c->use_smem_gather && !c->use_tma_gather;
-}
 #else
 static inline bool use_tc(const dsat_ctx*) { return false; }
 static inline __nv_bfloat16* vrow_b(dsat_ctx*) { return nullptr; }
@@ -562,11 +503,7 @@ int run_linear_tc(dsat_ctx* c, int op, long long rows, int epi, void* p0, int ld
 #ifdef DSAT_WITH_TCGEN05
 int run_fused(dsat_ctx* c, int which, int prof_class) {
     prof_mark(c, prof_class);
-    if (which == 2 && panel_now(c)) {
-        CK_CUDA(c, fm::launch_fused(c->fused_clause_panel, c->sm_count, c->stream));
-    } else {
-        CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
-    }
+    CK_CUDA(c, fm::launch_fused(c->fused[which], c->sm_count, c->stream));
     c->launches++;
     return DSAT_OK;
 }
@@ -598,43 +535,19 @@ static bool idx_fits(size_t table_bytes, int idx_vecs) {
     return sm_bytes / (with_idx + reserved) == sm_bytes / (table_bytes + reserved);
 }
 
-template <typename K>
-static bool set_dyn_smem(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
-}
 
 bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
-    if (c->tma_clause_ready && c->use_tma_gather && (c->Q == 128 || c->Q == 64)) {
-        const int grid = c->chains < c->sm_count ? c->chains : c->sm_count;
-        const tg::GatherPlan& gp = c->gp_clause;
-        if (c->Q == 128) {
-            static bool ok = set_dyn_smem(tg::clause_gather_tma_kernel<4>);
-            if (ok) {
-                tg::clause_gather_tma_kernel<4><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
-                    c->map_g_lit, c->map_g_sp, g, c->chains, gp, c->CROWb.p, c->ldc(), c->F);
-                return true;
-            }
-        } else {
-            static bool ok = set_dyn_smem(tg::clause_gather_tma_kernel<2>);
-            if (ok) {
-                tg::clause_gather_tma_kernel<2><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
-                    c->map_g_lit, c->map_g_sp, g, c->chains, gp, c->CROWb.p, c->ldc(), c->F);
-                return true;
-            }
-        }
-    }
     if (c->n_graphs != 1 || !c->use_smem_gather) return false;
     size_t bytes = 0;
     const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes, 56);    // measured best at cfg2: 4 CTAs per SM
     if (!w) return false;
-    __nv_bfloat16* cl4p = (panel_now(c) && w == 64) ? c->CL4P.p : nullptr;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
     const int Q = c->Q;
     const bool si = c->use_idx16 && idx_fits(bytes, g.cl_idx16_vecs);
     const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
     auto launch = [&](auto kernel) -> bool {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
-        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, c->ldc(), c->F, cl4p, c->Mt);
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, c->ldc(), c->F);
         return true;
     };
     if (w == 128) return si ? launch(clause_gather_smem_kernel<128, true>) : launch(clause_gather_smem_kernel<128, false>);
@@ -643,44 +556,18 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
 }
 
 bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
-    if (c->tma_literal_ready && c->use_tma_gather) {
-        const tg::GatherPlan& gp = c->gp_literal;
-        const int items = c->chains * gp.slices;
-        const int grid = items < c->sm_count ? items : c->sm_count;
-        if (gp.width == 128) {
-            static bool ok = set_dyn_smem(tg::literal_gather_tma_kernel<4>);
-            if (ok) {
-                tg::literal_gather_tma_kernel<4><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
-                    c->map_g_cl, c->map_g_ms, g, c->chains, c->Q, gp, c->QSb.p, 3 * c->Q, c->VROWb.p, c->ldv(),
-                    c->F + DSAT_AUX_PAD);
-                return true;
-            }
-        } else if (gp.width == 64) {
-            static bool ok = set_dyn_smem(tg::literal_gather_tma_kernel<2>);
-            if (ok) {
-                tg::literal_gather_tma_kernel<2><<<grid, tg::THREADS, gp.smem_bytes, c->stream>>>(
-                    c->map_g_cl, c->map_g_ms, g, c->chains, c->Q, gp, c->QSb.p, 3 * c->Q, c->VROWb.p, c->ldv(),
-                    c->F + DSAT_AUX_PAD);
-                return true;
-            }
-        }
-    }
     if (c->n_graphs != 1 || !c->use_smem_gather) return false;
     size_t bytes = 0;
     const int w = pick_slice_width((size_t)c->m, c->Q, &bytes, 112);
     if (!w) return false;
-    const bool pn = panel_now(c) && w == 64;
-    const __nv_bfloat16* cl4_src = pn ? c->CL4P.p : c->CROWb.p;
-    const __nv_bfloat16* msg_src = pn ? c->VMSGP.p : c->COUTb.p;
-    const long long prow = pn ? c->Mt : 0;
     dim3 grid((unsigned)c->chains, (unsigned)(c->Q / w));
     const int Q = c->Q, F = c->F;
     const bool si = c->use_idx16 && idx_fits(bytes, g.lit_idx16_vecs);
     const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
     auto launch = [&](auto kernel) -> bool {
         if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
-        kernel<<<grid, 512, smem, c->stream>>>(g, Q, cl4_src, c->ldc(), F + Q, msg_src, Q + F, c->QSb.p, 3 * Q, c->VROWb.p,
-                                               c->ldv(), F + DSAT_AUX_PAD, prow);
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F, c->QSb.p, 3 * Q, c->VROWb.p,
+                                               c->ldv(), F + DSAT_AUX_PAD);
         return true;
     };
     if (w == 128) return si ? launch(literal_gather_smem_kernel<128, true>) : launch(literal_gather_smem_kernel<128, false>);
@@ -788,8 +675,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
 #ifdef DSAT_WITH_TCGEN05
         else
             pairnorm_bf16_kernel<32 * V><<<grid, PN_WARPS * 32, 0, c->stream>>>(
-                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, panel_now(c) ? c->CNEWb.p : c->COUTb.p,
-                panel_now(c) ? F : Q + F, panel_now(c) ? 0 : Q, c->CROWb.p, ldc, nullptr, 0);
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUTb.p, Q + F, Q, c->CROWb.p, ldc, nullptr, 0);
 #endif
     });
     if (rc) return rc;
@@ -944,12 +830,8 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e) c->use_spmm_order = e[0] != '0';
         e = getenv("DSAT_IDX16");
         if (e) c->use_idx16 = e[0] != '0';
-        e = getenv("DSAT_PANELS");
-        if (e) c->use_panels = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
         if (e && e[0] == '0') c->use_smem_gather = false;
-        e = getenv("DSAT_TMA_GATHER");
-        if (e) c->use_tma_gather = e[0] != '0';
     }
 #endif
     *out = c;

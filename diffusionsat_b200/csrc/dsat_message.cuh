@@ -300,9 +300,7 @@ __global__ void __launch_bounds__(1024)
 clause_gather_smem_kernel(UnitGraphDev g, int Q,
                           const __nv_bfloat16* __restrict__ LIT, int ld_lit,
                           const __nv_bfloat16* __restrict__ SP, int ld_sp, int sp_off,
-                          __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off,
-                          __nv_bfloat16* __restrict__ CL4P, long long panel_rows) {
-    // CL4P != nullptr (needs W == 64): 4*clauses_loss goes to 64-column panels [Q/64][panel_rows][64] instead of OUT
+                          __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off) {
     using T = __nv_bfloat16;
     constexpr int LPR = W / 8, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -353,8 +351,7 @@ clause_gather_smem_kernel(UnitGraphDev g, int Q,
             for (int i = 0; i < 8; ++i) { ol[i] = al.v[i] * rw; os[i] = 4.0f * __expf(-as.v[i]); }
             T* dst = OUT + ((size_t)chain * g.m + j) * ld_out + out_off + slice * W;
             reinterpret_cast<uint4*>(dst)[li] = pack8(ol);
-            if (CL4P) reinterpret_cast<uint4*>(CL4P + ((size_t)slice * panel_rows + (size_t)chain * g.m + j) * 64)[li] = pack8(os);
-            else reinterpret_cast<uint4*>(dst + Q)[li] = pack8(os);
+            reinterpret_cast<uint4*>(dst + Q)[li] = pack8(os);
         }
     }
 }
@@ -366,8 +363,7 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
                            const __nv_bfloat16* __restrict__ CL4, int ld_cl, int cl_off,
                            const __nv_bfloat16* __restrict__ MSG, int ld_msg,
                            const __nv_bfloat16* __restrict__ QRY, int ld_q,
-                           __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off, long long panel_rows) {
-    // panel_rows > 0 (needs W == 64): CL4 and MSG are 64-column panels [Q/64][panel_rows][64] (contiguous per slice)
+                           __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off) {
     using T = __nv_bfloat16;
     constexpr int LPR = W / 8, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -381,9 +377,9 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
 #ifdef DSAT_GATHER_TRACE
     const long long t_start = clock64();
 #endif
-    if (panel_rows > 0) {
-        stage_rows_async<T>(t_cl, CL4 + ((size_t)slice * panel_rows + cbase) * 64, g.m, 64, W, tid, blockDim.x);
-        stage_rows_async<T>(t_ms, MSG + ((size_t)slice * panel_rows + cbase) * 64, g.m, 64, W, tid, blockDim.x);
+    if (ld_cl == W && ld_msg == W) {   // dense [m, W] tables (Q == W): constant row pitch
+        stage_rows_async<T>(t_cl, CL4 + cbase * W + cl_off, g.m, W, W, tid, blockDim.x);
+        stage_rows_async<T>(t_ms, MSG + cbase * W, g.m, W, W, tid, blockDim.x);
     } else {
         stage_rows_async<T>(t_cl, CL4 + cbase * ld_cl + cl_off + slice * W, g.m, ld_cl, W, tid, blockDim.x);
         stage_rows_async<T>(t_ms, MSG + cbase * ld_msg + slice * W, g.m, ld_msg, W, tid, blockDim.x);

@@ -61,9 +61,6 @@ struct FmParams {
     int stage_in_h;        // the output staging of a tile aliases its (by then dead) hidden region, at byte offset stage_off
     int stage_off;
     int a_slots;           // > 0: layer 0's A operand streams through an input ring of that many 16 KB blocks
-    int a_split_kb;        // k-blocks >= a_split_kb of the INPUT tile come from map_a2 (panel-major source), 1<<20 = never
-    long long a2_panel_rows;  // rows per 64-column panel of that source
-    long long out0_panel_rows;   // > 0: output columns [0, split) go to 64-column panels of this many rows (bf16)
     int stage_row;         // bytes per staged output row: 80 when every output is bf16 (64 B + pad), else 144
     int bias_total;        // floats in the shared bias array
     int smem_pad;          // bytes the plan reserved for aligning the dynamic shared memory base to 1024
@@ -276,7 +273,6 @@ struct EpiCtx {           // loop-invariant scalars of one (tile, layer) epilogu
     int N, epi, cpar, cstep, r, lane, qmaps, stage_row;
     size_t row_first; int rows_left;
     void* ptr0; void* ptr1; int ld0, ld1, bf0, bf1, split;
-    long long out0_panel_rows;
     bool skip;
 };
 
@@ -297,13 +293,8 @@ __device__ __forceinline__ void epi_process(const EpiCtx& e, const uint32_t (&ra
     const bool second = e.ptr1 != nullptr && c >= e.split;
     uint8_t* gbase = reinterpret_cast<uint8_t*>(second ? e.ptr1 : e.ptr0);
     const int is_bf16 = second ? e.bf1 : e.bf0;
-    size_t pitch = (size_t)(second ? e.ld1 : e.ld0) * (is_bf16 ? 2 : 4);
-    int cc = second ? c - e.split : c;
-    if (!second && e.out0_panel_rows > 0) {     // panel-major bf16 output: 64-column panels of dense 128-byte rows
-        gbase += (size_t)(c >> 6) * (size_t)e.out0_panel_rows * 128;
-        pitch = 128;
-        cc = c & 63;
-    }
+    const size_t pitch = (size_t)(second ? e.ld1 : e.ld0) * (is_bf16 ? 2 : 4);
+    const int cc = second ? c - e.split : c;
     const int valid = min(32, e.N - c);
     if (is_bf16 && e.epi != tc::TC_QUERY) {
         uint4 w[4];
@@ -367,8 +358,7 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint32_t tmem_empty_a
 
 template <bool TIMING, bool PAIR>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
-                 const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                  const __grid_constant__ CUtensorMap map_w2, FmParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -487,10 +477,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if constexpr (PAIR) mbar_expect_tx_at(at_leader(bar), bytes); else mbar_expect_tx(bar, bytes);
             };
             auto load_a_block = [&](uint8_t* dst, uint64_t* bar, int kb, int tile) {
-                if (kb < p.a_split_kb)
-                    load_2d(dst, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
-                else         // panel-major source: panel (kb - a_split_kb) is a dense [rows, 64] matrix
-                    load_2d(dst, &map_a2, bar, 0, (int)((kb - p.a_split_kb) * p.a2_panel_rows) + tile * BLOCK_M);
+                load_2d(dst, &map_a, bar, kb * BLOCK_K, tile * BLOCK_M);
             };
             for (int j0 = 0; j0 < nt; j0 += group)
                 for (int l = 0; l < n_layers; ++l)
@@ -602,7 +589,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         e.skip = (p.dbg & 1) != 0;
         e.ptr0 = p.out.ptr0; e.ptr1 = p.out.ptr1; e.ld0 = p.out.ld0; e.ld1 = p.out.ld1;
         e.bf0 = p.out.bf16_0; e.bf1 = p.out.bf16_1; e.split = p.out.split;
-        e.out0_panel_rows = p.out0_panel_rows;
         const uint32_t bias_addr0 = smem_u32(bias_s);
         const uint32_t stage_off = (uint32_t)(warp - 2) * (32 * p.stage_row);
         for (int j0 = 0; j0 < nt; j0 += group)
@@ -660,7 +646,6 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
 struct FusedMlp {
     CUtensorMap map_a;
-    CUtensorMap map_a2;        // optional panel-major second source of the input tile (see FmParams::a_split_kb)
     CUtensorMap map_w[MAX_LAYERS];
     FmParams p;
     int smem_bytes;
@@ -826,14 +811,14 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (f.p.prof) return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<true, true>, f.map_a, f.map_a2, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
-        return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<false, true>, f.map_a, f.map_a2, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
+        if (f.p.prof) return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<true, true>, f.map_a, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
+        return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<false, true>, f.map_a, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
     }
     const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
     if (f.p.prof)   // instrumented build of the same kernel (dsat_profile_fused)
-        fused_mlp_kernel<true, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
+        fused_mlp_kernel<true, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
     else
-        fused_mlp_kernel<false, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_a2, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
+        fused_mlp_kernel<false, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
     return cudaGetLastError();
 }
 
