@@ -296,7 +296,7 @@ __device__ __forceinline__ void stage_rows(T* __restrict__ dst, const T* __restr
 
 // clause side: tables LIT[2n][W] and SP[2n][W] of the chain's slice (row = literal code 2*var+sign)
 template <int W, bool SI>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512, 3)     // 40 registers: three CTAs per SM measured best (4 spills, 2 leaves latency exposed)
 clause_gather_smem_kernel(UnitGraphDev g, int Q,
                           const __nv_bfloat16* __restrict__ LIT, int ld_lit,
                           const __nv_bfloat16* __restrict__ SP, int ld_sp, int sp_off,
@@ -339,7 +339,22 @@ clause_gather_smem_kernel(UnitGraphDev g, int Q,
         }
         Acc8 al, as;
         acc8_zero(al); acc8_zero(as);
-        for (int e = e0; e < e1; ++e) {
+        int e = e0;
+        for (; e + 3 <= e1; e += 3) {      // 3-SAT: all six table reads of a clause in flight before the first add
+            const int c0 = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
+            const int c1 = SI ? (int)s_idx[g.cl_col_off + e + 1] : __ldg(g.cl_lit + e + 1);
+            const int c2 = SI ? (int)s_idx[g.cl_col_off + e + 2] : __ldg(g.cl_lit + e + 2);
+            const uint4 l0 = reinterpret_cast<const uint4*>(t_lit + (size_t)c0 * W)[li];
+            const uint4 p0 = reinterpret_cast<const uint4*>(t_sp + (size_t)c0 * W)[li];
+            const uint4 l1 = reinterpret_cast<const uint4*>(t_lit + (size_t)c1 * W)[li];
+            const uint4 p1 = reinterpret_cast<const uint4*>(t_sp + (size_t)c1 * W)[li];
+            const uint4 l2 = reinterpret_cast<const uint4*>(t_lit + (size_t)c2 * W)[li];
+            const uint4 p2 = reinterpret_cast<const uint4*>(t_sp + (size_t)c2 * W)[li];
+            acc8_add(al, l0); acc8_add(as, p0);
+            acc8_add(al, l1); acc8_add(as, p1);
+            acc8_add(al, l2); acc8_add(as, p2);
+        }
+        for (; e < e1; ++e) {
             const int code = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
             acc8_add(al, reinterpret_cast<const uint4*>(t_lit + (size_t)code * W)[li]);
             acc8_add(as, reinterpret_cast<const uint4*>(t_sp + (size_t)code * W)[li]);
