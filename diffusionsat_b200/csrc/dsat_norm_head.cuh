@@ -23,6 +23,9 @@ __device__ __forceinline__ int lane_col(int lane, int i) {
 // it is what variables_output reads (:283).  TS / TX = storage type of the input and of the state
 // (float on the fp32 path, bf16 on the tensor-core path; the arithmetic is fp32 either way).
 constexpr int PN_WARPS = 8;
+#ifndef PN_BF16_CTAS
+#define PN_BF16_CTAS 4     // resident CTAs per SM of pairnorm_bf16_kernel (64 registers); 3: -6 %, 5 spills: -40 %
+#endif
 constexpr int PN_UNROLL = 4;      // rows in flight per warp (memory-level parallelism)
 
 template <int V, typename TS, typename TX>
@@ -126,7 +129,7 @@ __device__ __forceinline__ float bernoulli_kl(float pa, float pb) {
 // PN_UNROLL row groups in flight give twice the bytes in flight per warp.  Same arithmetic (fp32), different summation
 // order than the generic kernel.
 template <int F>
-__global__ void __launch_bounds__(PN_WARPS * 32)
+__global__ void __launch_bounds__(PN_WARPS * 32, PN_BF16_CTAS)
 pairnorm_bf16_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
                      const __nv_bfloat16* __restrict__ SRC, int ld_src, int src_off,
                      __nv_bfloat16* __restrict__ STATE, int ld_state,
