@@ -417,51 +417,62 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
         const bool live = v0 + sub < g.n;
         int v = 0;
         if (live) v = SI ? (int)s_idx[g.lit_ord_off + v0 + sub] : __ldg(g.var_order + v0 + sub);
-        Acc8 s4[2], ms[2];
+        // the epilogue's global operands are requested first: their L2 latency hides under the entry loops
+        const size_t row = (size_t)chain * g.n + v;
+        T* dst = OUT + row * ld_out + out_off + slice * W;
+        uint4 qraw = make_uint4(0u, 0u, 0u, 0u);
+        float vw = 0.f, dw[2] = {0.f, 0.f};
+        if (live) {
+            qraw = __ldg(reinterpret_cast<const uint4*>(QRY + row * ld_q + slice * W) + li);
+            vw = __ldg(g.vdeg_w + v);
+            dw[0] = __ldg(g.deg_w + 2 * v); dw[1] = __ldg(g.deg_w + 2 * v + 1);
+        }
+        Acc8 s4[2];
 #pragma unroll
         for (int sgn = 0; sgn < 2; ++sgn) {
-            acc8_zero(s4[sgn]); acc8_zero(ms[sgn]);
+            Acc8 ms;
+            acc8_zero(s4[sgn]); acc8_zero(ms);
             const int code = 2 * v + sgn;
             int e0 = 0, e1 = 0;
             if (live) {
                 if constexpr (SI) { e0 = s_idx[code]; e1 = s_idx[code + 1]; }
                 else { e0 = __ldg(g.lit_rowptr + code); e1 = __ldg(g.lit_rowptr + code + 1); }
             }
+            auto col = [&](int e) { return SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e); };
             int e = e0;
-            for (; e + 2 <= e1; e += 2) {
-                const int j0 = SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e);
-                const int j1 = SI ? (int)s_idx[g.lit_col_off + e + 1] : __ldg(g.lit_clause + e + 1);
+            for (; e + 3 <= e1; e += 3) {      // three entries = six table reads in flight
+                const int j0 = col(e), j1 = col(e + 1), j2 = col(e + 2);
                 const uint4 a0 = reinterpret_cast<const uint4*>(t_cl + (size_t)j0 * W)[li];
                 const uint4 b0 = reinterpret_cast<const uint4*>(t_ms + (size_t)j0 * W)[li];
                 const uint4 a1 = reinterpret_cast<const uint4*>(t_cl + (size_t)j1 * W)[li];
                 const uint4 b1 = reinterpret_cast<const uint4*>(t_ms + (size_t)j1 * W)[li];
-                acc8_add(s4[sgn], a0); acc8_add(ms[sgn], b0);
-                acc8_add(s4[sgn], a1); acc8_add(ms[sgn], b1);
+                const uint4 a2 = reinterpret_cast<const uint4*>(t_cl + (size_t)j2 * W)[li];
+                const uint4 b2 = reinterpret_cast<const uint4*>(t_ms + (size_t)j2 * W)[li];
+                acc8_add(s4[sgn], a0); acc8_add(ms, b0);
+                acc8_add(s4[sgn], a1); acc8_add(ms, b1);
+                acc8_add(s4[sgn], a2); acc8_add(ms, b2);
             }
-            if (e < e1) {
-                const int j = SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e);
+            for (; e < e1; ++e) {
+                const int j = col(e);
                 acc8_add(s4[sgn], reinterpret_cast<const uint4*>(t_cl + (size_t)j * W)[li]);
-                acc8_add(ms[sgn], reinterpret_cast<const uint4*>(t_ms + (size_t)j * W)[li]);
+                acc8_add(ms, reinterpret_cast<const uint4*>(t_ms + (size_t)j * W)[li]);
+            }
+            if (live) {                        // this polarity's message sum leaves right away (fewer live accumulators)
+                float lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) lo[i] = ms.v[i] * dw[sgn];
+                reinterpret_cast<uint4*>(dst + (1 + sgn) * Q)[li] = pack8(lo);
             }
         }
         if (live) {
-            const size_t row = (size_t)chain * g.n + v;
-            float q[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(QRY + row * ld_q + slice * W) + li), q);
-            const float vw = __ldg(g.vdeg_w + v);
-            const float dwp = __ldg(g.deg_w + 2 * v), dwn = __ldg(g.deg_w + 2 * v + 1);
-            float grad[8], lp[8], ln[8];
+            float q[8], grad[8];
+            unpack8(qraw, q);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float sg = 1.0f / (1.0f + __expf(-q[i]));
                 grad[i] = (-sg * s4[0].v[i] + (1.0f - sg) * s4[1].v[i]) * vw;
-                lp[i] = ms[0].v[i] * dwp;
-                ln[i] = ms[1].v[i] * dwn;
             }
-            T* dst = OUT + row * ld_out + out_off + slice * W;
             reinterpret_cast<uint4*>(dst)[li] = pack8(grad);
-            reinterpret_cast<uint4*>(dst + Q)[li] = pack8(lp);
-            reinterpret_cast<uint4*>(dst + 2 * Q)[li] = pack8(ln);
         }
     }
 #ifdef DSAT_GATHER_TRACE
