@@ -298,12 +298,14 @@ int ensure_tc_buffers(dsat_ctx* c) {
                 f.ping_pong = ((pp_mask >> which) & 1) != 0;
                 static const int pair_mask = getenv("DSAT_PAIR_MODE") ? atoi(getenv("DSAT_PAIR_MODE")) : 0;
                 f.pair_mode = ((pair_mask >> which) & 1) != 0;
+                static const int split_on = getenv("DSAT_SPLIT_MODE") ? atoi(getenv("DSAT_SPLIT_MODE")) : 1;
+                f.split_mode = split_on != 0;       // takes effect only where every hidden layer is 512 wide (the literal MLP)
             }
             if (!fm::plan_fused(f)) return false;
             if (getenv("DSAT_PLAN_LOG"))
                 fprintf(stderr, "[dsat] fused mlp %d: smem %d B (pad %d), hidden blocks %d x%d, input ring %d, weight ring %d x %d B, "
-                        "epilogue warps %d, ping-pong %d, staging in hidden %d, cta pair %d\n", which, f.smem_bytes, f.p.smem_pad, f.p.ah_blocks,
-                        f.p.pp ? 2 : 1, f.p.a_slots, f.p.slots, f.p.slot_bytes, f.p.epi_warps, f.p.pp, f.p.stage_in_h, f.p.pair);
+                        "epilogue warps %d, ping-pong %d, staging in hidden %d, cta pair %d, split %d (%d steps)\n", which, f.smem_bytes, f.p.smem_pad, f.p.ah_blocks,
+                        f.p.pp ? 2 : 1, f.p.a_slots, f.p.slots, f.p.slot_bytes, f.p.epi_warps, f.p.pp, f.p.stage_in_h, f.p.pair, f.p.split, f.p.n_steps);
             return true;
         };
         auto W = [&](int op) { return (const __nv_bfloat16*)c->ops[op].w_bf16.p; };

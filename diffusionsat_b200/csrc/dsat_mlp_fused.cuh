@@ -42,6 +42,9 @@ constexpr int STAGE_BYTES = 4 * 32 * STAGE_ROW;            // four epilogue warp
 constexpr int BAR_BYTES = 512;
 constexpr int MAX_A_SLOTS = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
+#ifndef DSAT_EPI_SERIAL_HIDDEN
+#define DSAT_EPI_SERIAL_HIDDEN 0      // 1: hidden epilogues drain TMEM one chunk at a time (no second register buffer)
+#endif
 
 struct FmLayer {
     int K, N;              // multiples of 16; N <= 512
@@ -50,6 +53,14 @@ struct FmLayer {
     int bias_off;          // offset of this layer's biases in the shared bias array
     const float* bias;
 };
+
+// One accumulator-sized piece of work in split mode: columns [n0, n0 + N) of one layer, N <= 256.
+struct FmStep {
+    short layer, n0, N;
+    char hidden;           // the result goes to the hidden region (blocks n0/64 ...), else to global memory
+    char wait_next;        // its epilogue overwrites shared memory that the NEXT step's MMAs still read
+};
+constexpr int MAX_STEPS = 6;
 
 struct FmParams {
     int n_layers;
@@ -65,6 +76,9 @@ struct FmParams {
     int bias_total;        // floats in the shared bias array
     int smem_pad;          // bytes the plan reserved for aligning the dynamic shared memory base to 1024
     int epi_warps;         // 4 or 8 epilogue warps: with 8, two warps share a TMEM lane quadrant and alternate 32-column chunks
+    int split;             // split mode (fused_mlp_split_kernel): 512-wide layers run as two 256-column steps, see below
+    int n_steps;
+    FmStep step[MAX_STEPS];
     TcOut out;
     long long* prof;       // optional [16] cycle counters of CTA 0 (wait/work breakdown), nullptr = off
 };
@@ -341,17 +355,40 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint32_t tmem_empty_a
         if (!HIDDEN) { tc::tcgen05_fence_before(); arrive_addr<PAIR>(tmem_empty_addr); }
         return;
     }
+    if constexpr (!HIDDEN || DSAT_EPI_SERIAL_HIDDEN) {
 #pragma unroll 1
-    for (int c = 32 * e.cpar; c < e.N; c += e.cstep) {
-        uint32_t ra[32];
-        tmem_ld_32cols_async(e.lane_addr + (uint32_t)c, ra);
-        tmem_ld_wait(ra);
-        if (!HIDDEN && c + e.cstep >= e.N) {     // last TMEM read of this warp: hand the accumulator back early
-            tc::tcgen05_fence_before();
-            arrive_addr<PAIR>(tmem_empty_addr);
-            released = true;
+        for (int c = 32 * e.cpar; c < e.N; c += e.cstep) {
+            uint32_t ra[32];
+            tmem_ld_32cols_async(e.lane_addr + (uint32_t)c, ra);
+            tmem_ld_wait(ra);
+            if (!HIDDEN && c + e.cstep >= e.N) {     // last TMEM read of this warp: hand the accumulator back early
+                tc::tcgen05_fence_before();
+                arrive_addr<PAIR>(tmem_empty_addr);
+                released = true;
+            }
+            epi_process<HIDDEN>(e, ra, c);
         }
-        epi_process<HIDDEN>(e, ra, c);
+    } else {
+        // hidden layers (the MMA warp waits for these): two register buffers, chunk c + cstep is on its way out of
+        // TMEM while chunk c is processed.  (The final epilogue keeps one buffer: its store path needs the registers.)
+        int c = 32 * e.cpar;
+        if (c < e.N) {
+            uint32_t ra[32], rb[32];
+            tmem_ld_32cols_async(e.lane_addr + (uint32_t)c, ra);
+#pragma unroll 1
+            while (true) {
+                tmem_ld_wait(ra);
+                const int c1 = c + e.cstep;
+                if (c1 < e.N) tmem_ld_32cols_async(e.lane_addr + (uint32_t)c1, rb);
+                epi_process<HIDDEN>(e, ra, c);
+                if (c1 >= e.N) break;
+                tmem_ld_wait(rb);
+                c = c1 + e.cstep;
+                if (c < e.N) tmem_ld_32cols_async(e.lane_addr + (uint32_t)c, ra);
+                epi_process<HIDDEN>(e, rb, c1);
+                if (c >= e.N) break;
+            }
+        }
     }
     if (!HIDDEN && !released) { tc::tcgen05_fence_before(); arrive_addr<PAIR>(tmem_empty_addr); }
 }
@@ -644,6 +681,184 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+
+// ---- Split mode: an MLP whose hidden layers are 512 wide (the literal MLP: 144 -> 512 -> 512 -> 256) fills all 512
+// TMEM columns with one layer, so in fused_mlp_kernel every epilogue runs with the tensor pipe idle -- and draining
+// TMEM is slow (about 64 B per cycle and SM: 8 N cycles for a [128, N] fp32 accumulator against N K / 32 for its MMAs).
+// Here the work of a tile is a sequence of STEPS of at most 256 columns,
+//        L1[0:256) L1[256:512) L2[0:256) L2[256:512) L3
+// that alternate between the two accumulator halves (step g uses half g & 1, across tiles too), so the epilogue of one
+// step runs under the MMAs of the next one wherever the data allow it:
+//   * a layer reading the hidden region waits for blocks 0-3 (h_full[0]) before k-block 0 and for blocks 4-7
+//     (h_full[1]) before k-block 4: L2's first half starts while L1's second half is still draining;
+//   * the epilogue of a first half overwrites shared memory that the second half's MMAs still read (the input tile,
+//     or the previous hidden layer), so it also waits for the NEXT step's tmem_full (FmStep::wait_next);
+//   * the last step's output drains while the next tile's first step already accumulates in the other half.
+// Input tile resident in AH (blocks 0 ..), one hidden region, weight ring as in fused_mlp_kernel.
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
+                       const __grid_constant__ CUtensorMap map_w2, FmParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if ((int)(smem - smem_raw) > p.smem_pad) __trap();
+    uint8_t* ah = smem;
+    uint8_t* ring = smem + (size_t)p.ah_blocks * AH_BLOCK_BYTES;
+    uint8_t* stage_all = ring + (size_t)p.slots * p.slot_bytes;
+    uint8_t* tail = stage_all + (p.stage_in_h ? 0 : (size_t)p.epi_warps * 32 * p.stage_row);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* ah_free = a_full + 1;
+    uint64_t* h_full = a_full + 2;                     // [2]: hidden blocks 0-3 / 4-7 written
+    uint64_t* tmem_full = a_full + 4;                  // [2]
+    uint64_t* tmem_empty = a_full + 6;                 // [2]
+    uint64_t* ring_full = a_full + 8;                  // [MAX_SLOTS]
+    uint64_t* ring_empty = a_full + 8 + MAX_SLOTS;     // [MAX_SLOTS]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 8 + 2 * MAX_SLOTS + 2 * MAX_A_SLOTS);
+    float* bias_s = reinterpret_cast<float*>(tail + BAR_BYTES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int epi_threads = 32 * p.epi_warps;
+    const CUtensorMap* map_w[MAX_LAYERS] = {&map_w0, &map_w1, &map_w2};
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(ah_free, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&h_full[b], epi_threads);
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], epi_threads);
+        }
+        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (warp >= 2) {
+        for (int l = 0; l < p.n_layers; ++l)
+            for (int i = threadIdx.x - 64; i < p.layer[l].N; i += epi_threads) bias_s[p.layer[l].bias_off + i] = __ldg(p.layer[l].bias + i);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nv = p.n_steps;
+    const int nt = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_hidden = p.n_layers - 1;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ================================ TMA producer
+            const int k0_blocks = (p.layer[0].K + BLOCK_K - 1) / BLOCK_K;
+            int slot = 0; uint32_t phase = 0;
+            for (int j = 0; j < nt; ++j) {
+                const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+                for (int v = 0; v < nv; ++v) {
+                    const FmStep st = p.step[v];
+                    if (v == 0) {      // the input tile into AH, once the previous tile's last layer no longer reads it
+                        if (j > 0) mbar_wait(ah_free, (uint32_t)((j - 1) & 1));
+                        mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
+                        for (int kb = 0; kb < k0_blocks; ++kb)
+                            tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
+                    }
+                    const int kbs = (p.layer[st.layer].K + BLOCK_K - 1) / BLOCK_K;
+                    for (int kb = 0; kb < kbs; ++kb) {
+                        mbar_wait(&ring_empty[slot], phase ^ 1);
+                        mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[st.layer].box_rows * (BLOCK_K * 2));
+                        tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[st.layer], &ring_full[slot], kb * BLOCK_K, st.n0);
+                        if (++slot == p.slots) { slot = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {    // ================================ MMA issuer (whole warp converged, one elected lane issues)
+        int slot = 0; uint32_t phase = 0;
+        for (int j = 0; j < nt; ++j)
+            for (int v = 0; v < nv; ++v) {
+                const FmStep st = p.step[v];
+                const int g = j * nv + v, buf = g & 1, use = g >> 1;
+                mbar_wait(&tmem_empty[buf], (uint32_t)((use & 1) ^ 1));          // this accumulator half is drained
+                if (st.layer == 0) mbar_wait(a_full, (uint32_t)(j & 1));
+                tcgen05_fence_after();
+                const int K = p.layer[st.layer].K;
+                const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
+                const uint32_t idesc = make_idesc_bf16(BLOCK_M, st.N);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+                const uint32_t hphase = (uint32_t)((j * n_hidden + (st.layer - 1)) & 1);
+                for (int kb = 0; kb < kbs; ++kb) {
+                    if (st.layer > 0 && (kb & 3) == 0) {      // the next four hidden blocks are in shared memory
+                        mbar_wait(&h_full[kb >> 2], hphase);
+                        tcgen05_fence_after();
+                    }
+                    const uint64_t da = make_smem_desc_sw128(smem_u32(ah + (size_t)kb * AH_BLOCK_BYTES));
+                    const int ksteps = min(BLOCK_K / 16, (K - kb * BLOCK_K + 15) / 16);
+                    mbar_wait(&ring_full[slot], phase);
+                    const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
+                    if (ksteps == BLOCK_K / 16) {
+                        umma_bf16_kblock_commit_elect(acc, da, db, idesc, kb != 0, &ring_empty[slot]);
+                    } else {
+                        for (int k = 0; k < ksteps; ++k) umma_bf16_elect(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        tcgen05_commit_elect(&ring_empty[slot]);
+                    }
+                    if (++slot == p.slots) { slot = 0; phase ^= 1; }
+                }
+                tcgen05_commit_elect(&tmem_full[buf]);
+                if (v == nv - 1) tcgen05_commit_elect(ah_free);
+            }
+    } else {               // ================================ epilogue warps
+        const int quad = warp & 3;
+        EpiCtx e;
+        e.r = quad * 32 + lane;
+        e.lane = lane;
+        e.cpar = (warp - 2) >> 2;
+        e.cstep = 32 * (p.epi_warps >> 2);
+        e.stage_row = p.stage_row;
+        e.qmaps = p.qmaps;
+        e.skip = (p.dbg & 1) != 0;
+        e.ptr0 = p.out.ptr0; e.ptr1 = p.out.ptr1; e.ld0 = p.out.ld0; e.ld1 = p.out.ld1;
+        e.bf0 = p.out.bf16_0; e.bf1 = p.out.bf16_1; e.split = p.out.split;
+        const uint32_t bias_addr0 = smem_u32(bias_s);
+        const uint32_t stage_off = (uint32_t)(warp - 2) * (32 * p.stage_row);
+        e.stage_addr = (p.stage_in_h ? smem_u32(ah) + (uint32_t)p.stage_off : smem_u32(stage_all)) + stage_off;
+        for (int j = 0; j < nt; ++j) {
+            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+            e.row_first = (size_t)tile * BLOCK_M + quad * 32;
+            e.rows_left = p.rows - (int)e.row_first;
+            for (int v = 0; v < nv; ++v) {
+                const FmStep st = p.step[v];
+                const int g = j * nv + v, buf = g & 1, use = g >> 1;
+                e.N = st.N; e.epi = p.layer[st.layer].epi;
+                e.bl_addr = bias_addr0 + 4u * (uint32_t)(p.layer[st.layer].bias_off + st.n0);
+                e.ah_addr = smem_u32(ah) + (uint32_t)(st.n0 >> 6) * AH_BLOCK_BYTES;
+                e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
+                mbar_wait(&tmem_full[buf], (uint32_t)(use & 1));
+                if (st.wait_next) mbar_wait(&tmem_full[buf ^ 1], (uint32_t)(((g + 1) >> 1) & 1));
+                tcgen05_fence_after();
+                const uint32_t empty_addr = smem_u32(&tmem_empty[buf]);
+                if (st.hidden) {
+                    epi_drain<true, false>(e, empty_addr);
+                    tcgen05_fence_before();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    arrive_addr<false>(empty_addr);
+                    arrive_addr<false>(smem_u32(&h_full[st.n0 >> 8]));
+                } else {
+                    epi_drain<false, false>(e, empty_addr);
+                    if (p.stage_in_h) asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    }
+}
+
 struct FusedMlp {
     CUtensorMap map_a;
     CUtensorMap map_w[MAX_LAYERS];
@@ -652,6 +867,7 @@ struct FusedMlp {
     CUtensorMap map_wp[MAX_LAYERS];     // weight maps with half-height boxes (CTA-pair mode: each CTA loads half a block)
     bool stream_input = false;      // request the input ring (FmParams::a_slots), set before plan_fused
     bool ping_pong = false;         // request two tiles in flight (FmParams::pp); needs stream_input
+    bool split_mode = false;        // request split mode (fused_mlp_split_kernel) for MLPs with 512-wide hidden layers
     bool pair_mode = false;         // request the CTA-pair instantiation: half-height weight slots (map_wp), clusters of 2
 };
 
@@ -686,6 +902,8 @@ inline bool plan_fused(FusedMlp& f) {
     p.two_bufs = 1;
     p.a_slots = 0;
     p.pp = 0;
+    p.split = 0;
+    p.n_steps = 0;
     p.stage_in_h = 0;
     p.stage_off = 0;
     for (int l = 0; l < p.n_layers; ++l) {
@@ -783,6 +1001,23 @@ inline bool plan_fused(FusedMlp& f) {
         if (total <= SMEM_LIMIT) {
             p.slots = slots;
             f.smem_bytes = total;
+            // split mode: every hidden layer exactly 512 wide (two accumulator halves, two h_full halves), output <= 256
+            bool split = f.split_mode && !pair && p.n_layers >= 2 && p.layer[p.n_layers - 1].N <= 256 && p.rows > 0;
+            for (int l = 0; l + 1 < p.n_layers; ++l) split = split && p.layer[l].N == 512;
+            if (split) {
+                int n = 0;
+                for (int l = 0; l < p.n_layers; ++l) {
+                    const bool hidden = l + 1 < p.n_layers;
+                    for (int n0 = 0; n0 < p.layer[l].N; n0 += 256) {
+                        FmStep& st = p.step[n++];
+                        st.layer = (short)l; st.n0 = (short)n0; st.N = (short)min(256, p.layer[l].N - n0);
+                        st.hidden = hidden ? 1 : 0;
+                        st.wait_next = hidden && n0 + 256 < p.layer[l].N ? 1 : 0;
+                    }
+                }
+                p.n_steps = n;
+                p.split = 1;
+            }
             return true;
         }
     }
@@ -797,6 +1032,7 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -815,6 +1051,10 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<false, true>, f.map_a, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
     }
     const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
+    if (f.p.split) {    // (no instrumented build of the split kernel: dsat_profile_fused reads zeros for it)
+        fused_mlp_split_kernel<<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
+        return cudaGetLastError();
+    }
     if (f.p.prof)   // instrumented build of the same kernel (dsat_profile_fused)
         fused_mlp_kernel<true, false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
     else
