@@ -299,6 +299,7 @@ int ensure_tc_buffers(dsat_ctx* c) {
                 static const int pair_mask = getenv("DSAT_PAIR_MODE") ? atoi(getenv("DSAT_PAIR_MODE")) : 0;
                 f.pair_mode = ((pair_mask >> which) & 1) != 0;
                 static const int split_on = getenv("DSAT_SPLIT_MODE") ? atoi(getenv("DSAT_SPLIT_MODE")) : 1;
+                f.split_step_bias = (split_on & 2) == 0;  // DSAT_SPLIT_MODE=3: split mode with the whole bias array in shared memory (two weight slots)
                 f.split_mode = split_on != 0;       // takes effect only where every hidden layer is 512 wide (the literal MLP)
             }
             if (!fm::plan_fused(f)) return false;

@@ -76,6 +76,8 @@ struct FmParams {
     int bias_total;        // floats in the shared bias array
     int smem_pad;          // bytes the plan reserved for aligning the dynamic shared memory base to 1024
     int epi_warps;         // 4 or 8 epilogue warps: with 8, two warps share a TMEM lane quadrant and alternate 32-column chunks
+    int step_bias;         // split mode: only the current step's biases are in shared memory (2 x 256 floats, staged per step):
+                           // the space of the whole bias array buys a third weight slot
     int split;             // split mode (fused_mlp_split_kernel): 512-wide layers run as two 256-column steps, see below
     int n_steps;
     FmStep step[MAX_STEPS];
@@ -738,7 +740,7 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if (warp >= 2) {
+    if (!p.step_bias && warp >= 2) {
         for (int l = 0; l < p.n_layers; ++l)
             for (int i = threadIdx.x - 64; i < p.layer[l].N; i += epi_threads) bias_s[p.layer[l].bias_off + i] = __ldg(p.layer[l].bias + i);
     }
@@ -823,6 +825,19 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const uint32_t bias_addr0 = smem_u32(bias_s);
         const uint32_t stage_off = (uint32_t)(warp - 2) * (32 * p.stage_row);
         e.stage_addr = (p.stage_in_h ? smem_u32(ah) + (uint32_t)p.stage_off : smem_u32(stage_all)) + stage_off;
+        // step_bias: the biases of the step after this one travel from global memory into registers while this step
+        // is processed, and into one of two 256-float shared buffers at the start of their step
+        const int et = (int)threadIdx.x - 64;
+        float bnext[2] = {0.f, 0.f};
+        auto fetch_bias = [&](int v) {
+            const FmStep s = p.step[v];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int i = et + k * epi_threads;
+                bnext[k] = i < s.N ? __ldg(p.layer[s.layer].bias + s.n0 + i) : 0.f;
+            }
+        };
+        if (p.step_bias && nt > 0) fetch_bias(0);
         for (int j = 0; j < nt; ++j) {
             const int tile = (int)blockIdx.x + j * (int)gridDim.x;
             e.row_first = (size_t)tile * BLOCK_M + quad * 32;
@@ -831,6 +846,17 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const FmStep st = p.step[v];
                 const int g = j * nv + v, buf = g & 1, use = g >> 1;
                 e.N = st.N; e.epi = p.layer[st.layer].epi;
+                if (p.step_bias) {
+                    float* dst = bias_s + (g & 1) * 256;      // last read two steps ago; every warp passed the previous step's barrier since
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int i = et + k * epi_threads;
+                        if (i < 256) dst[i] = bnext[k];
+                    }
+                    fetch_bias(v + 1 < nv ? v + 1 : 0);
+                    asm volatile("bar.sync 2, %0;" ::"r"(epi_threads) : "memory");
+                    e.bl_addr = smem_u32(dst);
+                } else
                 e.bl_addr = bias_addr0 + 4u * (uint32_t)(p.layer[st.layer].bias_off + st.n0);
                 e.ah_addr = smem_u32(ah) + (uint32_t)(st.n0 >> 6) * AH_BLOCK_BYTES;
                 e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);
@@ -867,6 +893,7 @@ struct FusedMlp {
     CUtensorMap map_wp[MAX_LAYERS];     // weight maps with half-height boxes (CTA-pair mode: each CTA loads half a block)
     bool stream_input = false;      // request the input ring (FmParams::a_slots), set before plan_fused
     bool ping_pong = false;         // request two tiles in flight (FmParams::pp); needs stream_input
+    bool split_step_bias = true;    // split mode stages biases per step (room for one more weight slot)
     bool split_mode = false;        // request split mode (fused_mlp_split_kernel) for MLPs with 512-wide hidden layers
     bool pair_mode = false;         // request the CTA-pair instantiation: half-height weight slots (map_wp), clusters of 2
 };
@@ -903,6 +930,7 @@ inline bool plan_fused(FusedMlp& f) {
     p.a_slots = 0;
     p.pp = 0;
     p.split = 0;
+    p.step_bias = 0;
     p.n_steps = 0;
     p.stage_in_h = 0;
     p.stage_off = 0;
@@ -986,10 +1014,15 @@ inline bool plan_fused(FusedMlp& f) {
     // activations there are dead once the last layer's MMAs have completed, the next tile's input only overwrites the
     // first k0 blocks, and the next hidden epilogue comes after this one in the same warps' program order.
     const int k0_blocks_res = (p.layer[0].K + 63) / 64;
+    // split mode: every hidden layer exactly 512 wide (two accumulator halves, two h_full halves), output <= 256
+    bool split = f.split_mode && !pair && p.n_layers >= 2 && p.layer[p.n_layers - 1].N <= 256 && p.rows > 0;
+    for (int l = 0; l + 1 < p.n_layers; ++l) split = split && p.layer[l].N == 512;
+    const bool step_bias = split && f.split_step_bias;
+    const int bias_bytes = step_bias ? 2 * 256 * 4 : bias_total * 4;
     for (int ew : {8, 4}) {     // prefer 8 epilogue warps when two ring slots still fit
         const int stage_bytes = ew * 32 * p.stage_row;
         const int in_h = p.n_layers > 1 && (blocks - k0_blocks_res) * AH_BLOCK_BYTES >= stage_bytes;
-        if (pad + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4 <= SMEM_LIMIT) {
+        if (pad + blocks * AH_BLOCK_BYTES + 2 * p.slot_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_bytes <= SMEM_LIMIT) {
             p.epi_warps = ew;
             p.stage_in_h = in_h;
             p.stage_off = in_h ? k0_blocks_res * AH_BLOCK_BYTES : 0;
@@ -997,13 +1030,10 @@ inline bool plan_fused(FusedMlp& f) {
         }
     }
     for (int slots = MAX_SLOTS; slots >= 2; --slots) {
-        const int total = pad + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + (p.stage_in_h ? 0 : p.epi_warps * 32 * p.stage_row) + BAR_BYTES + bias_total * 4;
+        const int total = pad + blocks * AH_BLOCK_BYTES + slots * p.slot_bytes + (p.stage_in_h ? 0 : p.epi_warps * 32 * p.stage_row) + BAR_BYTES + bias_bytes;
         if (total <= SMEM_LIMIT) {
             p.slots = slots;
             f.smem_bytes = total;
-            // split mode: every hidden layer exactly 512 wide (two accumulator halves, two h_full halves), output <= 256
-            bool split = f.split_mode && !pair && p.n_layers >= 2 && p.layer[p.n_layers - 1].N <= 256 && p.rows > 0;
-            for (int l = 0; l + 1 < p.n_layers; ++l) split = split && p.layer[l].N == 512;
             if (split) {
                 int n = 0;
                 for (int l = 0; l < p.n_layers; ++l) {
@@ -1017,6 +1047,7 @@ inline bool plan_fused(FusedMlp& f) {
                 }
                 p.n_steps = n;
                 p.split = 1;
+                p.step_bias = step_bias ? 1 : 0;
             }
             return true;
         }
