@@ -350,11 +350,19 @@ __device__ __forceinline__ void arrive_addr(uint32_t addr) {
     else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 
+// One arrival per epilogue WARP (the barriers count warps): every lane has done its own fences, the warp converges, one
+// lane signals.  In CTA-pair mode the arrival is a remote (cluster) operation; 256 of them per barrier phase serialised.
+template <bool PAIR>
+__device__ __forceinline__ void warp_arrive(uint32_t addr, int lane) {
+    __syncwarp();
+    if (lane == 0) arrive_addr<PAIR>(addr);
+}
+
 template <bool HIDDEN, bool PAIR>
 __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint32_t tmem_empty_addr) {
     bool released = false;
     if (e.skip) {          // timing experiment: hand everything back without touching the accumulator
-        if (!HIDDEN) { tc::tcgen05_fence_before(); arrive_addr<PAIR>(tmem_empty_addr); }
+        if (!HIDDEN) { tc::tcgen05_fence_before(); warp_arrive<PAIR>(tmem_empty_addr, e.lane); }
         return;
     }
     if constexpr (!HIDDEN || DSAT_EPI_SERIAL_HIDDEN) {
@@ -365,7 +373,7 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint32_t tmem_empty_a
             tmem_ld_wait(ra);
             if (!HIDDEN && c + e.cstep >= e.N) {     // last TMEM read of this warp: hand the accumulator back early
                 tc::tcgen05_fence_before();
-                arrive_addr<PAIR>(tmem_empty_addr);
+                warp_arrive<PAIR>(tmem_empty_addr, e.lane);
                 released = true;
             }
             epi_process<HIDDEN>(e, ra, c);
@@ -392,7 +400,7 @@ __device__ __forceinline__ void epi_drain(const EpiCtx& e, uint32_t tmem_empty_a
             }
         }
     }
-    if (!HIDDEN && !released) { tc::tcgen05_fence_before(); arrive_addr<PAIR>(tmem_empty_addr); }
+    if (!HIDDEN && !released) { tc::tcgen05_fence_before(); warp_arrive<PAIR>(tmem_empty_addr, e.lane); }
 }
 
 template <bool TIMING, bool PAIR>
@@ -438,9 +446,9 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_init(a_full, NC);
         mbar_init(ah_free, 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&h_full[b], NC * epi_threads);
+            mbar_init(&h_full[b], NC * p.epi_warps);
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], NC * epi_threads);
+            mbar_init(&tmem_empty[b], NC * p.epi_warps);
         }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], NC); mbar_init(&ring_empty[s], 1); }
         for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_ring_full[s], NC); mbar_init(&a_ring_empty[s], 1); }
@@ -652,8 +660,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         // st.shared -> visible to the MMA (async proxy); the leader's MMA also reads the peer's shared memory
                         if constexpr (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
                         else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        arrive_addr<PAIR>(empty_addr);
-                        arrive_addr<PAIR>(at_leader(&h_full[st.hidx]));
+                        __syncwarp();
+                        if (lane == 0) { arrive_addr<PAIR>(empty_addr); arrive_addr<PAIR>(at_leader(&h_full[st.hidx])); }
                         if (timing) w1 += clock64() - t_epi0;
                     } else {
                         epi_drain<false, PAIR>(e, empty_addr);
@@ -725,9 +733,9 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         mbar_init(a_full, 1);
         mbar_init(ah_free, 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&h_full[b], epi_threads);
+            mbar_init(&h_full[b], p.epi_warps);
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], epi_threads);
+            mbar_init(&tmem_empty[b], p.epi_warps);
         }
         for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -868,8 +876,8 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     epi_drain<true, false>(e, empty_addr);
                     tcgen05_fence_before();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    arrive_addr<false>(empty_addr);
-                    arrive_addr<false>(smem_u32(&h_full[st.n0 >> 8]));
+                    __syncwarp();
+                    if (lane == 0) { arrive_addr<false>(empty_addr); arrive_addr<false>(smem_u32(&h_full[st.n0 >> 8])); }
                 } else {
                     epi_drain<false, false>(e, empty_addr);
                     if (p.stage_in_h) asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
