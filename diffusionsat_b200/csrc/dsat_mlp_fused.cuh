@@ -927,6 +927,11 @@ inline int dyn_smem_pad() {
     return pad;
 }
 
+inline int pair_a_slots() {
+    static const int v = getenv("DSAT_PAIR_A_SLOTS") ? atoi(getenv("DSAT_PAIR_A_SLOTS")) : 4;
+    return v < 2 ? 2 : v;
+}
+
 // shared-memory plan; returns false when the MLP does not fit
 inline bool plan_fused(FusedMlp& f) {
     FmParams& p = f.p;
@@ -1004,6 +1009,9 @@ inline bool plan_fused(FusedMlp& f) {
             int a_slots = (SMEM_LIMIT - fixed) / AH_BLOCK_BYTES;
             if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;
             if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
+            // CTA pair: weight slots are half-height (as large as an input block) and the in-order producer never runs the
+            // input ring further ahead than the weight ring lets it: the weight ring gets the larger share
+            if (p.pair && a_slots > pair_a_slots()) a_slots = pair_a_slots();
             fixed -= (w_min - 2) * p.slot_bytes;          // `fixed` below counts two weight slots
             if (a_slots >= 2 && a_slots >= (k0_blocks + 1) / 2) {
                 p.a_slots = a_slots;

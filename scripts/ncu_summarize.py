@@ -46,7 +46,7 @@ def main(report, summary_path, traffic_path=None):
     with open(summary_path, "w") as f:
         json.dump(launches, f, indent=1)
     if traffic_path:
-        mlp = [e for e in launches if "fused_mlp_kernel" in e["kernel"]]
+        mlp = [e for e in launches if "fused_mlp" in e["kernel"]]      # fused_mlp_kernel and fused_mlp_split_kernel
         out = {}
         if mlp:
             out["fused_mlp_kernel"] = {
