@@ -130,7 +130,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t
     return r;
 }
 __device__ __forceinline__ void mbar_expect_tx_at(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+    // default semantics (release at CTA scope): the producer thread has written nothing the other CTA reads, the bytes arrive
+    // through the TMA; a cluster-scope release here made every expect_tx a cluster-wide fence in the producer's issue loop
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_at(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");

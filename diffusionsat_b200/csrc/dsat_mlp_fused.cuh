@@ -441,6 +441,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // arrival from the leader's multicast commit.
     const uint32_t rank = PAIR ? cluster_rank() : 0u;
     const bool leader = rank == 0;
+    const bool pair_wait_cta_scope = (p.dbg & 2) == 0;      // DSAT_FM_DEBUG=2: the old cluster-scope waits everywhere
     constexpr int NC = PAIR ? 2 : 1;
     if (threadIdx.x == 0) {
         mbar_init(a_full, NC);
@@ -481,6 +482,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int n_layers = p.n_layers;
     auto wait = [&](uint64_t* bar, uint32_t parity) {
         if constexpr (PAIR) mbar_wait_cluster_scope(bar, parity); else mbar_wait(bar, parity);
+    };
+    // Barriers completed by TMA transactions or tcgen05.commit order async-proxy work on both sides and need no cluster-scope
+    // acquire by the waiting thread; only the barriers the peer's epilogue THREADS arrive on (tmem_empty, h_full) do.  (With a
+    // cluster-scope try_wait on every ring slot the pair instantiation spent ~2 k cycles per k-block.)
+    auto wait_async = [&](uint64_t* bar, uint32_t parity) {
+        if constexpr (PAIR) { if (pair_wait_cta_scope) mbar_wait(bar, parity); else mbar_wait_cluster_scope(bar, parity); }
+        else mbar_wait(bar, parity);
     };
     // address of the barrier the leader's issue warp waits on (this CTA's own one when not paired)
     auto at_leader = [&](uint64_t* bar) -> uint32_t { return PAIR ? mapa_rank(smem_u32(bar), 0) : smem_u32(bar); };
@@ -532,7 +540,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         if (j0 + s >= nt) continue;
                         const int j = j0 + s, tile = tile_of(j);
                         if (l == 0 && p.a_slots == 0) {      // whole input tile into AH
-                            if (j > 0) DSAT_TIMED_WAIT(w0, wait(ah_free, (uint32_t)((j - 1) & 1)));   // tile j-1 no longer reads AH
+                            if (j > 0) DSAT_TIMED_WAIT(w0, wait_async(ah_free, (uint32_t)((j - 1) & 1)));   // tile j-1 no longer reads AH
                             expect(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
                             for (int kb = 0; kb < k0_blocks; ++kb) load_a_block(ah + (size_t)kb * AH_BLOCK_BYTES, a_full, kb, tile);
                         }
@@ -540,13 +548,13 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const int halves = (p.layer[l].N + 255) / 256;
                         for (int kb = 0; kb < kbs; ++kb) {
                             if (l == 0 && p.a_slots > 0) {     // input block kb of this tile into the input ring
-                                DSAT_TIMED_WAIT(w0, wait(&a_ring_empty[aslot], aphase ^ 1));
+                                DSAT_TIMED_WAIT(w0, wait_async(&a_ring_empty[aslot], aphase ^ 1));
                                 expect(&a_ring_full[aslot], (uint32_t)p.a_box_rows * (BLOCK_K * 2));
                                 load_a_block(a_ring + (size_t)aslot * AH_BLOCK_BYTES, &a_ring_full[aslot], kb, tile);
                                 if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
                             }
                             for (int h = 0; h < halves; ++h) {
-                                DSAT_TIMED_WAIT(w1, wait(&ring_empty[slot], phase ^ 1));
+                                DSAT_TIMED_WAIT(w1, wait_async(&ring_empty[slot], phase ^ 1));
                                 if constexpr (PAIR) {     // this CTA's half of the weight block: rows [h*256 + rank*bn/2, +bn/2) of W^T
                                     const int bn = min(256, p.layer[l].N - h * 256);
                                     expect(&ring_full[slot], (uint32_t)(bn / 2) * (BLOCK_K * 2));
@@ -576,7 +584,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         const int j = j0 + s;
                         DSAT_TIMED_WAIT(w0, wait(&tmem_empty[st.buf], (uint32_t)((st.use & 1) ^ 1)));   // accumulator drained
                         const bool streamed = l == 0 && p.a_slots > 0;
-                        if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, wait(a_full, (uint32_t)(j & 1))); }
+                        if (l == 0) { if (!streamed) DSAT_TIMED_WAIT(w1, wait_async(a_full, (uint32_t)(j & 1))); }
                         else DSAT_TIMED_WAIT(w2, wait(&h_full[st.hidx], (uint32_t)(st.hcnt & 1)));
                         tcgen05_fence_after();
                         const int K = p.layer[l].K, N = p.layer[l].N;
@@ -588,14 +596,14 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                         for (int kb = 0; kb < kbs; ++kb) {
                             // (no tcgen05 fence after the ring waits: TMA writes and MMA reads are both async-proxy accesses
                             //  ordered by the mbarrier; the fences that matter are the per-step ones above)
-                            if (streamed) { DSAT_TIMED_WAIT(w1, wait(&a_ring_full[aslot], aphase)); }
+                            if (streamed) { DSAT_TIMED_WAIT(w1, wait_async(&a_ring_full[aslot], aphase)); }
                             const uint64_t da = make_smem_desc_sw128(smem_u32(streamed ? a_ring + (size_t)aslot * AH_BLOCK_BYTES
                                                                                        : a_src + (size_t)kb * AH_BLOCK_BYTES));
                             const int ksteps = min(BLOCK_K / 16, (K - kb * BLOCK_K + 15) / 16);
                             for (int h = 0; h < halves; ++h) {
                                 const int bn = min(256, N - h * 256);
                                 const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, bn);
-                                DSAT_TIMED_WAIT(w3, wait(&ring_full[slot], phase));
+                                DSAT_TIMED_WAIT(w3, wait_async(&ring_full[slot], phase));
                                 const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
                                 const long long t_i0 = timing ? clock64() : 0;
                                 const uint32_t acc_h = acc + (uint32_t)(h * 256);
@@ -650,16 +658,18 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     e.N = p.layer[l].N; e.epi = p.layer[l].epi;
                     e.bl_addr = bias_addr0 + 4u * (uint32_t)p.layer[l].bias_off;
                     e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st.buf * 256);
-                    DSAT_TIMED_WAIT(w0, wait(&tmem_full[st.buf], (uint32_t)(st.use & 1)));
+                    DSAT_TIMED_WAIT(w0, wait_async(&tmem_full[st.buf], (uint32_t)(st.use & 1)));
                     tcgen05_fence_after();
                     const long long t_epi0 = timing ? clock64() : 0;
                     const uint32_t empty_addr = at_leader(&tmem_empty[st.buf]);
                     if (l + 1 < n_layers) {
                         epi_drain<true, PAIR>(e, empty_addr);
                         tcgen05_fence_before();
-                        // st.shared -> visible to the MMA (async proxy); the leader's MMA also reads the peer's shared memory
-                        if constexpr (PAIR) asm volatile("fence.proxy.async;" ::: "memory");
-                        else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        // st.shared -> visible to the MMA (async proxy)
+                        // (pair mode too: the hidden activations are the A operand, which each CTA's tensor core reads from its
+                        //  OWN shared memory; only B halves cross the pair.  The all-spaces form of the fence made the
+                        //  hidden epilogues of the pair instantiation 2.4x slower.)
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) { arrive_addr<PAIR>(empty_addr); arrive_addr<PAIR>(at_leader(&h_full[st.hidx])); }
                         if (timing) w1 += clock64() - t_epi0;
