@@ -217,13 +217,27 @@ __device__ __forceinline__ void acc8_zero(Acc8& a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) a.v[i] = 0.f;
 }
-// add 8 bf16 (one uint4) to 8 fp32 accumulators; bf16 -> fp32 is a shift / mask of the 32-bit pair
+// fp32 accumulator += one bf16 half of a packed pair, in ONE instruction: sm_100a's mixed-precision add
+// (PTX add.rn.f32.bf16, SASS FHADD.BF16 with an .H0/.H1 operand selector) widens the bf16 operand exactly and rounds the
+// fp32 sum once -- bit-identical to widening by shift/mask and an FADD, at half the instructions.  The gathers are
+// issue-bound (ncu: 73-88 % issue-slot use), and unpack + add was all of their inner loop.
+__device__ __forceinline__ float add_bf16_lo(float acc, uint32_t pair) {
+    float d;
+    asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"((unsigned short)(pair & 0xffffu)), "f"(acc));
+    return d;
+}
+__device__ __forceinline__ float add_bf16_hi(float acc, uint32_t pair) {
+    float d;
+    asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"((unsigned short)(pair >> 16)), "f"(acc));
+    return d;
+}
+// add 8 bf16 (one uint4) to 8 fp32 accumulators
 __device__ __forceinline__ void acc8_add(Acc8& a, const uint4& w) {
     const uint32_t u[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        a.v[2 * i] += __uint_as_float(u[i] << 16);
-        a.v[2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u);
+        a.v[2 * i] = add_bf16_lo(a.v[2 * i], u[i]);
+        a.v[2 * i + 1] = add_bf16_hi(a.v[2 * i + 1], u[i]);
     }
 }
 __device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8]) {

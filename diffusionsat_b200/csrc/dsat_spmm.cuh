@@ -22,12 +22,11 @@ namespace dsat {
 template <bool BF16>
 __device__ __forceinline__ void spmm_add_chunk(float* acc, const uint4& x) {
     if constexpr (BF16) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&x);
+        const uint32_t u[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h[i]);
-            acc[2 * i] += f.x;
-            acc[2 * i + 1] += f.y;
+            acc[2 * i] = add_bf16_lo(acc[2 * i], u[i]);
+            acc[2 * i + 1] = add_bf16_hi(acc[2 * i + 1], u[i]);
         }
     } else {
         acc[0] += __uint_as_float(x.x);
