@@ -38,7 +38,6 @@ constexpr int MAX_SLOTS = 8;
 constexpr int AH_BLOCK_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB: 128 rows x 64 bf16
 constexpr int TMEM_COLS = 512;
 constexpr int STAGE_ROW = 128 + 16;                        // bytes per staged row (one 32-column fp32 chunk + pad)
-constexpr int STAGE_BYTES = 4 * 32 * STAGE_ROW;            // four epilogue warps
 constexpr int BAR_BYTES = 512;
 constexpr int MAX_A_SLOTS = 8;
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -84,10 +83,6 @@ struct FmParams {
     TcOut out;
     long long* prof;       // optional [16] cycle counters of CTA 0 (wait/work breakdown), nullptr = off
 };
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
-}
 
 #define DSAT_TIMED_WAIT(acc, call)                 \
     do {                                           \
@@ -246,43 +241,6 @@ __device__ __forceinline__ void store_chunk_fast(uint32_t stage_addr, int stage_
     }
     __syncwarp();
 }
-
-// one 32-column chunk of one output row per lane -> global memory through a per-warp transpose buffer
-template <bool BF16>
-__device__ __forceinline__ void store_chunk_coalesced(uint8_t* stage, int lane, const float (&v)[32], int valid,
-                                                      uint8_t* gbase, size_t row_pitch_bytes, size_t row_first,
-                                                      int rows_left, int col) {
-    uint8_t* mine = stage + lane * STAGE_ROW;
-    if (BF16) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-            uint4 pack;
-            pack.x = *reinterpret_cast<uint32_t*>(&p0); pack.y = *reinterpret_cast<uint32_t*>(&p1);
-            pack.z = *reinterpret_cast<uint32_t*>(&p2); pack.w = *reinterpret_cast<uint32_t*>(&p3);
-            *reinterpret_cast<uint4*>(mine + 16 * q) = pack;
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(mine + 16 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    }
-    __syncwarp();
-    constexpr int ES = BF16 ? 2 : 4;
-    constexpr int PIECES = BF16 ? 4 : 8;                    // 16-byte pieces per staged row
-    const int valid_pieces = valid * ES / 16;
-#pragma unroll
-    for (int k = 0; k < PIECES; ++k) {
-        const int pidx = lane + 32 * k;
-        const int rr = pidx / PIECES, piece = pidx % PIECES;
-        if (rr < rows_left && piece < valid_pieces)
-            *reinterpret_cast<uint4*>(gbase + (row_first + rr) * row_pitch_bytes + (size_t)col * ES + 16 * piece) =
-                *reinterpret_cast<const uint4*>(stage + rr * STAGE_ROW + 16 * piece);
-    }
-    __syncwarp();
-}
-
 
 struct EpiCtx {           // loop-invariant scalars of one (tile, layer) epilogue, all in registers
     uint32_t lane_addr, ah_addr, bl_addr, stage_addr;
