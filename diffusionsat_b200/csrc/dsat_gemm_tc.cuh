@@ -135,7 +135,10 @@ __device__ __forceinline__ void mbar_expect_tx_at(uint32_t cluster_addr, uint32_
     asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_at(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): what the arriving epilogue warps
+    // wrote is read by their OWN CTA's tensor core (after fence.proxy.async.shared::cta) or was read from TMEM
+    // (tcgen05.fence::before_thread_sync); nothing of it is read by threads of the other CTA
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster_scope(uint64_t* bar, uint32_t parity) {
     asm volatile(

@@ -439,7 +439,8 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
     const int n_layers = p.n_layers;
     auto wait = [&](uint64_t* bar, uint32_t parity) {
-        if constexpr (PAIR) mbar_wait_cluster_scope(bar, parity); else mbar_wait(bar, parity);
+        if constexpr (PAIR) { if (pair_wait_cta_scope) mbar_wait(bar, parity); else mbar_wait_cluster_scope(bar, parity); }
+        else mbar_wait(bar, parity);
     };
     // Barriers completed by TMA transactions or tcgen05.commit order async-proxy work on both sides and need no cluster-scope
     // acquire by the waiting thread; only the barriers the peer's epilogue THREADS arrive on (tmem_empty, h_full) do.  (With a

@@ -14,7 +14,8 @@ MODES = {
     "split_off": {"DSAT_SPLIT_MODE": "0"},                      # literal MLP through fused_mlp_kernel (one tile, 512 TMEM columns)
     "split_full_bias": {"DSAT_SPLIT_MODE": "3"},                # split mode, two weight slots, biases resident
     "cta_pair": {"DSAT_PAIR_MODE": "31", "DSAT_SPLIT_MODE": "0"},   # cta_group::2 instantiation for all five MLPs
-    "one_tile_at_a_time": {"DSAT_PING_PONG": "0", "DSAT_A_RING": "0"},   # resident input, no ping-pong
+    "no_pair": {"DSAT_PAIR_MODE": "0"},                         # the clause MLP through the single-CTA kernel too
+    "one_tile_at_a_time": {"DSAT_PING_PONG": "0", "DSAT_A_RING": "0", "DSAT_PAIR_MODE": "0"},   # resident input, no ping-pong
 }
 
 
