@@ -674,6 +674,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 //     or the previous hidden layer), so it also waits for the NEXT step's tmem_full (FmStep::wait_next);
 //   * the last step's output drains while the next tile's first step already accumulates in the other half.
 // Input tile resident in AH (blocks 0 ..), one hidden region, weight ring as in fused_mlp_kernel.
+template <bool PAIR>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
 fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
                        const __grid_constant__ CUtensorMap map_w2, FmParams p) {
@@ -698,15 +699,22 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int epi_threads = 32 * p.epi_warps;
     const CUtensorMap* map_w[MAX_LAYERS] = {&map_w0, &map_w1, &map_w2};
+    // PAIR (clusters of 2, cta_group::2, as in fused_mlp_kernel): rank 0 leads and issues M = 256 MMAs; each CTA loads its own
+    // 128 input rows and HALF of every weight block; "full" barriers live in the leader and count both CTAs, "empty"
+    // barriers and tmem_full are local and get the leader's multicast commits.
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const bool leader = rank == 0;
+    constexpr int NC = PAIR ? 2 : 1;
+    auto at_leader = [&](uint64_t* bar) -> uint32_t { return PAIR ? mapa_rank(smem_u32(bar), 0) : smem_u32(bar); };
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
+        mbar_init(a_full, NC);
         mbar_init(ah_free, 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&h_full[b], p.epi_warps);
+            mbar_init(&h_full[b], NC * p.epi_warps);
             mbar_init(&tmem_full[b], 1);
-            mbar_init(&tmem_empty[b], p.epi_warps);
+            mbar_init(&tmem_empty[b], NC * p.epi_warps);
         }
-        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+        for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(&ring_full[s], NC); mbar_init(&ring_empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
@@ -714,8 +722,13 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     if (!p.step_bias && warp >= 2) {
         for (int l = 0; l < p.n_layers; ++l)
@@ -723,10 +736,16 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();              // both CTAs' barriers exist before any remote arrive
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nv = p.n_steps;
-    const int nt = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // work units: 128-row tiles of this CTA, or (PAIR) 256-row macro tiles of the pair, of which this CTA owns one half
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units = PAIR ? (p.n_tiles + 1) / 2 : p.n_tiles;
+    const int nt = unit0 < n_units ? (n_units - unit0 + unit_stride - 1) / unit_stride : 0;
+    auto tile_of = [&](int j) { const int u = unit0 + j * unit_stride; return PAIR ? 2 * u + (int)rank : u; };
     const int n_hidden = p.n_layers - 1;
 
     if (warp == 0) {
@@ -734,20 +753,29 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const int k0_blocks = (p.layer[0].K + BLOCK_K - 1) / BLOCK_K;
             int slot = 0; uint32_t phase = 0;
             for (int j = 0; j < nt; ++j) {
-                const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+                const int tile = tile_of(j);
                 for (int v = 0; v < nv; ++v) {
                     const FmStep st = p.step[v];
                     if (v == 0) {      // the input tile into AH, once the previous tile's last layer no longer reads it
                         if (j > 0) mbar_wait(ah_free, (uint32_t)((j - 1) & 1));
-                        mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
-                        for (int kb = 0; kb < k0_blocks; ++kb)
-                            tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
+                        if constexpr (PAIR) mbar_expect_tx_at(at_leader(a_full), (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
+                        else mbar_expect_tx(a_full, (uint32_t)(k0_blocks * p.a_box_rows) * (BLOCK_K * 2));
+                        for (int kb = 0; kb < k0_blocks; ++kb) {
+                            if constexpr (PAIR) tma_load_2d_cg2(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, at_leader(a_full), kb * BLOCK_K, tile * BLOCK_M);
+                            else tma_load_2d(ah + (size_t)kb * AH_BLOCK_BYTES, &map_a, a_full, kb * BLOCK_K, tile * BLOCK_M);
+                        }
                     }
                     const int kbs = (p.layer[st.layer].K + BLOCK_K - 1) / BLOCK_K;
                     for (int kb = 0; kb < kbs; ++kb) {
                         mbar_wait(&ring_empty[slot], phase ^ 1);
-                        mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[st.layer].box_rows * (BLOCK_K * 2));
-                        tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[st.layer], &ring_full[slot], kb * BLOCK_K, st.n0);
+                        if constexpr (PAIR) {      // this CTA's half of the step's weight rows (the maps have half-height boxes)
+                            mbar_expect_tx_at(at_leader(&ring_full[slot]), (uint32_t)(st.N / 2) * (BLOCK_K * 2));
+                            tma_load_2d_cg2(ring + (size_t)slot * p.slot_bytes, map_w[st.layer], at_leader(&ring_full[slot]), kb * BLOCK_K,
+                                            st.n0 + (int)rank * (st.N / 2));
+                        } else {
+                            mbar_expect_tx(&ring_full[slot], (uint32_t)p.layer[st.layer].box_rows * (BLOCK_K * 2));
+                            tma_load_2d(ring + (size_t)slot * p.slot_bytes, map_w[st.layer], &ring_full[slot], kb * BLOCK_K, st.n0);
+                        }
                         if (++slot == p.slots) { slot = 0; phase ^= 1; }
                     }
                 }
@@ -755,6 +783,8 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
     } else if (warp == 1) {    // ================================ MMA issuer (whole warp converged, one elected lane issues)
         int slot = 0; uint32_t phase = 0;
+        auto commit = [&](uint64_t* bar) { if constexpr (PAIR) tcgen05_commit_elect_cg2(bar); else tcgen05_commit_elect(bar); };
+        if (leader)
         for (int j = 0; j < nt; ++j)
             for (int v = 0; v < nv; ++v) {
                 const FmStep st = p.step[v];
@@ -764,7 +794,7 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 tcgen05_fence_after();
                 const int K = p.layer[st.layer].K;
                 const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
-                const uint32_t idesc = make_idesc_bf16(BLOCK_M, st.N);
+                const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, st.N);
                 const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
                 const uint32_t hphase = (uint32_t)((j * n_hidden + (st.layer - 1)) & 1);
                 for (int kb = 0; kb < kbs; ++kb) {
@@ -777,15 +807,19 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     mbar_wait(&ring_full[slot], phase);
                     const uint64_t db = make_smem_desc_sw128(smem_u32(ring + (size_t)slot * p.slot_bytes));
                     if (ksteps == BLOCK_K / 16) {
-                        umma_bf16_kblock_commit_elect(acc, da, db, idesc, kb != 0, &ring_empty[slot]);
+                        if constexpr (PAIR) umma_bf16_kblock_commit_elect_cg2(acc, da, db, idesc, kb != 0, &ring_empty[slot]);
+                        else umma_bf16_kblock_commit_elect(acc, da, db, idesc, kb != 0, &ring_empty[slot]);
                     } else {
-                        for (int k = 0; k < ksteps; ++k) umma_bf16_elect(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        tcgen05_commit_elect(&ring_empty[slot]);
+                        for (int k = 0; k < ksteps; ++k) {
+                            if constexpr (PAIR) umma_bf16_elect_cg2(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            else umma_bf16_elect(acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        }
+                        commit(&ring_empty[slot]);
                     }
                     if (++slot == p.slots) { slot = 0; phase ^= 1; }
                 }
-                tcgen05_commit_elect(&tmem_full[buf]);
-                if (v == nv - 1) tcgen05_commit_elect(ah_free);
+                commit(&tmem_full[buf]);
+                if (v == nv - 1) commit(ah_free);
             }
     } else {               // ================================ epilogue warps
         const int quad = warp & 3;
@@ -816,7 +850,7 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         };
         if (p.step_bias && nt > 0) fetch_bias(0);
         for (int j = 0; j < nt; ++j) {
-            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+            const int tile = tile_of(j);
             e.row_first = (size_t)tile * BLOCK_M + quad * 32;
             e.rows_left = p.rows - (int)e.row_first;
             for (int v = 0; v < nv; ++v) {
@@ -840,15 +874,15 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 mbar_wait(&tmem_full[buf], (uint32_t)(use & 1));
                 if (st.wait_next) mbar_wait(&tmem_full[buf ^ 1], (uint32_t)(((g + 1) >> 1) & 1));
                 tcgen05_fence_after();
-                const uint32_t empty_addr = smem_u32(&tmem_empty[buf]);
+                const uint32_t empty_addr = at_leader(&tmem_empty[buf]);
                 if (st.hidden) {
-                    epi_drain<true, false>(e, empty_addr);
+                    epi_drain<true, PAIR>(e, empty_addr);
                     tcgen05_fence_before();
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) { arrive_addr<false>(empty_addr); arrive_addr<false>(smem_u32(&h_full[st.n0 >> 8])); }
+                    if (lane == 0) { arrive_addr<PAIR>(empty_addr); arrive_addr<PAIR>(at_leader(&h_full[st.n0 >> 8])); }
                 } else {
-                    epi_drain<false, false>(e, empty_addr);
+                    epi_drain<false, PAIR>(e, empty_addr);
                     if (p.stage_in_h) asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
                 }
             }
@@ -856,9 +890,11 @@ fused_mlp_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
     tcgen05_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();              // the leader's MMAs may still read this CTA's shared memory
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
 }
 
@@ -1000,7 +1036,7 @@ inline bool plan_fused(FusedMlp& f) {
     // first k0 blocks, and the next hidden epilogue comes after this one in the same warps' program order.
     const int k0_blocks_res = (p.layer[0].K + 63) / 64;
     // split mode: every hidden layer exactly 512 wide (two accumulator halves, two h_full halves), output <= 256
-    bool split = f.split_mode && !pair && p.n_layers >= 2 && p.layer[p.n_layers - 1].N <= 256 && p.rows > 0;
+    bool split = f.split_mode && p.n_layers >= 2 && p.layer[p.n_layers - 1].N <= 256 && p.rows > 0;
     for (int l = 0; l + 1 < p.n_layers; ++l) split = split && p.layer[l].N == 512;
     const bool step_bias = split && f.split_step_bias;
     const int bias_bytes = step_bias ? 2 * 256 * 4 : bias_total * 4;
@@ -1048,7 +1084,8 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -1063,12 +1100,13 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+        if (f.p.split) return cudaLaunchKernelEx(&cfg, fused_mlp_split_kernel<true>, f.map_a, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
         if (f.p.prof) return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<true, true>, f.map_a, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
         return cudaLaunchKernelEx(&cfg, fused_mlp_kernel<false, true>, f.map_a, f.map_wp[0], f.map_wp[1], f.map_wp[last], f.p);
     }
     const unsigned grid = (unsigned)(f.p.n_tiles < sm_count ? f.p.n_tiles : sm_count);
     if (f.p.split) {    // (no instrumented build of the split kernel: dsat_profile_fused reads zeros for it)
-        fused_mlp_split_kernel<<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
+        fused_mlp_split_kernel<false><<<grid, threads, f.smem_bytes, stream>>>(f.map_a, f.map_w[0], f.map_w[1], f.map_w[last], f.p);
         return cudaGetLastError();
     }
     if (f.p.prof)   // instrumented build of the same kernel (dsat_profile_fused)
