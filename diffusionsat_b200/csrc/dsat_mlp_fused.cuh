@@ -937,6 +937,13 @@ inline int pair_a_slots() {
     return v < 2 ? 2 : v;
 }
 
+inline int pair_pp_wmin() {
+    // half-height weight slots reserved before the input ring gets the rest (CTA pair + ping-pong): the update MLP measured
+    // 0.263 / 0.230 / 0.245 ms with 4 / 3 / 2 (input ring 2 / 3 / 4)
+    static const int v = getenv("DSAT_PAIR_PP_WMIN") ? atoi(getenv("DSAT_PAIR_PP_WMIN")) : 3;
+    return v < 2 ? 2 : v;
+}
+
 // shared-memory plan; returns false when the MLP does not fit
 inline bool plan_fused(FusedMlp& f) {
     FmParams& p = f.p;
@@ -990,7 +997,7 @@ inline bool plan_fused(FusedMlp& f) {
                 const int in_h = stage_bytes <= h_bytes;
                 const int fixed = pad + 2 * h_bytes + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4;
                 // weight slots to reserve before the input ring gets the rest: four half-height ones in pair mode
-                int w_min = p.pair ? 4 : 2;
+                int w_min = p.pair ? pair_pp_wmin() : 2;
                 if (SMEM_LIMIT - fixed - w_min * p.slot_bytes < 2 * AH_BLOCK_BYTES) w_min = 2;
                 int a_slots = (SMEM_LIMIT - fixed - w_min * p.slot_bytes) / AH_BLOCK_BYTES;
                 if (a_slots > 2 * k0_blocks) a_slots = 2 * k0_blocks;

@@ -14,7 +14,7 @@ MODES = {
     "split_off": {"DSAT_SPLIT_MODE": "0"},                      # literal MLP through fused_mlp_kernel (one tile, 512 TMEM columns)
     "split_full_bias": {"DSAT_SPLIT_MODE": "3", "DSAT_PAIR_MODE": "4"},   # split mode, single CTA, two weight slots, biases resident
     "cta_pair": {"DSAT_PAIR_MODE": "31", "DSAT_SPLIT_MODE": "0"},   # cta_group::2 instantiation for all five MLPs
-    "no_pair": {"DSAT_PAIR_MODE": "0"},                         # clause and literal MLPs through the single-CTA kernels too
+    "no_pair": {"DSAT_PAIR_MODE": "0"},                         # literal, clause and update MLPs through the single-CTA kernels too
     "one_tile_at_a_time": {"DSAT_PING_PONG": "0", "DSAT_A_RING": "0", "DSAT_PAIR_MODE": "0"},   # resident input, no ping-pong
 }
 
