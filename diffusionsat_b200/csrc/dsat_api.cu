@@ -292,14 +292,17 @@ int ensure_tc_buffers(dsat_ctx* c) {
             {   // input ring per MLP: DSAT_A_RING is a bit mask over (query, literal, clause, update, output)
                 static const int mask = getenv("DSAT_A_RING") ? atoi(getenv("DSAT_A_RING")) : 0x1d;
                 f.stream_input = ((mask >> which) & 1) != 0;
-                // ping-pong everywhere it fits except the clause MLP: there the same shared memory buys a three-slot weight ring and
-                // a four-slot input ring for one tile at a time, which measured 2 % faster than two tiles on two-slot rings
-                static const int pp_mask = getenv("DSAT_PING_PONG") ? atoi(getenv("DSAT_PING_PONG")) : 0x1b;
-                f.ping_pong = ((pp_mask >> which) & 1) != 0;
-                // CTA pair (cta_group::2) for the literal (split mode), clause and update MLPs: measured 3-4 %, 3-4 % and 9 % faster there,
+                // CTA pair (cta_group::2) for the literal (split mode), clause and update MLPs: measured 4 %, 7 % and 9 % faster there,
                 // 2-5 % slower for the small query and output MLPs
                 static const int pair_mask = getenv("DSAT_PAIR_MODE") ? atoi(getenv("DSAT_PAIR_MODE")) : 0xe;
                 f.pair_mode = ((pair_mask >> which) & 1) != 0;
+                // ping-pong everywhere it fits.  The clause MLP as a single CTA is the exception: there the same shared memory buys
+                // a three-slot weight ring and a four-slot input ring for one tile at a time, 2 % faster than two tiles on
+                // two-slot rings; as a CTA pair (half-height weight slots: three of them next to three input slots) two tiles
+                // in flight are 4 % faster than one
+                static const bool pp_env = getenv("DSAT_PING_PONG") != nullptr;
+                static const int pp_mask = pp_env ? atoi(getenv("DSAT_PING_PONG")) : 0x1b;
+                f.ping_pong = ((pp_mask >> which) & 1) != 0 || (!pp_env && which == FC && f.pair_mode);
                 static const int split_on = getenv("DSAT_SPLIT_MODE") ? atoi(getenv("DSAT_SPLIT_MODE")) : 1;
                 f.split_step_bias = (split_on & 2) == 0;  // DSAT_SPLIT_MODE=3: split mode with the whole bias array in shared memory (two weight slots)
                 f.split_mode = split_on != 0;       // takes effect only where every hidden layer is 512 wide (the literal MLP)
