@@ -16,7 +16,10 @@ from .weights import QuerySATWeights, flat_layer_names
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdsat.so")
 
-F32, BF16 = 0, 1
+# dsat_dtype: F32 = fp32 FMA on the CUDA cores, F32_TC = fp32-accurate split-bf16 products on the tensor cores (default),
+# BF16 = plain bf16 tensor-core path, BF16_UNFUSED = the same with one kernel per Dense layer
+F32, BF16, BF16_UNFUSED, F32_TC = 0, 1, 2, 3
+PRECISIONS = {"fp32": F32_TC, "fp32_tc": F32_TC, "fp32_simt": F32, "bf16": BF16, "bf16_unfused": BF16_UNFUSED}
 
 BUFFERS = {name: i for i, name in enumerate(
     ["VROW", "CROW", "H1", "H2", "QS", "LIT", "CH", "COUT", "U1", "U2", "UOUT", "SPRE", "O1", "LOGITS", "OUT", "X"])}
@@ -39,6 +42,7 @@ _SIGNATURES = {
     "dsat_launch_count": (C.c_longlong, [_vp]),
     "dsat_set_model": (C.c_int, [_vp, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), _i32p, _i32p]),
     "dsat_set_precision": (C.c_int, [_vp, C.c_int]),
+    "dsat_get_precision": (C.c_int, [_vp]),
     "dsat_set_graph": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, C.c_int, _i32p, _i32p,
                                  C.c_int, C.c_int]),
     "dsat_model_call": (C.c_int, [_vp, C.c_float, _f32p, _i32p, _f32p, C.c_int, C.c_uint64, C.c_uint64, _f32p, _i32p,
@@ -59,6 +63,7 @@ _SIGNATURES = {
     "dsat_debug_read": (C.c_int, [_vp, C.c_int, _f32p, C.c_longlong]),
     "dsat_debug_write": (C.c_int, [_vp, C.c_int, _f32p, C.c_longlong]),
     "dsat_debug_groups": (C.c_int, [_vp, _i32p, _i32p, _f32p, _i32p, _i32p]),
+    "dsat_debug_mlp": (C.c_int, [_vp, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -167,8 +172,14 @@ class Context:
         self._check(self._lib.dsat_set_model(self._h, len(names), kp, bp, _ptr(ins, C.c_int32), _ptr(outs, C.c_int32)))
         self.feature_maps, self.query_maps = weights.feature_maps, weights.query_maps
 
-    def set_precision(self, dtype: int):
+    def set_precision(self, dtype):
+        """`dtype`: a dsat_dtype code or one of PRECISIONS' names ("fp32" = fp32-accurate tensor-core path)."""
+        if isinstance(dtype, str):
+            dtype = PRECISIONS[dtype]
         self._check(self._lib.dsat_set_precision(self._h, int(dtype)))
+
+    def get_precision(self) -> int:
+        return int(self._lib.dsat_get_precision(self._h))
 
     def set_graph(self, graph: UnitGraph, chains: int, group_graphs: int = 0):
         g = graph
@@ -303,6 +314,14 @@ class Context:
         rows, ld = self.debug_dims(name)
         arr = _as(values, np.float32, (rows, ld))
         self._check(self._lib.dsat_debug_write(self._h, BUFFERS[name], _ptr(arr, C.c_float), rows * ld))
+
+    MLPS = ("variables_query", "lit_query", "clause_update", "update_gate", "variables_output")
+
+    def debug_mlp(self, which):
+        """Run one MLP alone (index or name from MLPS) on the current contents of its input buffer."""
+        if isinstance(which, str):
+            which = self.MLPS.index(which)
+        self._check(self._lib.dsat_debug_mlp(self._h, int(which)))
 
     def debug_groups(self):
         done = np.empty(self.n_groups, dtype=np.int32)

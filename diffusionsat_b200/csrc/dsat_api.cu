@@ -19,6 +19,7 @@
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
 #include "dsat_mlp_fused.cuh"
+#include "dsat_mlp_x3.cuh"
 #endif
 
 using namespace dsat;
@@ -72,7 +73,11 @@ struct dsat_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     long long launches = 0;
+#ifdef DSAT_WITH_TCGEN05
+    int precision = DSAT_F32_TC;        // default: fp32-accurate Dense layers on the tensor cores
+#else
     int precision = DSAT_F32;
+#endif
     // per-class CUDA-event marks (dsat_profile_rounds)
     struct ProfMark { cudaEvent_t ev; int cls; };
     std::vector<ProfMark> prof;
@@ -121,7 +126,16 @@ struct dsat_ctx {
     bool fused_ready = false;
     bool use_fused = true;
     bool use_smem_gather = true;
+    // fp32-accurate tensor-core path (dsat_mlp_x3.cuh): MLP inputs live as hi/lo bf16 planes [2][rows][ld]
+    DevBuf<__nv_bfloat16> VROWp, CROWp, SPREp, H1p, H2p;
+    DevBuf<__nv_bfloat16> wx[12];       // stacked hi/lo K-major weights [2N, K64] per reference layer
+    int wx_k64[12] = {0}, wx_n[12] = {0};
+    x3::X3Mlp x3[7];                    // query, lit layer 1, lit layer 2, lit layer 3, clause, update, output
+    bool has_x3_buffers = false;
+    bool x3_ready = false;
 #endif
+    bool has_simt_buffers = false;
+    float last_noise_scale = 0.f;
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
     int ldc() const { return F + 2 * Q; }
@@ -165,23 +179,15 @@ UnitGraphDev graph_view(const dsat_ctx* c) {
     return g;
 }
 
-int ensure_buffers(dsat_ctx* c) {
+// buffers every precision uses: the fp32 outputs of the MLPs, the diffusion state and the per-graph bookkeeping
+int ensure_common_buffers(dsat_ctx* c) {
     if (c->has_buffers) return DSAT_OK;
     if (!c->has_model || !c->has_graph) { c->err = "set the model and the graph first"; return DSAT_ERR_STATE; }
     const size_t Nt = (size_t)c->Nt, Mt = (size_t)c->Mt;
-    CK_CUDA(c, c->VROW.alloc(Nt * c->ldv()));
-    CK_CUDA(c, c->CROW.alloc(Mt * c->ldc()));
-    CK_CUDA(c, c->H1.alloc(Nt * c->ldh1()));
-    CK_CUDA(c, c->H2.alloc(Nt * c->HL));
     CK_CUDA(c, c->QS.alloc(Nt * 3 * c->Q));
     CK_CUDA(c, c->LIT.alloc(Nt * 2 * c->Q));
-    CK_CUDA(c, c->CH.alloc(Mt * c->HC));
     CK_CUDA(c, c->COUT.alloc(Mt * (c->Q + c->F)));
-    CK_CUDA(c, c->U1.alloc(Nt * c->HU));
-    CK_CUDA(c, c->U2.alloc(Nt * c->HU));
     CK_CUDA(c, c->UOUT.alloc(Nt * c->F));
-    CK_CUDA(c, c->SPRE.alloc(Nt * c->F));
-    CK_CUDA(c, c->O1.alloc(Nt * c->HO));
     CK_CUDA(c, c->LOGITS.alloc(Nt * DSAT_LOGIT_PAD));
     CK_CUDA(c, c->OUT.alloc(Nt));
     CK_CUDA(c, c->X.alloc(Nt + 1));
@@ -203,11 +209,30 @@ int ensure_buffers(dsat_ctx* c) {
     CK_CUDA(c, c->is_sat.alloc(G));
     CK_CUDA(c, c->sat_any.alloc(G));
     CK_CUDA(c, c->packed.alloc(G * c->words));
+    CK_CUDA(c, cudaMemsetAsync(c->OUT.p, 0, c->OUT.count * sizeof(float), c->stream));
+    c->has_buffers = true;
+    return DSAT_OK;
+}
+
+// + the fp32 row buffers and hidden activations of the CUDA-core path (the bf16 path mirrors the state there too)
+int ensure_buffers(dsat_ctx* c) {
+    int rc = ensure_common_buffers(c);
+    if (rc) return rc;
+    if (c->has_simt_buffers) return DSAT_OK;
+    const size_t Nt = (size_t)c->Nt, Mt = (size_t)c->Mt;
+    CK_CUDA(c, c->VROW.alloc(Nt * c->ldv()));
+    CK_CUDA(c, c->CROW.alloc(Mt * c->ldc()));
+    CK_CUDA(c, c->H1.alloc(Nt * c->ldh1()));
+    CK_CUDA(c, c->H2.alloc(Nt * c->HL));
+    CK_CUDA(c, c->CH.alloc(Mt * c->HC));
+    CK_CUDA(c, c->U1.alloc(Nt * c->HU));
+    CK_CUDA(c, c->U2.alloc(Nt * c->HU));
+    CK_CUDA(c, c->SPRE.alloc(Nt * c->F));
+    CK_CUDA(c, c->O1.alloc(Nt * c->HO));
     // padded columns must be zero forever: clear everything once
     CK_CUDA(c, cudaMemsetAsync(c->VROW.p, 0, c->VROW.count * sizeof(float), c->stream));
     CK_CUDA(c, cudaMemsetAsync(c->CROW.p, 0, c->CROW.count * sizeof(float), c->stream));
-    CK_CUDA(c, cudaMemsetAsync(c->OUT.p, 0, c->OUT.count * sizeof(float), c->stream));
-    c->has_buffers = true;
+    c->has_simt_buffers = true;
     return DSAT_OK;
 }
 
@@ -377,8 +402,11 @@ void release_buffers(dsat_ctx* c) {
     c->CHb.release(); c->COUTb.release(); c->UOUTb.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
     c->O1b.release();
     c->has_tc_buffers = false;
+    c->VROWp.release(); c->CROWp.release(); c->SPREp.release(); c->H1p.release(); c->H2p.release();
+    c->has_x3_buffers = false;
 #endif
     c->has_buffers = false;
+    c->has_simt_buffers = false;
 }
 
 // ---------------------------------------------------------------------------- launch helpers
@@ -397,6 +425,127 @@ void prof_mark(dsat_ctx* c, int cls) {
     cudaEventRecord(c->prof[c->prof_used].ev, c->stream);
     c->prof_used++;
 }
+
+#ifdef DSAT_WITH_TCGEN05
+// ------------------------------------------------------------------ fp32-accurate tensor-core path (x3)
+// Stacked hi/lo K-major copies [2N, K64] of the twelve reference layers, cut out of the packed fp32 operators.
+int x3_pack_weights(dsat_ctx* c) {
+    struct Cut { int op, col0, n; };
+    const Cut cuts[12] = {
+        {OP_V1, 0, c->HQ}, {OP_Q2, 0, c->Q}, {OP_V1, c->HQ, c->HL}, {OP_L2, 0, c->HL}, {OP_L3, 0, 2 * c->Q},
+        {OP_C1, 0, c->HC}, {OP_C2, 0, c->Q + c->F}, {OP_U1, 0, c->HU}, {OP_U2, 0, c->HU}, {OP_U3, 0, c->F},
+        {OP_O1, 0, c->HO}, {OP_O2, 0, DSAT_LOGIT_PAD}};
+    for (int i = 0; i < 12; ++i) {
+        const int op = cuts[i].op, K = c->ops[op].K, Nop = c->ops[op].N, n = cuts[i].n;
+        const int K64 = (K + 63) / 64 * 64;
+        std::vector<float> w((size_t)K * Nop);
+        CK_CUDA(c, dsat_memcpy_sync(w.data(), c->ops[op].w.p, w.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<__nv_bfloat16> wt((size_t)2 * n * K64, __float2bfloat16(0.f));
+        for (int k = 0; k < K; ++k)
+            for (int j = 0; j < n; ++j) {
+                const float v = w[(size_t)k * Nop + cuts[i].col0 + j];
+                const __nv_bfloat16 hi = __float2bfloat16(v);
+                wt[(size_t)j * K64 + k] = hi;
+                wt[(size_t)(n + j) * K64 + k] = __float2bfloat16(v - __bfloat162float(hi));
+            }
+        CK_CUDA(c, c->wx[i].alloc(wt.size()));
+        CK_CUDA(c, dsat_memcpy_sync(c->wx[i].p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice));
+        c->wx_k64[i] = K64; c->wx_n[i] = n;
+    }
+    return DSAT_OK;
+}
+
+int ensure_x3_buffers(dsat_ctx* c) {
+    if (c->has_x3_buffers) return DSAT_OK;
+    int rc = ensure_common_buffers(c);
+    if (rc) return rc;
+    const size_t Nt = (size_t)c->Nt, Mt = (size_t)c->Mt;
+    const int F = c->F, Q = c->Q;
+    CK_CUDA(c, c->VROWp.alloc(2 * Nt * c->ldv()));
+    CK_CUDA(c, c->CROWp.alloc(2 * Mt * c->ldc()));
+    CK_CUDA(c, c->SPREp.alloc(2 * Nt * F));
+    CK_CUDA(c, c->H1p.alloc(2 * Nt * c->HL));
+    CK_CUDA(c, c->H2p.alloc(2 * Nt * c->HL));
+    CK_CUDA(c, cudaMemsetAsync(c->VROWp.p, 0, c->VROWp.count * 2, c->stream));
+    CK_CUDA(c, cudaMemsetAsync(c->CROWp.p, 0, c->CROWp.count * 2, c->stream));
+    enum { XQ = 0, XL1, XL2, XL3, XC, XU, XO };
+    struct L { int wi; int op; int bias_off; int epi; };        // wi = index into wx[] (reference layer order)
+    static const int pair_mask = getenv("DSAT_X3_PAIR") ? atoi(getenv("DSAT_X3_PAIR")) : 0x3e;   // all but query and output
+    auto build = [&](int which, const __nv_bfloat16* a_hi, size_t a_plane, long long rows, int k, int lda,
+                     std::initializer_list<L> layers, int n_groups, int out_mode, void* out0, void* out1, int ld_out) -> bool {
+        x3::X3Mlp& f = c->x3[which];
+        f.ready = false;
+        x3::X3Params& p = f.p;
+        p.n_layers = (int)layers.size();
+        p.rows = (int)rows;
+        p.n_groups = n_groups;
+        p.a_box_rows = (int)(rows < x3::BLOCK_M ? rows : x3::BLOCK_M);
+        p.qmaps = Q;
+        p.prof = nullptr;
+        p.out_mode = out_mode; p.out0 = out0; p.out1 = out1; p.ld_out = ld_out;
+        f.pair_mode = ((pair_mask >> which) & 1) != 0;
+        if (!tc::make_bf16_map(&f.map_a_hi, a_hi, rows, k, lda, p.a_box_rows)) return false;
+        if (!tc::make_bf16_map(&f.map_a_lo, a_hi + a_plane, rows, k, lda, p.a_box_rows)) return false;
+        int i = 0;
+        for (const L& l : layers) {
+            x3::X3Layer& ly = p.layer[i];
+            const int n_total = c->wx_n[l.wi];
+            ly.K = c->ops[l.op].K; ly.N = n_groups > 1 ? 256 : n_total; ly.n_total = n_total;
+            ly.epi = l.epi; ly.w_lo_row = n_total; ly.bias = c->ops[l.op].b.p + l.bias_off;
+            if (n_groups > 1 && n_total != 256 * n_groups) return false;
+            ++i;
+        }
+        if (!x3::plan_x3(f)) return false;
+        i = 0;
+        for (const L& l : layers) {     // weight boxes: the layer's N rows, or half of them per CTA of a pair
+            const int box = f.p.pair ? p.layer[i].N / 2 : p.layer[i].N;
+            if (!tc::make_bf16_map(&f.map_w[i], c->wx[l.wi].p, 2 * c->wx_n[l.wi], c->wx_k64[l.wi], c->wx_k64[l.wi], box)) return false;
+            ++i;
+        }
+        for (; i < x3::MAX_LAYERS; ++i) f.map_w[i] = f.map_w[0];
+        if (getenv("DSAT_PLAN_LOG"))
+            fprintf(stderr, "[dsat] x3 mlp %d: smem %d B, hidden blocks 2 x %d, input ring %d, weight ring %d x %d B, epilogue warps %d, "
+                    "staging in hidden %d, cta pair %d, groups %d\n", which, f.smem_bytes, p.h_blocks, p.a_slots, p.w_slots, p.w_slot_bytes,
+                    p.epi_warps, p.stage_in_h, p.pair, p.n_groups);
+        return true;
+    };
+    const size_t vplane = Nt * c->ldv(), cplane = Mt * c->ldc(), splane = Nt * F, hplane = Nt * c->HL;
+    bool ok = true;
+    ok = ok && build(XQ, c->VROWp.p, vplane, c->Nt, F + DSAT_AUX_PAD, c->ldv(),
+                     {{0, OP_V1, 0, tc::TC_LRELU}, {1, OP_Q2, 0, tc::TC_QUERY}}, 1, x3::OUT_F32, c->QS.p, nullptr, 3 * Q);
+    const int lgroups = c->HL > 256 ? c->HL / 256 : 1;
+    ok = ok && (c->HL <= 256 || c->HL % 256 == 0);
+    ok = ok && build(XL1, c->VROWp.p, vplane, c->Nt, F + DSAT_AUX_PAD, c->ldv(),
+                     {{2, OP_V1, c->HQ, tc::TC_LRELU}}, lgroups, x3::OUT_SPLIT, c->H1p.p, c->H1p.p + hplane, c->HL);
+    ok = ok && build(XL2, c->H1p.p, hplane, c->Nt, c->HL, c->HL,
+                     {{3, OP_L2, 0, tc::TC_LRELU}}, lgroups, x3::OUT_SPLIT, c->H2p.p, c->H2p.p + hplane, c->HL);
+    const int l3groups = 2 * Q > 256 ? 2 * Q / 256 : 1;
+    ok = ok && build(XL3, c->H2p.p, hplane, c->Nt, c->HL, c->HL,
+                     {{4, OP_L3, 0, tc::TC_LINEAR}}, l3groups, x3::OUT_F32, c->LIT.p, nullptr, 2 * Q);
+    if (Q + F <= 256 && c->HC <= 256)
+        ok = ok && build(XC, c->CROWp.p, cplane, c->Mt, F + 2 * Q, c->ldc(),
+                         {{5, OP_C1, 0, tc::TC_LRELU}, {6, OP_C2, 0, tc::TC_LINEAR}}, 1, x3::OUT_F32, c->COUT.p, nullptr, Q + F);
+    else ok = false;
+    if (c->HU <= 256)
+        ok = ok && build(XU, c->VROWp.p, vplane, c->Nt, F + DSAT_AUX_PAD + 3 * Q, c->ldv(),
+                         {{7, OP_U1, 0, tc::TC_LRELU}, {8, OP_U2, 0, tc::TC_LRELU}, {9, OP_U3, 0, tc::TC_LINEAR}}, 1, x3::OUT_F32,
+                         c->UOUT.p, nullptr, F);
+    else ok = false;
+    ok = ok && build(XO, c->SPREp.p, splane, c->Nt, F, F,
+                     {{10, OP_O1, 0, tc::TC_LRELU}, {11, OP_O2, 0, tc::TC_LINEAR}}, 1, x3::OUT_F32, c->LOGITS.p, nullptr, DSAT_LOGIT_PAD);
+    c->x3_ready = ok;
+    if (!ok) { c->err = "the fp32-accurate tensor-core path supports feature_maps = query_maps <= 128 (hidden widths <= 256 or 512)"; return DSAT_ERR_UNSUPPORTED; }
+    c->has_x3_buffers = true;
+    return DSAT_OK;
+}
+
+int run_x3(dsat_ctx* c, int which, int prof_class) {
+    prof_mark(c, prof_class);
+    CK_CUDA(c, x3::launch_x3(c->x3[which], c->device, c->sm_count, c->stream));
+    c->launches++;
+    return DSAT_OK;
+}
+#endif
 
 int run_linear(dsat_ctx* c, int op, const float* A, int lda, float* Y, int ldy, long long rows, int epi) {
     prof_mark(c, op);
@@ -440,10 +589,12 @@ LossScalars loss_scalars(float noise_scale) {
 
 #ifdef DSAT_WITH_TCGEN05
 static inline bool use_tc(const dsat_ctx* c) { return c->precision == DSAT_BF16 || c->precision == DSAT_BF16_UNFUSED; }
-static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p : nullptr; }
-static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : nullptr; }
+static inline bool use_x3(const dsat_ctx* c) { return c->precision == DSAT_F32_TC; }
+static inline __nv_bfloat16* vrow_b(dsat_ctx* c) { return use_tc(c) ? c->VROWb.p : use_x3(c) ? c->VROWp.p : nullptr; }
+static inline __nv_bfloat16* crow_b(dsat_ctx* c) { return use_tc(c) ? c->CROWb.p : use_x3(c) ? c->CROWp.p : nullptr; }
 #else
 static inline bool use_tc(const dsat_ctx*) { return false; }
+static inline bool use_x3(const dsat_ctx*) { return false; }
 static inline __nv_bfloat16* vrow_b(dsat_ctx*) { return nullptr; }
 static inline __nv_bfloat16* crow_b(dsat_ctx*) { return nullptr; }
 #endif
@@ -452,6 +603,7 @@ static inline __nv_bfloat16* crow_b(dsat_ctx*) { return nullptr; }
 int ensure_active_buffers(dsat_ctx* c) {
 #ifdef DSAT_WITH_TCGEN05
     if (use_tc(c)) return ensure_tc_buffers(c);
+    if (use_x3(c)) return ensure_x3_buffers(c);
 #endif
     return ensure_buffers(c);
 }
@@ -460,28 +612,44 @@ int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const flo
                const int* labels_dev, bool use_x, NoiseSource ns) {
     const long long Nt = c->Nt;
     const int threads = 256;
+    const bool x3p = use_x3(c);
+    const size_t vplane = x3p ? (size_t)Nt * c->ldv() : 0, cplane = x3p ? (size_t)c->Mt * c->ldc() : 0;
+    c->last_noise_scale = noise_scale;
     step_begin_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
         Nt, noise_scale, use_x ? c->X.p : nullptr, noisy_dev, uniforms_dev, labels_dev, c->labels.p,
-        c->VROW.p, c->ldv(), c->F, vrow_b(c), ns);
+        x3p ? nullptr : c->VROW.p, c->ldv(), c->F, vrow_b(c), ns, vplane);
     LAUNCHED(c);
     {   // variables_state = ones, clauses_state = ones (reference model/query_sat.py:141,148)
-        long long tot = Nt * (c->F / 4);
-        fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
-            c->VROW.p, c->ldv(), Nt, c->F / 4, 1.0f);
-        LAUNCHED(c);
-        tot = c->Mt * (c->F / 4);
-        fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
-            c->CROW.p, c->ldc(), c->Mt, c->F / 4, 1.0f);
-        LAUNCHED(c);
-        if (use_tc(c)) {
+        long long tot;
+        if (!x3p) {
+            tot = Nt * (c->F / 4);
+            fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+                c->VROW.p, c->ldv(), Nt, c->F / 4, 1.0f);
+            LAUNCHED(c);
+            tot = c->Mt * (c->F / 4);
+            fill_cols_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+                c->CROW.p, c->ldc(), c->Mt, c->F / 4, 1.0f);
+            LAUNCHED(c);
+        }
+        if (use_tc(c) || x3p) {
             tot = Nt * (c->F / 8);
             fill_cols_bf16_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
                 vrow_b(c), c->ldv(), Nt, c->F / 8, 1.0f);
             LAUNCHED(c);
+            if (x3p) {      // lo plane of a state of ones
+                fill_cols_bf16_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+                    vrow_b(c) + vplane, c->ldv(), Nt, c->F / 8, 0.0f);
+                LAUNCHED(c);
+            }
             tot = c->Mt * (c->F / 8);
             fill_cols_bf16_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
                 crow_b(c), c->ldc(), c->Mt, c->F / 8, 1.0f);
             LAUNCHED(c);
+            if (x3p) {
+                fill_cols_bf16_kernel<<<(unsigned)((tot + threads - 1) / threads), threads, 0, c->stream>>>(
+                    crow_b(c) + cplane, c->ldc(), c->Mt, c->F / 8, 0.0f);
+                LAUNCHED(c);
+            }
         }
     }
     CK_CUDA(c, cudaMemsetAsync(c->done.p, 0, c->done.count * sizeof(int), c->stream));
@@ -590,20 +758,30 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     const int F = c->F, Q = c->Q, ldv = c->ldv(), ldc = c->ldc(), ldh1 = c->ldh1();
     const UnitGraphDev g = graph_view(c);
     const bool tcp = use_tc(c);
+    const bool x3p = use_x3(c);
+    const size_t vplane = x3p ? (size_t)Nt * ldv : 0, cplane = x3p ? (size_t)Mt * ldc : 0;
 #ifdef DSAT_WITH_TCGEN05
     const bool fusedp = tcp && c->precision == DSAT_BF16 && c->fused_ready && c->use_fused;
+    enum { XQ = 0, XL1, XL2, XL3, XC, XU, XO };
 #endif
     int rc;
     {
         const int threads = 256;
         prof_mark(c, PROF_NOISE);
         round_noise_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
-            Nt, normals_dev, c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round);
+            Nt, normals_dev, x3p ? nullptr : c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round, vplane);
         LAUNCHED(c);
     }
     // v1 -> [hidden of variables_query | first hidden of lit_query]   (:240, :252)
     // query (+ softplus pair) (:240);  lit_query layers 2, 3 (:252)
-    if (!tcp) {
+    if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+        if ((rc = run_x3(c, XQ, OP_Q2))) return rc;
+        if ((rc = run_x3(c, XL1, OP_V1))) return rc;
+        if ((rc = run_x3(c, XL2, OP_L2))) return rc;
+        if ((rc = run_x3(c, XL3, OP_L3))) return rc;
+#endif
+    } else if (!tcp) {
         if ((rc = run_linear(c, OP_V1, c->VROW.p, ldv, c->H1.p, ldh1, Nt, EPI_LRELU))) return rc;
         if ((rc = run_linear(c, OP_Q2, c->H1.p, ldh1, c->QS.p, 3 * Q, Nt, EPI_QUERY))) return rc;
         if ((rc = run_linear(c, OP_L2, c->H1.p + c->HQ, ldh1, c->H2.p, c->HL, Nt, EPI_LRELU))) return rc;
@@ -628,7 +806,10 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         const int grid = tcp ? gather_grid(clause_gather_kernel<V, __nv_bfloat16>, Mt, GATHER_WARPS, c->sm_count)
                              : gather_grid(clause_gather_kernel<V, float>, Mt, GATHER_WARPS, c->sm_count);
-        if (!tcp)
+        if (x3p)
+            clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
+                g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, nullptr, ldc, F, crow_b(c), cplane);
+        else if (!tcp)
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
 #ifdef DSAT_WITH_TCGEN05
@@ -640,7 +821,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if (rc) return rc;
     LAUNCHED(c);
     // clause_update MLP                                                          (:258-261)
-    if (!tcp) {
+    if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+        if ((rc = run_x3(c, XC, OP_C2))) return rc;
+#endif
+    } else if (!tcp) {
         if ((rc = run_linear(c, OP_C1, c->CROW.p, ldc, c->CH.p, c->HC, Mt, EPI_LRELU))) return rc;
         if ((rc = run_linear(c, OP_C2, c->CH.p, c->HC, c->COUT.p, Q + F, Mt, EPI_LINEAR))) return rc;
     }
@@ -661,7 +846,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         const int grid = tcp ? gather_grid(literal_gather_kernel<V, __nv_bfloat16>, Nt, GATHER_WARPS, c->sm_count)
                              : gather_grid(literal_gather_kernel<V, float>, Nt, GATHER_WARPS, c->sm_count);
-        if (!tcp)
+        if (x3p)    // 4*clauses_loss is read back as hi + lo from the clause rows' planes
+            literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
+                g, c->chains, nullptr, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, nullptr, ldv, F + DSAT_AUX_PAD,
+                vrow_b(c), vplane, crow_b(c), cplane);
+        else if (!tcp)
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
 #ifdef DSAT_WITH_TCGEN05
@@ -677,7 +866,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
-        if (!tcp)
+        if (x3p)
+            pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, nullptr, ldc, nullptr, 0,
+                crow_b(c), cplane, nullptr, 0);
+        else if (!tcp)
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
 #ifdef DSAT_WITH_TCGEN05
@@ -689,7 +882,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if (rc) return rc;
     LAUNCHED(c);
     // update_gate MLP                                                            (:277-278)
-    if (!tcp) {
+    if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+        if ((rc = run_x3(c, XU, OP_U3))) return rc;
+#endif
+    } else if (!tcp) {
         if ((rc = run_linear(c, OP_U1, c->VROW.p, ldv, c->U1.p, c->HU, Nt, EPI_LRELU))) return rc;
         if ((rc = run_linear(c, OP_U2, c->U1.p, c->HU, c->U2.p, c->HU, Nt, EPI_LRELU))) return rc;
         if ((rc = run_linear(c, OP_U3, c->U2.p, c->HU, c->UOUT.p, F, Nt, EPI_LINEAR))) return rc;
@@ -710,7 +907,13 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
-        if (!tcp)
+        if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+            pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
+                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, nullptr, ldv, nullptr, F,
+                vrow_b(c), vplane, c->SPREp.p, (size_t)Nt * F);
+#endif
+        } else if (!tcp)
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
 #ifdef DSAT_WITH_TCGEN05
@@ -722,7 +925,11 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     if (rc) return rc;
     LAUNCHED(c);
     // variables_output MLP                                                       (:283)
-    if (!tcp) {
+    if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+        if ((rc = run_x3(c, XO, OP_O2))) return rc;
+#endif
+    } else if (!tcp) {
         if ((rc = run_linear(c, OP_O1, c->SPRE.p, F, c->O1.p, c->HO, Nt, EPI_LRELU))) return rc;
         if ((rc = run_linear(c, OP_O2, c->O1.p, c->HO, c->LOGITS.p, DSAT_LOGIT_PAD, Nt, EPI_LINEAR))) return rc;
     }
@@ -857,6 +1064,9 @@ void dsat_destroy(dsat_ctx* c) {
         op.w_bf16.release();
 #endif
     }
+#ifdef DSAT_WITH_TCGEN05
+    for (auto& w : c->wx) w.release();
+#endif
     c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
     c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release(); c->var_order.release();
     c->cl_idx16.release(); c->lit_idx16.release(); c->cl_idx16_vecs = c->lit_idx16_vecs = 0;
@@ -900,11 +1110,29 @@ int dsat_timer_end(dsat_ctx* c, float* ms) {
 
 long long dsat_launch_count(const dsat_ctx* c) { return c ? c->launches : 0; }
 
+#ifdef DSAT_WITH_TCGEN05
+// widths the x3 kernels tile: every layer at most 256 wide, or a single layer that is a multiple of 256
+static bool x3_supported(const dsat_ctx* c) {
+    auto wide_ok = [](int n) { return n <= 256 || n % 256 == 0; };
+    return c->HQ <= 256 && c->HC <= 256 && c->HU <= 256 && c->HO <= 256 && c->Q + c->F <= 256 && wide_ok(c->HL) && wide_ok(2 * c->Q);
+}
+#endif
+
+int dsat_get_precision(const dsat_ctx* c) { return c ? c->precision : DSAT_ERR_ARG; }
+
 int dsat_set_precision(dsat_ctx* c, int dtype) {
     if (!c) return DSAT_ERR_ARG;
     if (dtype == DSAT_F32) { c->precision = dtype; return DSAT_OK; }
 #ifdef DSAT_WITH_TCGEN05
     if (dtype == DSAT_BF16 || dtype == DSAT_BF16_UNFUSED) { c->precision = dtype; return DSAT_OK; }
+    if (dtype == DSAT_F32_TC) {
+        if (c->has_model && !x3_supported(c)) {
+            c->err = "DSAT_F32_TC needs layer widths of at most 256 (feature_maps, query_maps <= 128); use DSAT_F32";
+            return DSAT_ERR_UNSUPPORTED;
+        }
+        c->precision = dtype;
+        return DSAT_OK;
+    }
 #endif
     c->err = "precision not available in this build";
     return DSAT_ERR_UNSUPPORTED;
@@ -932,6 +1160,9 @@ int dsat_set_model(dsat_ctx* c, int n_layers, const float* const* kernels, const
     if (rc) return rc;
 #ifdef DSAT_WITH_TCGEN05
     if ((rc = tc_pack_weights(c))) return rc;
+    if ((rc = x3_pack_weights(c))) return rc;
+    // widths the split-precision kernels do not tile run their Dense layers on the CUDA cores instead (same fp32 results)
+    if (c->precision == DSAT_F32_TC && !x3_supported(c)) c->precision = DSAT_F32;
 #endif
     c->has_model = true;
     return DSAT_OK;
@@ -1354,6 +1585,25 @@ int dsat_debug_read(dsat_ctx* c, int buffer, float* host_out, long long count) {
     CK_ARG(c, count == rows * ld, "dsat_debug_read: count must be rows*ld");
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
 #ifdef DSAT_WITH_TCGEN05
+    if (use_x3(c)) {    // MLP inputs live as hi/lo planes, the hidden activations of the fused MLPs are never materialised
+        const __nv_bfloat16* src = nullptr;
+        switch (buffer) {
+            case DSAT_BUF_VROW: src = c->VROWp.p; break;
+            case DSAT_BUF_CROW: src = c->CROWp.p; break;
+            case DSAT_BUF_SPRE: src = c->SPREp.p; break;
+            case DSAT_BUF_H2: src = c->H2p.p; break;
+            case DSAT_BUF_H1: case DSAT_BUF_CH: case DSAT_BUF_U1: case DSAT_BUF_U2: case DSAT_BUF_O1:
+                c->err = "this buffer stays on-chip on the fp32-accurate tensor-core path";
+                return DSAT_ERR_UNSUPPORTED;
+            default: break;
+        }
+        if (src) {
+            std::vector<__nv_bfloat16> tmp((size_t)count * 2);
+            CK_CUDA(c, dsat_memcpy_sync(tmp.data(), src, (size_t)count * 4, cudaMemcpyDeviceToHost));
+            for (long long i = 0; i < count; ++i) host_out[i] = __bfloat162float(tmp[i]) + __bfloat162float(tmp[count + i]);
+            return DSAT_OK;
+        }
+    }
     if (use_tc(c)) {    // on the tensor-core path these buffers live in bf16: convert for the caller
         const __nv_bfloat16* src = nullptr;
         switch (buffer) {
@@ -1387,10 +1637,27 @@ int dsat_debug_write(dsat_ctx* c, int buffer, const float* host_in, long long co
     if ((rc = debug_buffer(c, buffer, &p, &rows, &ld))) return rc;
     CK_ARG(c, count == rows * ld, "dsat_debug_write: count must be rows*ld");
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
+#ifdef DSAT_WITH_TCGEN05
+    if (use_x3(c)) {
+        __nv_bfloat16* dst = buffer == DSAT_BUF_VROW ? c->VROWp.p : buffer == DSAT_BUF_CROW ? c->CROWp.p
+                           : buffer == DSAT_BUF_SPRE ? c->SPREp.p : nullptr;
+        if (dst) {
+            std::vector<__nv_bfloat16> tmp((size_t)count * 2);
+            for (long long i = 0; i < count; ++i) {
+                const __nv_bfloat16 hi = __float2bfloat16(host_in[i]);
+                tmp[i] = hi;
+                tmp[count + i] = __float2bfloat16(host_in[i] - __bfloat162float(hi));
+            }
+            CK_CUDA(c, dsat_memcpy_sync(dst, tmp.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
+            return DSAT_OK;
+        }
+        if (p == nullptr) { c->err = "this buffer stays on-chip on the fp32-accurate tensor-core path"; return DSAT_ERR_UNSUPPORTED; }
+    }
+#endif
     CK_CUDA(c, dsat_memcpy_sync(p, host_in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
 #ifdef DSAT_WITH_TCGEN05
-    if (use_tc(c) && (buffer == DSAT_BUF_VROW || buffer == DSAT_BUF_CROW)) {   // keep the bf16 state mirror in step
-        __nv_bfloat16* dst = buffer == DSAT_BUF_VROW ? c->VROWb.p : c->CROWb.p;
+    if (use_tc(c) && (buffer == DSAT_BUF_VROW || buffer == DSAT_BUF_CROW || buffer == DSAT_BUF_SPRE)) {   // keep the bf16 mirrors in step
+        __nv_bfloat16* dst = buffer == DSAT_BUF_VROW ? c->VROWb.p : buffer == DSAT_BUF_CROW ? c->CROWb.p : c->SPREb.p;
         const long long tot = rows * ld;
         mirror_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(p, ld, dst, ld, rows, ld);
         LAUNCHED(c);
@@ -1472,7 +1739,6 @@ int dsat_debug_begin(dsat_ctx* c, float noise_scale, const float* noisy_num, con
     }
     NoiseSource ns{0ull, 0ull, 0u};
     if ((rc = begin_call(c, noise_scale, c->inj_noisy.p, nullptr, labels ? c->inj_labels.p : nullptr, false, ns))) return rc;
-    // dsat_debug_round re-reads the noise scale from aux column 6 of row 0
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
     return DSAT_OK;
 }
@@ -1487,11 +1753,72 @@ int dsat_debug_round(dsat_ctx* c, int round, const float* normals) {
         CK_CUDA(c, c->inj_normals.alloc(Nt * 4));
         CK_CUDA(c, c->inj_normals.upload(normals, Nt * 4, c->stream));
     }
-    float noise_scale = 0.f;
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
-    CK_CUDA(c, dsat_memcpy_sync(&noise_scale, c->VROW.p + c->F + 6, sizeof(float), cudaMemcpyDeviceToHost));
+    const float noise_scale = c->last_noise_scale;      // set by dsat_debug_begin
     NoiseSource ns{0ull, 0ull, 0u};
     rc = run_round(c, round, normals ? c->inj_normals.p : nullptr, ns, loss_scalars(noise_scale));
+    if (rc) return rc;
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DSAT_OK;
+}
+
+// One MLP alone in the active precision, on whatever its input buffer holds (written with dsat_debug_write):
+// 0 variables_query (VROW -> QS), 1 lit_query (VROW -> LIT), 2 clause_update (CROW -> COUT), 3 update_gate (VROW -> UOUT),
+// 4 variables_output (SPRE -> LOGITS).
+int dsat_debug_mlp(dsat_ctx* c, int which) {
+    if (!c || which < 0 || which > 4) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_active_buffers(c);
+    if (rc) return rc;
+    const long long Nt = c->Nt, Mt = c->Mt;
+    const int F = c->F, Q = c->Q, ldv = c->ldv(), ldc = c->ldc(), ldh1 = c->ldh1();
+    (void)Mt; (void)ldc;
+#ifdef DSAT_WITH_TCGEN05
+    if (use_x3(c)) {
+        enum { XQ = 0, XL1, XL2, XL3, XC, XU, XO };
+        switch (which) {
+            case 0: rc = run_x3(c, XQ, OP_Q2); break;
+            case 1: rc = run_x3(c, XL1, OP_V1); if (!rc) rc = run_x3(c, XL2, OP_L2); if (!rc) rc = run_x3(c, XL3, OP_L3); break;
+            case 2: rc = run_x3(c, XC, OP_C2); break;
+            case 3: rc = run_x3(c, XU, OP_U3); break;
+            default: rc = run_x3(c, XO, OP_O2); break;
+        }
+    } else if (use_tc(c) && c->precision == DSAT_BF16 && c->fused_ready && c->use_fused) {
+        static const int cls[5] = {OP_Q2, OP_L3, OP_C2, OP_U3, OP_O2};
+        rc = run_fused(c, which, cls[which]);
+    } else if (use_tc(c)) {
+        switch (which) {
+            case 0: rc = run_linear_tc(c, OP_V1, Nt, tc::TC_LRELU, c->H1b.p, ldh1, true);
+                    if (!rc) rc = run_linear_tc(c, OP_Q2, Nt, tc::TC_QUERY, c->QSb.p, 3 * Q, true); break;
+            case 1: rc = run_linear_tc(c, OP_V1, Nt, tc::TC_LRELU, c->H1b.p, ldh1, true);
+                    if (!rc) rc = run_linear_tc(c, OP_L2, Nt, tc::TC_LRELU, c->H2b.p, c->HL, true);
+                    if (!rc) rc = run_linear_tc(c, OP_L3, Nt, tc::TC_LINEAR, c->LITb.p, 2 * Q, true); break;
+            case 2: rc = run_linear_tc(c, OP_C1, Mt, tc::TC_LRELU, c->CHb.p, c->HC, true);
+                    if (!rc) rc = run_linear_tc(c, OP_C2, Mt, tc::TC_LINEAR, c->COUTb.p, Q + F, true); break;
+            case 3: rc = run_linear_tc(c, OP_U1, Nt, tc::TC_LRELU, c->U1b.p, c->HU, true);
+                    if (!rc) rc = run_linear_tc(c, OP_U2, Nt, tc::TC_LRELU, c->U2b.p, c->HU, true);
+                    if (!rc) rc = run_linear_tc(c, OP_U3, Nt, tc::TC_LINEAR, c->UOUTb.p, F, true); break;
+            default: rc = run_linear_tc(c, OP_O1, Nt, tc::TC_LRELU, c->O1b.p, c->HO, true);
+                     if (!rc) rc = run_linear_tc(c, OP_O2, Nt, tc::TC_LINEAR, c->LOGITS.p, DSAT_LOGIT_PAD, false); break;
+        }
+    } else
+#endif
+    {
+        switch (which) {
+            case 0: rc = run_linear(c, OP_V1, c->VROW.p, ldv, c->H1.p, ldh1, Nt, EPI_LRELU);
+                    if (!rc) rc = run_linear(c, OP_Q2, c->H1.p, ldh1, c->QS.p, 3 * Q, Nt, EPI_QUERY); break;
+            case 1: rc = run_linear(c, OP_V1, c->VROW.p, ldv, c->H1.p, ldh1, Nt, EPI_LRELU);
+                    if (!rc) rc = run_linear(c, OP_L2, c->H1.p + c->HQ, ldh1, c->H2.p, c->HL, Nt, EPI_LRELU);
+                    if (!rc) rc = run_linear(c, OP_L3, c->H2.p, c->HL, c->LIT.p, 2 * Q, Nt, EPI_LINEAR); break;
+            case 2: rc = run_linear(c, OP_C1, c->CROW.p, ldc, c->CH.p, c->HC, Mt, EPI_LRELU);
+                    if (!rc) rc = run_linear(c, OP_C2, c->CH.p, c->HC, c->COUT.p, Q + F, Mt, EPI_LINEAR); break;
+            case 3: rc = run_linear(c, OP_U1, c->VROW.p, ldv, c->U1.p, c->HU, Nt, EPI_LRELU);
+                    if (!rc) rc = run_linear(c, OP_U2, c->U1.p, c->HU, c->U2.p, c->HU, Nt, EPI_LRELU);
+                    if (!rc) rc = run_linear(c, OP_U3, c->U2.p, c->HU, c->UOUT.p, F, Nt, EPI_LINEAR); break;
+            default: rc = run_linear(c, OP_O1, c->SPRE.p, F, c->O1.p, c->HO, Nt, EPI_LRELU);
+                     if (!rc) rc = run_linear(c, OP_O2, c->O1.p, c->HO, c->LOGITS.p, DSAT_LOGIT_PAD, Nt, EPI_LINEAR); break;
+        }
+    }
     if (rc) return rc;
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
     return DSAT_OK;

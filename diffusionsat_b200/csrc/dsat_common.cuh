@@ -118,6 +118,57 @@ __device__ __forceinline__ void lane_store_bf16(__nv_bfloat16* __restrict__ row,
     }
 }
 
+// Split-plane storage (fp32-accurate tensor-core path, dsat_mlp_x3.cuh): a value v lives as hi = bf16(v) in one
+// plane and lo = bf16(v - hi) in a second plane `plane` elements further on (v = hi + lo up to 2^-17 |v|); both
+// planes have the layout of a bf16 row buffer, so the MLP kernels fetch them as two bf16 A operands.
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+    __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+template <int V>
+__device__ __forceinline__ void lane_store_split(__nv_bfloat16* __restrict__ row_hi, size_t plane, int lane, const LaneVec<V>& r) {
+    if constexpr (V == 2) {
+        uint32_t hi, lo;
+        split_bf16x2(r.v[0], r.v[1], hi, lo);
+        reinterpret_cast<uint32_t*>(row_hi)[lane] = hi;
+        reinterpret_cast<uint32_t*>(row_hi + plane)[lane] = lo;
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c) {
+            uint2 hi, lo;
+            split_bf16x2(r.v[4 * c + 0], r.v[4 * c + 1], hi.x, lo.x);
+            split_bf16x2(r.v[4 * c + 2], r.v[4 * c + 3], hi.y, lo.y);
+            reinterpret_cast<uint2*>(row_hi + c * 128)[lane] = hi;
+            reinterpret_cast<uint2*>(row_hi + plane + c * 128)[lane] = lo;
+        }
+    }
+}
+// coherent load of hi + lo (rows that the same kernel also writes)
+template <int V>
+__device__ __forceinline__ LaneVec<V> lane_load_split_rw(const __nv_bfloat16* row_hi, size_t plane, int lane) {
+    LaneVec<V> r;
+    if constexpr (V == 2) {
+        const uint32_t hi = reinterpret_cast<const uint32_t*>(row_hi)[lane];
+        const uint32_t lo = reinterpret_cast<const uint32_t*>(row_hi + plane)[lane];
+        r.v[0] = __uint_as_float(hi << 16) + __uint_as_float(lo << 16);
+        r.v[1] = __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u);
+    } else {
+#pragma unroll
+        for (int c = 0; c < V / 4; ++c) {
+            const uint2 hi = reinterpret_cast<const uint2*>(row_hi + c * 128)[lane];
+            const uint2 lo = reinterpret_cast<const uint2*>(row_hi + plane + c * 128)[lane];
+            r.v[4 * c + 0] = __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
+            r.v[4 * c + 1] = __uint_as_float(hi.x & 0xffff0000u) + __uint_as_float(lo.x & 0xffff0000u);
+            r.v[4 * c + 2] = __uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16);
+            r.v[4 * c + 3] = __uint_as_float(hi.y & 0xffff0000u) + __uint_as_float(lo.y & 0xffff0000u);
+        }
+    }
+    return r;
+}
+
 // storage-type generic front ends (T = float or __nv_bfloat16)
 template <int V, typename T>
 __device__ __forceinline__ LaneVec<V> lane_load_t(const T* __restrict__ row, int lane) {

@@ -197,6 +197,42 @@ __device__ __forceinline__ void umma_bf16_kblock_commit_elect_cg2(uint32_t tmem_
         "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], m;\n"
         "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(slot_free_bar)) : "memory");
 }
+// One K block (four k-steps) without a commit: used where several K blocks share one ring slot (the split-precision
+// kernels multiply two A planes with the same weight block).
+__device__ __forceinline__ void umma_bf16_kblock_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                       uint32_t accumulate_first) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
+        "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_kblock_elect_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                           uint32_t accumulate_first) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q, t;\n"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "setp.eq.b32 t, 0, 0;\n"
+        "add.s64 a1, %1, 2;\n add.s64 a2, %1, 4;\n add.s64 a3, %1, 6;\n"
+        "add.s64 b1, %2, 2;\n add.s64 b2, %2, 4;\n add.s64 b3, %2, 6;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate_first) : "memory");
+}
 __device__ __forceinline__ void tcgen05_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n"

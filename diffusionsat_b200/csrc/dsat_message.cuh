@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32)
 clause_gather_kernel(UnitGraphDev g, int chains,
                      const T* __restrict__ LIT, int ld_lit,
                      const T* __restrict__ SP, int ld_sp, int sp_off,
-                     T* __restrict__ OUT, int ld_out, int out_off) {
+                     T* __restrict__ OUT, int ld_out, int out_off,
+                     __nv_bfloat16* __restrict__ OUT_HI = nullptr, size_t out_plane = 0) {   // split-plane output instead of OUT
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
     RowCursor cur = row_cursor((long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5),
@@ -111,6 +112,12 @@ clause_gather_kernel(UnitGraphDev g, int chains,
             acc_l.v[i] *= rw;
             acc_s.v[i] = 4.0f * expf(-acc_s.v[i]);
         }
+        if (OUT_HI) {
+            __nv_bfloat16* dsth = OUT_HI + ((size_t)c * g.m + j) * ld_out + out_off;
+            lane_store_split<V>(dsth, out_plane, lane, acc_l);
+            lane_store_split<V>(dsth + Q, out_plane, lane, acc_s);
+            continue;
+        }
         T* dst = OUT + ((size_t)c * g.m + j) * ld_out + out_off;
         lane_store_t<V, T>(dst, lane, acc_l);
         lane_store_t<V, T>(dst + Q, lane, acc_s);
@@ -130,7 +137,9 @@ literal_gather_kernel(UnitGraphDev g, int chains,
                       const T* __restrict__ CL4, int ld_cl, int cl_off,
                       const T* __restrict__ MSG, int ld_msg,
                       const T* __restrict__ QRY, int ld_q,
-                      T* __restrict__ OUT, int ld_out, int out_off) {
+                      T* __restrict__ OUT, int ld_out, int out_off,
+                      __nv_bfloat16* __restrict__ OUT_HI = nullptr, size_t out_plane = 0,    // split-plane output instead of OUT
+                      const __nv_bfloat16* __restrict__ CL4_HI = nullptr, size_t cl_plane = 0) {   // split-plane CL4 instead of CL4
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
     RowCursor cur = row_cursor((long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5),
@@ -148,8 +157,10 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             int e = e0;
             for (; e + 2 <= e1; e += 2) {
                 const size_t j0 = cbase + __ldg(g.lit_clause + e), j1 = cbase + __ldg(g.lit_clause + e + 1);
-                LaneVec<V> a0 = lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
-                LaneVec<V> a1 = lane_load_t<V, T>(CL4 + j1 * ld_cl + cl_off, lane);
+                LaneVec<V> a0 = CL4_HI ? lane_load_split_rw<V>(CL4_HI + j0 * ld_cl + cl_off, cl_plane, lane)
+                                       : lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
+                LaneVec<V> a1 = CL4_HI ? lane_load_split_rw<V>(CL4_HI + j1 * ld_cl + cl_off, cl_plane, lane)
+                                       : lane_load_t<V, T>(CL4 + j1 * ld_cl + cl_off, lane);
                 LaneVec<V> b0 = lane_load_t<V, T>(MSG + j0 * ld_msg, lane);
                 LaneVec<V> b1 = lane_load_t<V, T>(MSG + j1 * ld_msg, lane);
 #pragma unroll
@@ -160,7 +171,8 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             }
             for (; e < e1; ++e) {
                 const size_t j0 = cbase + __ldg(g.lit_clause + e);
-                LaneVec<V> a0 = lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
+                LaneVec<V> a0 = CL4_HI ? lane_load_split_rw<V>(CL4_HI + j0 * ld_cl + cl_off, cl_plane, lane)
+                                       : lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
                 LaneVec<V> b0 = lane_load_t<V, T>(MSG + j0 * ld_msg, lane);
 #pragma unroll
                 for (int i = 0; i < V; ++i) { s4[sgn].v[i] += a0.v[i]; ms[sgn].v[i] += b0.v[i]; }
@@ -177,6 +189,13 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             grad.v[i] = (-sg * s4[0].v[i] + sgn_ * s4[1].v[i]) * vw;
             ms[0].v[i] *= dwp;
             ms[1].v[i] *= dwn;
+        }
+        if (OUT_HI) {
+            __nv_bfloat16* dsth = OUT_HI + row * ld_out + out_off;
+            lane_store_split<V>(dsth, out_plane, lane, grad);
+            lane_store_split<V>(dsth + Q, out_plane, lane, ms[0]);
+            lane_store_split<V>(dsth + 2 * Q, out_plane, lane, ms[1]);
+            continue;
         }
         T* dst = OUT + row * ld_out + out_off;
         lane_store_t<V, T>(dst, lane, grad);

@@ -33,7 +33,10 @@ __global__ void __launch_bounds__(PN_WARPS * 32)
 pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
                 const TS* __restrict__ SRC, int ld_src, int src_off,
                 TX* __restrict__ STATE, int ld_state,
-                TX* __restrict__ PRE, int ld_pre) {
+                TX* __restrict__ PRE, int ld_pre,
+                // split-plane state (fp32-accurate tensor-core path): hi planes + distance to the lo planes, instead of STATE / PRE
+                __nv_bfloat16* STATE_HI = nullptr, size_t state_plane = 0,
+                __nv_bfloat16* __restrict__ PRE_HI = nullptr, size_t pre_plane = 0) {
     constexpr int F = 32 * V;
     __shared__ float red[PN_WARPS][F];
     __shared__ float mean_s[F];
@@ -89,8 +92,17 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
                 nw.v[i] = __fadd_rn(__fmul_rn(x.v[i] * inv, 0.25f), __fmul_rn(0.1f, old.v[i]));
                 carried.v[i] = __fadd_rn(__fmul_rn(nw.v[i], 0.2f), __fmul_rn(nw.v[i], 0.8f));
             }
+            if (STATE_HI) {
+                if (PRE_HI) lane_store_split<V>(PRE_HI + r * ld_pre, pre_plane, lane, nw);
+                lane_store_split<V>(STATE_HI + r * ld_state, state_plane, lane, carried);
+                return;
+            }
             if (PRE) lane_store_t<V, TX>(PRE + r * ld_pre, lane, nw);
             lane_store_t<V, TX>(STATE + r * ld_state, lane, carried);
+        };
+        auto load_old = [&](size_t r) {
+            return STATE_HI ? lane_load_split_rw<V>(STATE_HI + r * ld_state, state_plane, lane)
+                            : lane_load_rw_t<V, TX>(STATE + r * ld_state, lane);
         };
         {
             size_t r = r0 + warp;
@@ -99,14 +111,14 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
 #pragma unroll
                 for (int u = 0; u < PN_UNROLL; ++u) {
                     x[u] = lane_load_t<V, TS>(SRC + (r + u * PN_WARPS) * ld_src + src_off, lane);
-                    old[u] = lane_load_rw_t<V, TX>(STATE + (r + u * PN_WARPS) * ld_state, lane);
+                    old[u] = load_old(r + u * PN_WARPS);
                 }
 #pragma unroll
                 for (int u = 0; u < PN_UNROLL; ++u) finish_row(r + u * PN_WARPS, x[u], old[u]);
             }
             for (; r < r1; r += PN_WARPS) {
                 LaneVec<V> x = lane_load_t<V, TS>(SRC + r * ld_src + src_off, lane);
-                LaneVec<V> old = lane_load_rw_t<V, TX>(STATE + r * ld_state, lane);
+                LaneVec<V> old = load_old(r);
                 finish_row(r, x, old);
             }
         }
@@ -350,7 +362,7 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
                                   const int* __restrict__ labels_in,       // [n_rows] or null -> Philox
                                   int* __restrict__ labels,
                                   float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
-                                  NoiseSource ns) {
+                                  NoiseSource ns, size_t lo_plane = 0) {   // lo_plane > 0: VROW_B is a hi plane with its lo plane that far on
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     float a, b;
@@ -363,11 +375,23 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
         b = 1.0f - a;
     }
     if (X) X[r] = make_float2(a, b);
-    float* aux = VROW + (size_t)r * ld + aux_off;
-    reinterpret_cast<float4*>(aux)[1] = make_float4(a, b, noise_scale, 0.f);
-    reinterpret_cast<float4*>(aux)[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-    reinterpret_cast<float4*>(aux)[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (VROW_B) {   // columns 4..15 of the bf16 aux block (0..3 are the per-round normals)
+    if (VROW) {
+        float* aux = VROW + (size_t)r * ld + aux_off;
+        reinterpret_cast<float4*>(aux)[1] = make_float4(a, b, noise_scale, 0.f);
+        reinterpret_cast<float4*>(aux)[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(aux)[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (VROW_B && lo_plane) {   // split planes: a, b are 0/1 (exact in bf16), the noise scale is split
+        __nv_bfloat16* auxh = VROW_B + (size_t)r * ld + aux_off;
+        __nv_bfloat16* auxl = auxh + lo_plane;
+        uint32_t ab_hi, ab_lo, ns_hi, ns_lo;
+        split_bf16x2(a, b, ab_hi, ab_lo);
+        split_bf16x2(noise_scale, 0.f, ns_hi, ns_lo);
+        reinterpret_cast<uint32_t*>(auxh)[2] = ab_hi; reinterpret_cast<uint32_t*>(auxl)[2] = ab_lo;
+        reinterpret_cast<uint32_t*>(auxh)[3] = ns_hi; reinterpret_cast<uint32_t*>(auxl)[3] = ns_lo;
+#pragma unroll
+        for (int i = 4; i < 8; ++i) { reinterpret_cast<uint32_t*>(auxh)[i] = 0u; reinterpret_cast<uint32_t*>(auxl)[i] = 0u; }
+    } else if (VROW_B) {   // columns 4..15 of the bf16 aux block (0..3 are the per-round normals)
         __nv_bfloat16* auxb = VROW_B + (size_t)r * ld + aux_off;
         __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
         reinterpret_cast<__nv_bfloat162*>(auxb)[2] = __floats2bfloat162_rn(a, b);
@@ -382,7 +406,7 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
 // Fresh N(0,1)[.,4] every round (reference model/query_sat.py:239).
 __global__ void round_noise_kernel(long long n_rows, const float* __restrict__ normals_in /*[n_rows,4] or null*/,
                                    float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
-                                   NoiseSource ns, unsigned int round) {
+                                   NoiseSource ns, unsigned int round, size_t lo_plane = 0) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     float4 nrm;
@@ -393,8 +417,15 @@ __global__ void round_noise_kernel(long long n_rows, const float* __restrict__ n
         box_muller(p.x, p.y, nrm.x, nrm.y);
         box_muller(p.z, p.w, nrm.z, nrm.w);
     }
-    reinterpret_cast<float4*>(VROW + (size_t)r * ld + aux_off)[0] = nrm;
-    if (VROW_B) {
+    if (VROW) reinterpret_cast<float4*>(VROW + (size_t)r * ld + aux_off)[0] = nrm;
+    if (VROW_B && lo_plane) {
+        uint2 hi, lo;
+        split_bf16x2(nrm.x, nrm.y, hi.x, lo.x);
+        split_bf16x2(nrm.z, nrm.w, hi.y, lo.y);
+        __nv_bfloat16* auxh = VROW_B + (size_t)r * ld + aux_off;
+        *reinterpret_cast<uint2*>(auxh) = hi;
+        *reinterpret_cast<uint2*>(auxh + lo_plane) = lo;
+    } else if (VROW_B) {
         __nv_bfloat162* auxb = reinterpret_cast<__nv_bfloat162*>(VROW_B + (size_t)r * ld + aux_off);
         auxb[0] = __floats2bfloat162_rn(nrm.x, nrm.y);
         auxb[1] = __floats2bfloat162_rn(nrm.z, nrm.w);

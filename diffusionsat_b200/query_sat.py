@@ -129,7 +129,14 @@ class QuerySAT:
                              (self.weights.feature_maps, self.weights.query_maps))
         self.ctx = context if context is not None else _lib.Context(device)
         self.ctx.set_model(self.weights)
-        self.ctx.set_precision({"fp32": _lib.F32, "bf16": _lib.BF16}[precision])
+        # "fp32" = fp32-accurate Dense layers on the tensor cores (DSAT_F32_TC); widths those kernels do not tile
+        # (feature_maps = 256) run the same fp32 arithmetic on the CUDA cores
+        try:
+            self.ctx.set_precision(_lib.PRECISIONS[precision])
+        except _lib.DsatError:
+            if _lib.PRECISIONS[precision] != _lib.F32_TC:
+                raise
+            self.ctx.set_precision(_lib.F32)
         self.precision = precision
         self._graph_key = None
 

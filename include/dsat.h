@@ -35,8 +35,14 @@ enum dsat_status {
     DSAT_ERR_UNSUPPORTED = -4
 };
 
-/* DSAT_BF16: tcgen05 path with one kernel per MLP; DSAT_BF16_UNFUSED: one tcgen05 kernel per Dense layer */
-enum dsat_dtype { DSAT_F32 = 0, DSAT_BF16 = 1, DSAT_BF16_UNFUSED = 2 };
+/* Arithmetic of the twelve Dense layers (everything else is fp32 in every mode):
+ *   DSAT_F32          fp32 FMA on the CUDA cores (bit-level cross-check of the tensor-core paths)
+ *   DSAT_F32_TC       fp32-accurate on the tcgen05 tensor cores: every operand is carried as two bf16 planes (hi, lo) and
+ *                     every product is three bf16 MMAs into one fp32 accumulator (~1e-5 relative); the default of the
+ *                     Python drop-in classes; matches the reference's fp32 Dense layers within the 1e-3 tolerance
+ *   DSAT_BF16         plain bf16 operands and bf16 activation storage, one tcgen05 kernel per MLP (stated separately)
+ *   DSAT_BF16_UNFUSED the same with one tcgen05 kernel per Dense layer */
+enum dsat_dtype { DSAT_F32 = 0, DSAT_BF16 = 1, DSAT_BF16_UNFUSED = 2, DSAT_F32_TC = 3 };
 
 /* debug/parity access to the activation buffers of one round (dsat_debug_read / dsat_debug_write) */
 enum dsat_buffer {
@@ -83,8 +89,11 @@ long long dsat_launch_count(const dsat_ctx* ctx);
 int dsat_set_model(dsat_ctx* ctx, int n_layers, const float* const* kernels, const float* const* biases,
                    const int* in_dims, const int* out_dims);
 
-/* dtype of the MLP path: DSAT_F32 = CUDA-core fp32 (parity path), DSAT_BF16 = tcgen05 tensor cores */
+/* dtype of the MLP path, see enum dsat_dtype */
 int dsat_set_precision(dsat_ctx* ctx, int dtype);
+/* The active dtype.  A new context starts in DSAT_F32_TC; dsat_set_model switches it to DSAT_F32 (CUDA cores, the same
+ * fp32 results) for layer widths the split-precision kernels do not tile (feature_maps or query_maps = 256). */
+int dsat_get_precision(const dsat_ctx* ctx);
 
 /* Unit graph shared by all chains.  cl_lit holds literal codes 2*var+sign (var 0-based in the unit);
  * lit_rowptr is indexed by literal code.  var_seg/clause_seg [n_graphs+1] delimit the formulas of a
@@ -152,6 +161,10 @@ int dsat_debug_read(dsat_ctx* ctx, int buffer, float* host_out, long long count)
 int dsat_debug_write(dsat_ctx* ctx, int buffer, const float* host_in, long long count);
 int dsat_debug_groups(dsat_ctx* ctx, int32_t* done, int32_t* steps_taken, float* loss_sum,
                       int32_t* graph_sat, int32_t* graph_map);
+/* One MLP alone in the active precision on the current contents of its input buffer (model/query_sat.py:117-122):
+ * which = 0 variables_query (VROW -> QS), 1 lit_query (VROW -> LIT), 2 clause_update (CROW -> COUT),
+ * 3 update_gate (VROW -> UOUT), 4 variables_output (SPRE -> LOGITS). */
+int dsat_debug_mlp(dsat_ctx* ctx, int which);
 
 #ifdef __cplusplus
 }

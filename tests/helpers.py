@@ -34,3 +34,19 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-12))
+
+
+def bf16_round(x):
+    """Round-to-nearest-even to bfloat16, returned as float32 (numpy has no bf16)."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    bits = a.view(np.uint32).astype(np.uint64)
+    rounded = ((bits + 0x7FFF + ((bits >> 16) & 1)) >> 16) << 16
+    return rounded.astype(np.uint32).view(np.float32).reshape(a.shape)
+
+
+def elementwise_excess(got, want, rel, abs_of_rms):
+    """max over elements of |got - want| / (rel |want| + abs_of_rms rms(want)); <= 1 means every element is inside."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    rms = float(np.sqrt(np.mean(want ** 2))) + 1e-30
+    return float(np.max(np.abs(got - want) / (rel * np.abs(want) + abs_of_rms * rms)))
