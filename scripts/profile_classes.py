@@ -3,7 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from diffusionsat_b200 import _lib, synth, weights, graph
 chains = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-prec = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+prec = int(prec) if prec.isdigit() else _lib.PRECISIONS[prec]
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 ctx = _lib.Context(0); ctx.set_model(weights.init_weights(seed=1234)); ctx.set_precision(prec)
 nv, cl = synth.random_3sat(n, seed=0); ctx.set_graph(graph.build_unit_graph(nv, cl), chains=chains, group_graphs=31)

@@ -12,7 +12,7 @@ n = int(sys.argv[5]) if len(sys.argv) > 5 else 100
 build.build()
 ctx = _lib.Context(0)
 ctx.set_model(weights.init_weights(seed=1234))
-ctx.set_precision({"fp32": 0, "bf16": 1}[prec])
+ctx.set_precision(_lib.PRECISIONS[prec])
 nv, clauses = synth.random_3sat(n, seed=0)
 unit = graph.build_unit_graph(nv, clauses)
 ctx.set_graph(unit, chains=chains, group_graphs=graph.chains_per_reference_batch(nv, len(clauses)))

@@ -2,7 +2,8 @@
 restatement of reference model/mlp.py:42-50 (Dense = x @ kernel + bias, hidden activation leaky_relu 0.2), element-wise.
 
 * fp32-accurate tensor-core path (DSAT_F32_TC, the default) and the CUDA-core fp32 path: |got - want| <= 2e-4 |want| +
-  2e-5 rms(want) per element (the reference's own fp32 arithmetic sits at ~1e-6; the split-bf16 products at ~1e-5).
+  1e-4 rms(want row) per element (the reference's own fp32 arithmetic sits at ~1e-6 of the row's magnitude, the
+  split-bf16 products at ~1e-5; the absolute term is per ROW because the rows are scaled differently).
 * bf16 path: the fp64 chain rounds to bf16 exactly where the kernel does (operands, hidden activations after the bias add,
   leaky relu on bf16 values, outputs); 2e-3 |want| + 2e-3 rms for at least 99 % of the elements (half a bf16 ulp), and
   one bf16 ulp (8e-3) for every element: an accumulator within rounding distance of a bf16 tie may round the other way.
@@ -119,7 +120,7 @@ def test_fp32_mlp_kernels_elementwise(ctx, precision):
     for name, (got, x, wts) in run_case(ctx, _lib.PRECISIONS[precision]).items():
         want = reference_fp64(name, x, wts)
         rms = float(np.sqrt(np.mean(want ** 2)))
-        bound = 2e-4 * np.abs(want) + 2e-5 * rms
+        bound = 2e-4 * np.abs(want) + 1e-4 * np.sqrt(np.mean(want ** 2, axis=1, keepdims=True))
         bad = np.abs(got - want) > bound
         assert not bad.any(), "%s (%s): %d of %d elements off, worst %.3e at value %.3e (rms %.3e)" % (
             name, precision, int(bad.sum()), bad.size, float(np.abs(got - want).max()), float(want[np.unravel_index(np.argmax(np.abs(got - want)), want.shape)]), rms)
