@@ -10,6 +10,9 @@ enabled, reference batch composition of 31 chains per early-exit group) of 4096 
 `message_pass`: the segment-sum SpMM kernels alone on BASELINE configs[4]'s graph (n=10000), HBM GB/s.
 `cpu_baseline`: the CPU oracle port of the same path on the host cores (bounded sample).
 
+`precisions`: both MLP arithmetics measured the same way; the top-level `value` / `dtype` are the fp32-accurate path's.
+`parity_checked`: one early-exit group of the timed launch re-run on the CPU oracle after the timed region.
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
 """
 from __future__ import annotations
@@ -95,15 +98,6 @@ class ClockSampler:
 
 
 _RESTORE_STDOUT = lambda: None
-
-
-def ncu_traffic(precision):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if precision != "bf16" or not os.path.exists(path):
-        return None
-    with open(path) as fh:
-        return json.load(fh)["fused_mlp_kernel"]["dram_bytes_per_launch"]
 
 
 def formula():
@@ -214,12 +208,135 @@ def message_pass_roofline(ctx, torch, pk):
             "sweep_gbs": {k: {d: round(v[d]["gbs"], 1) for d in v} for k, v in sweep.items()}}
 
 
+PRECISION_DTYPE = {"fp32": "f32", "bf16": "bf16"}
+PRECISION_KERNEL = {
+    "fp32": "x3_mlp_kernel (tcgen05, fp32-accurate: every product = 3 bf16 MMAs on hi/lo planes into one fp32 TMEM accumulator; "
+            "7 persistent launches per round)",
+    "bf16": "fused_mlp_kernel / fused_mlp_split_kernel (tcgen05 bf16, one persistent launch per MLP, 5 per round)",
+}
+
+
+def ncu_traffic(precision):
+    """DRAM bytes per launch of the dominant kernel class from the committed `ncu --set full` capture: NOT measured in this
+    run (a run under ncu is never a bench value); `traffic_source` in the line says so."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            with open(path) as fh:
+                blob = json.load(fh)
+            key = {"fp32": "x3_mlp_kernel", "bf16": "fused_mlp_kernel"}[precision]
+            if key in blob:
+                return blob[key]["dram_bytes_per_launch"], "profiles/" + name
+    return None, None
+
+
+def parity_check(ctx, precision, unit, n, clauses, batch, chains, wts, chain_offset):
+    """One early-exit group from the middle of the timed launch, re-run on the CPU oracle with the same Philox noise
+    (host restatement, diffusionsat_b200/philox.py), after the timed region: 32 free-running rounds of one model call."""
+    import torch
+    from diffusionsat_b200 import philox
+    from oracle import querysat_oracle as O
+    seed, noise_scale = 4242, 0.75
+    rng = np.random.default_rng(17)
+    bits = rng.integers(0, 2, chains * n).astype(np.float32)
+    noisy = np.stack([bits, 1 - bits], axis=1)
+    pred, steps, _ = ctx.model_call(noise_scale, noisy, rounds=ROUNDS, seed=seed, chain_offset=chain_offset)
+    gmap = ctx.debug_groups()["graph_map"]
+    g = (chains // batch) // 2
+    c0 = g * batch
+    rows = slice(c0 * n, (c0 + batch) * n)
+    elems = np.arange((chain_offset + c0) * n, (chain_offset + c0 + batch) * n, dtype=np.uint64)
+    labels = philox.labels(seed, elems, 0)
+    normals = np.stack([philox.normals(seed, elems, 0, r) for r in range(ROUNDS)])
+    graph = O.OracleGraph.copies(n, clauses, batch)
+    trace = []
+    out = O.model_loop(graph, O.weights_to_torch(wts), noise_scale, torch.from_numpy(noisy[rows]),
+                       torch.from_numpy(labels.astype(np.int64)), torch.from_numpy(normals), ROUNDS, trace=trace)
+    want = out[0].numpy().astype(np.float64)
+    same = np.repeat(gmap[c0:c0 + batch] == trace[-1]["best_graph_map"].numpy(), n)
+    got = pred[rows].astype(np.float64)
+    rms = float(np.sqrt(np.mean(want ** 2)))
+    err = np.abs(got - want)[same]
+    tol = 1e-3 if precision == "fp32" else 1e-1
+    inside = err <= tol * np.abs(want[same]) + tol * rms
+    return {"group": int(g), "chains": int(batch), "of_chains": int(chains), "rounds": ROUNDS, "oracle": "fp32 torch-CPU port",
+            "logit_map_agree": float(same.mean()), "max_abs_err_over_rms": float(err.max() / rms) if err.size else None,
+            "tolerance": "%g |z| + %g rms(z) per element" % (tol, tol), "elements_inside": float(inside.mean()) if err.size else None,
+            "decisions_equal": float(((got > 0) == (want > 0))[same].mean()) if err.size else None,
+            "steps_taken_equal": bool(steps[g] == out[1]), "ok": bool(err.size and inside.all() and steps[g] == out[1])}
+
+
+def measure_precision(ctx, precision, args, world, rank, local_rank, unit, batch, chains, chain_offset, barrier, dist, torch, pk):
+    """`value` of one precision: W warm-up + K timed whole reverse-diffusion runs, everything resident, CUDA events on the
+    launching stream, max over ranks; then (rank 0) the per-class device time of four rounds for the roofline."""
+    from diffusionsat_b200 import _lib
+    ctx.set_precision(_lib.PRECISIONS[precision])
+    ctx.set_graph(unit, chains=chains, group_graphs=batch)
+    steps = args.steps if precision == args.precision else max(1, min(args.steps, 3))
+    warmup = args.warmup if precision == args.precision else 3
+    for i in range(warmup):
+        ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=1000 + i, chain_offset=chain_offset)
+    ctx.synchronize()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = ctx.launch_count()
+    ctx.timer_begin()
+    for i in range(steps):
+        ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=1000 + warmup + i, chain_offset=chain_offset)
+    ms = ctx.timer_end()
+    launches = ctx.launch_count() - launches0
+    barrier()
+    clock_info = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    res = {"value": world * chains * steps / (ms_max / 1e3), "unit": "samples/s", "dtype": PRECISION_DTYPE[precision],
+           "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "gpu_launches": int(launches), "clocks": clock_info}
+    if rank != 0:
+        return res
+    prof = ctx.profile_rounds(rounds=4, seed=7)
+    total_ms = sum(v[0] for v in prof.values())
+    gemm_names = list(_lib.Context.PROFILE_CLASSES[:11])
+    gemm_ms = sum(prof[k][0] for k in gemm_names)
+    gemm_launches = sum(prof[k][1] for k in gemm_names)
+    flops = mlp_flops_per_round(ctx.n_rows, ctx.n_clause_rows) * 4
+    achieved_tf = flops / (gemm_ms / 1e3) / 1e12
+    peak_tf = pk["bf16_tflops_sustained"]
+    traffic, traffic_src = ncu_traffic(precision)
+    mma_per_product = 3 if precision == "fp32" else 1
+    res["roofline"] = {
+        "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": pk["source"] + " bf16 sustained",
+        "kernel": PRECISION_KERNEL[precision], "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+        "share_of_round": gemm_ms / total_ms, "flops_per_launch": flops / max(gemm_launches, 1),
+        "bf16_mma_per_algorithmic_product": mma_per_product,
+        "tensor_pipe_frac": mma_per_product * achieved_tf / peak_tf,
+        "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items() if v[1]}}
+    es = 4 if precision == "fp32" else 2
+    q = 128
+    nnz = unit.nnz
+    cg_bytes = ctx.n_rows * 4 * q * es + ctx.n_clause_rows * 2 * q * es + (nnz + unit.n_clauses + 1) * 4
+    lg_bytes = ctx.n_clause_rows * 2 * q * es + ctx.n_rows * q * es + ctx.n_rows * 3 * q * es + (nnz + 2 * unit.n_vars + 1) * 4
+    res["message_pass_in_model"] = {}
+    for name, nbytes in (("clause_gather", cg_bytes), ("literal_gather", lg_bytes)):
+        if prof[name][1] == 0:
+            continue
+        ms_launch = prof[name][0] / prof[name][1]
+        res["message_pass_in_model"][name] = {"gbs": nbytes / ms_launch / 1e6, "frac": nbytes / ms_launch / 1e6 / pk["hbm_gbs"],
+                                              "ms": ms_launch, "bytes": nbytes}
+    return res
+
+
 def run_ours(args):
+    import tempfile
     import torch
     import torch.distributed as dist
-    from diffusionsat_b200 import _lib, build, graph, weights
+    from diffusionsat_b200 import _lib, build, graph, synth, weights
     from diffusionsat_b200 import dist as D
     from diffusionsat_b200.graph import chains_per_reference_batch
+    from diffusionsat_b200.sampler import DiffusionSampler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,17 +350,10 @@ def run_ours(args):
     ctx = _lib.Context(local_rank)
     wts = weights.init_weights(seed=1234)
     ctx.set_model(wts)
-    precision = args.precision
-    try:
-        ctx.set_precision({"fp32": _lib.F32, "bf16": _lib.BF16}[precision])
-    except _lib.DsatError:
-        precision = "fp32"
-        ctx.set_precision(_lib.F32)
     n, clauses = formula()
     unit = graph.build_unit_graph(n, clauses)
     batch = chains_per_reference_batch(n, len(clauses))
     chains = args.chains
-    ctx.set_graph(unit, chains=chains, group_graphs=batch)
     chain_offset = rank * chains
 
     def barrier():
@@ -251,38 +361,44 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step(i):
-        ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=1000 + i, chain_offset=chain_offset)
+    # headline precision first (fp32-accurate tensor-core path = the reference's arithmetic), then the other one
+    order = [args.precision] + [p for p in ("fp32", "bf16") if p != args.precision]
+    if args.single_precision:
+        order = order[:1]
+    per_precision = {}
+    for precision in order:
+        per_precision[precision] = measure_precision(ctx, precision, args, world, rank, local_rank, unit, batch, chains,
+                                                     chain_offset, barrier, dist, torch, pk)
+    head = per_precision[args.precision]
 
-    for i in range(args.warmup):
-        resident_step(i)
-    ctx.synchronize()
+    # end to end through the PUBLIC API: DiffusionSampler(model_path, dimacs).samples(...) with the formula file and the
+    # weights file on the host; every step re-uploads the formula, runs `chains` chains (reference batches of 31, stop rule
+    # on the SAT rate disabled: random-init weights solve nothing), reduces the histogram on the device and copies the SAT
+    # flags and the histogram table back; the ranks' tables are merged over NCCL (all-gather + reduce)
+    tmp = tempfile.mkdtemp(prefix="dsat_bench_")
+    cnf_path, npz_path = os.path.join(tmp, "formula.cnf"), os.path.join(tmp, "weights.npz")
+    with open(cnf_path, "w") as fh:
+        fh.write(synth.dimacs_text(n, clauses))
+    weights.save_weights(npz_path, wts)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sampler = DiffusionSampler(npz_path, cnf_path, context=ctx, precision=args.precision, seed=2000,
+                                   chains_per_launch=chains, chain_offset=chain_offset)
+    sampler.min_sat_rate = 0.0
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    launches0 = ctx.launch_count()
-    ctx.timer_begin()
-    for i in range(args.steps):
-        resident_step(args.warmup + i)
-    ms = ctx.timer_end()
-    launches = ctx.launch_count() - launches0
-    barrier()
-    clock_info = clocks.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * chains * args.steps / (ms_max / 1e3)
-
-    # end to end: host buffers in, host results out, through the C ABI, plus the histogram merge
-    barrier()
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = args.steps
+    hist_sizes = []
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        ctx.set_graph(unit, chains=chains, group_graphs=batch)          # formula upload (host -> device)
-        packed, is_sat, latch, _ = ctx.sample(DIFFUSION_STEPS, ROUNDS, seed=2000 + i, chain_offset=chain_offset)
-        keys, counts = D.local_histogram(packed, is_sat)
-        D.merge_histograms(keys, counts, n)
+        ctx.graph = None                                            # forces dsat_set_graph: the formula travels host -> device
+        with contextlib.redirect_stdout(io.StringIO()):
+            if world == 1:
+                hist = sampler.samples(10 ** 9, max_chains=chains)
+            else:
+                keys, counts = sampler.samples_table(10 ** 9, max_chains=chains)
+                hist = D.merge_histograms(keys, counts, n) or {}
+        hist_sizes.append(sampler.last_stats["distinct"])
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -291,69 +407,64 @@ def run_ours(args):
     e2e_value = world * chains * e2e_steps / float(t.item())
     h2d = int(sum(a.nbytes for a in (unit.cl_rowptr, unit.cl_lit, unit.lit_rowptr, unit.lit_clause, unit.var_seg,
                                      unit.clause_seg)))
-    d2h = int(packed.nbytes + is_sat.nbytes + latch.nbytes)
-    sat_rate = float(is_sat.mean())
+    d2h = int(chains + 8 + max(hist_sizes) * (8 * (-(-n // 64)) + 8))          # SAT flags + totals + histogram table
+    sat_rate = sampler.last_stats["sat"] / max(sampler.last_stats["total"], 1)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # per-class device time of the rounds (CUDA events on the launching stream)
-    prof = ctx.profile_rounds(rounds=4, seed=7)
-    total_ms = sum(v[0] for v in prof.values())
-    gemm_names = list(_lib.Context.PROFILE_CLASSES[:11])
-    gemm_ms = sum(prof[k][0] for k in gemm_names)
-    gemm_launches = sum(prof[k][1] for k in gemm_names)
-    flops = mlp_flops_per_round(ctx.n_rows, ctx.n_clause_rows) * 4
-    achieved_tf = flops / (gemm_ms / 1e3) / 1e12
-    peak_tf = pk["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": ncu_traffic(precision), "peak_source": pk["source"] + " bf16 sustained",
-                "kernel": "sgemm128_kernel (fp32 CUDA cores)" if precision == "fp32"
-                          else "fused_mlp_kernel / fused_mlp_split_kernel (tcgen05 bf16, one persistent launch per MLP, 5 per round)",
-                "avg_launch_ms": gemm_ms / max(gemm_launches, 1), "share_of_round": gemm_ms / total_ms,
-                "flops_per_launch": flops / max(gemm_launches, 1),
-                "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items()}}
-    working_set_gb = (ctx.n_rows * 3500 + ctx.n_clause_rows * 850) * (4 if precision == "fp32" else 2) / 1e9
-    # the two in-model message-passing kernels at the bench configuration: compulsory bytes / event time
-    es = 4 if precision == "fp32" else 2
-    q = 128
-    nnz = unit.nnz
-    cg_bytes = ctx.n_rows * 4 * q * es + ctx.n_clause_rows * 2 * q * es + (nnz + unit.n_clauses + 1) * 4
-    lg_bytes = ctx.n_clause_rows * 2 * q * es + ctx.n_rows * q * es + ctx.n_rows * 3 * q * es + (nnz + 2 * unit.n_vars + 1) * 4
-    in_model = {}
-    for name, nbytes in (("clause_gather", cg_bytes), ("literal_gather", lg_bytes)):
-        ms_launch = prof[name][0] / max(prof[name][1], 1)
-        in_model[name] = {"gbs": nbytes / ms_launch / 1e6, "frac": nbytes / ms_launch / 1e6 / pk["hbm_gbs"],
-                          "ms": ms_launch, "bytes": nbytes}
+    parity = {}
+    if not args.skip_parity:
+        for precision in order:
+            ctx.set_precision(_lib.PRECISIONS[precision])
+            ctx.set_graph(unit, chains=chains, group_graphs=batch)
+            parity[precision] = parity_check(ctx, precision, unit, n, clauses, batch, chains, wts, chain_offset)
+    ctx.set_precision(_lib.PRECISIONS[args.precision])
     message_pass = None if args.skip_message_pass else message_pass_roofline(ctx, torch, pk)
 
     # TRAINED fixture weights (tests/golden/trained_small.npz: a short CPU training on n <= 30) on a satisfiable formula of
     # BASELINE configs[0]'s shape (n=30, m=133): formulas do get satisfied here, so the first-SAT latch and the per-group
     # early exit take effect.  (At n=100, ratio 4.28, these weights solve nothing: they never saw that size.)
     trained = None
+    cfg1 = None
     fixture = os.path.join(ROOT, "tests", "golden", "trained_small.npz")
     if os.path.exists(fixture) and not args.skip_trained:
-        from diffusionsat_b200 import synth
         tn, tclauses, _ = synth.planted_3sat(30, 133, seed=0)
         tunit = graph.build_unit_graph(tn, tclauses)
         tbatch = chains_per_reference_batch(tn, len(tclauses))
         tchains = tbatch * 128
         ctx.set_model(weights.load_weights(fixture))
-        ctx.set_graph(tunit, chains=tchains, group_graphs=tbatch)
-        ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=3000, chain_offset=0)
-        ctx.synchronize()
-        ctx.timer_begin()
-        ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=3001, chain_offset=0)
-        t_ms = ctx.timer_end()
-        t_packed, t_sat, t_latch, _ = ctx.sample_fetch()
         trained = {"workload": "planted 3-SAT n=30 m=133, %d chains in early-exit groups of %d, 32 x 32" % (tchains, tbatch),
-                   "samples_per_s": tchains / (t_ms / 1e3), "sat_rate": float(t_sat.mean()),
-                   "distinct_models": int(len(np.unique(t_packed[t_sat.astype(bool)], axis=0))),
-                   "mean_latch_step": float(t_latch[t_latch >= 0].mean()) if (t_latch >= 0).any() else None,
                    "weights": "tests/golden/trained_small.npz"}
+        for precision in order:
+            ctx.set_precision(_lib.PRECISIONS[precision])
+            ctx.set_graph(tunit, chains=tchains, group_graphs=tbatch)
+            ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=3000, chain_offset=0)
+            ctx.synchronize()
+            ctx.timer_begin()
+            ctx.sample_enqueue(DIFFUSION_STEPS, ROUNDS, seed=3001, chain_offset=0)
+            t_ms = ctx.timer_end()
+            t_packed, t_sat, t_latch, _ = ctx.sample_fetch()
+            trained[precision] = {"samples_per_s": tchains / (t_ms / 1e3), "sat_rate": float(t_sat.mean()),
+                                  "distinct_models": int(len(np.unique(t_packed[t_sat.astype(bool)], axis=0))),
+                                  "mean_latch_step": float(t_latch[t_latch >= 0].mean()) if (t_latch >= 0).any() else None}
+        # BASELINE configs[0]: DiffusionSampler.samples(256) at n=30 through the public API (small-launch regime)
+        cnf1 = os.path.join(tmp, "cfg1.cnf")
+        with open(cnf1, "w") as fh:
+            fh.write(synth.dimacs_text(tn, tclauses))
+        cfg1 = {"workload": "planted 3-SAT n=30 m=133, DiffusionSampler.samples(256), trained fixture weights"}
+        for precision in order:
+            with contextlib.redirect_stdout(io.StringIO()):
+                s1 = DiffusionSampler(fixture, cnf1, context=ctx, precision=precision, seed=5)
+                s1.samples(256)                                     # warm-up (buffers, plans)
+                t1 = time.perf_counter()
+                h1 = s1.samples(256)
+                dt = time.perf_counter() - t1
+            cfg1[precision] = {"seconds": dt, "samples": int(sum(h1.values())), "chains_launched": s1.last_stats["chains_launched"]}
         ctx.set_model(wts)
+        ctx.set_precision(_lib.PRECISIONS[args.precision])
         ctx.set_graph(unit, chains=chains, group_graphs=batch)
 
     cpu = None
@@ -364,19 +475,24 @@ def run_ours(args):
                "sample": "%d chains (one reference batch), 1 of 32 denoising steps x 32 rounds, scaled x32; %.1f s per step"
                          % (batch, secs)}
 
+    working_set_gb = (ctx.n_rows * 3500 + ctx.n_clause_rows * 850) * (4 if args.precision == "fp32" else 2) / 1e9
     line = {
-        "metric": "diffusion samples/sec, 3-SAT n=100", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16", "data": "synthetic",
+        "metric": "diffusion samples/sec, 3-SAT n=100", "value": head["value"], "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
         "config": {"workload": "hard random 3-SAT n=100 m=%d (ratio 4.3), %d chains per GPU, 32 denoising steps x 32 rounds, "
                                "random-init QuerySAT F=Q=128, early-exit groups of %d chains" % (len(clauses), chains, batch),
                    "chains_per_gpu": chains, "parallelism": "chains sharded, dp%d" % world,
                    "l2": "activations touched per round ~%.1f GB >> 126 MB L2: inputs larger than L2, no flush needed"
                          % working_set_gb,
-                   "precision": precision},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "message_pass": message_pass,
-        "message_pass_in_model": in_model, "cpu_baseline": cpu, "sat_rate": sat_rate, "trained_weights": trained,
+                   "precision": args.precision + (" (fp32-accurate Dense layers on tcgen05: 3 split-bf16 MMAs per product; "
+                                                  "everything else fp32)" if args.precision == "fp32" else "")},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "DiffusionSampler(weights.npz, formula.cnf).samples(n, max_chains=%d) + dist.merge_histograms" % chains},
+        "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": head.get("roofline"),
+        "message_pass": message_pass, "message_pass_in_model": head.get("message_pass_in_model"),
+        "precisions": {p: {k: v for k, v in r.items()} for p, r in per_precision.items()},
+        "parity_checked": parity, "cpu_baseline": cpu, "sat_rate": sat_rate, "trained_weights": trained, "cfg1": cfg1,
     }
     _RESTORE_STDOUT()
     print(json.dumps(line), flush=True)
@@ -390,7 +506,11 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DSAT_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("DSAT_PRECISION", "fp32"), choices=["fp32", "bf16"],
+                    help="headline precision: fp32 = fp32-accurate Dense layers on the tensor cores (the reference's arithmetic), "
+                         "bf16 = plain bf16 path; the other one is measured too and reported under `precisions`")
+    ap.add_argument("--single-precision", action="store_true", help="measure only --precision")
+    ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-message-pass", action="store_true")

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "dsat_sample_enqueue": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
     "dsat_sample_fetch": (C.c_int, [_vp, _u64p, _u8p, _i32p, _u8p]),
     "dsat_words_per_graph": (C.c_int, [_vp]),
+    "dsat_hist_reduce": (C.c_int, [_vp, C.c_int, _u64p, C.POINTER(C.c_int64), C.c_int, _i32p, _i32p]),
     "dsat_spmm": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int]),
     "dsat_profile_classes": (C.c_int, []),
     "dsat_profile_fused": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_longlong)]),
@@ -251,6 +252,24 @@ class Context:
         self._check(self._lib.dsat_sample_fetch(self._h, _ptr(packed, C.c_uint64), _ptr(is_sat, C.c_uint8),
                                                 _ptr(latch, C.c_int32), _ptr(sat_any, C.c_uint8)))
         return packed, is_sat, latch, sat_any
+
+    def sample_fetch_sat(self) -> np.ndarray:
+        """Only the per-chain SAT flags of the last run (the sampler's stop rules need nothing else)."""
+        is_sat = np.empty(self.total_graphs, dtype=np.uint8)
+        self._check(self._lib.dsat_sample_fetch(self._h, None, _ptr(is_sat, C.c_uint8), None, None))
+        return is_sat
+
+    def hist_reduce(self, chain_limit: int = 0):
+        """Device-side sort / unique / count of the satisfying assignments of chains ``[0, chain_limit)`` of the last
+        run (0 = all): ``(keys [K, words] uint64 ascending, counts [K] int64, n_sat)``."""
+        words = int(self._lib.dsat_words_per_graph(self._h))
+        cap = self.total_graphs if chain_limit <= 0 else min(int(chain_limit), self.total_graphs)
+        keys = np.empty((cap, words), dtype=np.uint64)
+        counts = np.empty(cap, dtype=np.int64)
+        k, n_sat = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.dsat_hist_reduce(self._h, int(chain_limit), _ptr(keys, C.c_uint64),
+                                               counts.ctypes.data_as(C.POINTER(C.c_int64)), cap, C.byref(k), C.byref(n_sat)))
+        return keys[:k.value], counts[:k.value], int(n_sat.value)
 
     def spmm(self, direction: int, x_dev_ptr: int, y_dev_ptr: int, feat: int, dtype: int, chains: int):
         self._check(self._lib.dsat_spmm(self._h, int(direction), _vp(x_dev_ptr), _vp(y_dev_ptr), int(feat), int(dtype),

@@ -15,7 +15,7 @@ SOURCES = ["dsat_api.cu"]
 
 def _headers():
     found = [f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    return found + [os.path.join("..", "..", "include", "dsat.h")]
+    return found + [os.path.join("..", "..", "include", h) for h in ("dsat.h", "dsat_debug.h")]
 
 
 def _nvcc() -> str:

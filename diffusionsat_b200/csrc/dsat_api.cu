@@ -11,11 +11,13 @@
 #include <vector>
 
 #include "../../include/dsat.h"
+#include "../../include/dsat_debug.h"
 #include "dsat_common.cuh"
 #include "dsat_gemm_simt.cuh"
 #include "dsat_message.cuh"
 #include "dsat_spmm.cuh"
 #include "dsat_norm_head.cuh"
+#include "dsat_hist.cuh"
 #ifdef DSAT_WITH_TCGEN05
 #include "dsat_gemm_tc.cuh"
 #include "dsat_mlp_fused.cuh"
@@ -111,6 +113,9 @@ struct dsat_ctx {
     DevBuf<float> loss_sum, graph_loss;
     DevBuf<unsigned char> BITS, LAST, LATCH, FINAL, is_sat, sat_any;
     DevBuf<unsigned long long> packed;
+    // histogram reduction scratch (dsat_hist.cuh)
+    DevBuf<int> hist_idx, hist_run, hist_totals;
+    DevBuf<unsigned long long> hist_keys, hist_counts;
     // injected noise staging
     DevBuf<float> inj_normals, inj_uniforms, inj_noisy;
     DevBuf<int> inj_labels;
@@ -397,6 +402,7 @@ void release_buffers(dsat_ctx* c) {
     c->graph_sat.release(); c->graph_map.release(); c->graph_loss.release(); c->latch_step.release();
     c->sat_now.release(); c->is_sat.release(); c->sat_any.release(); c->packed.release();
     c->inj_normals.release(); c->inj_uniforms.release(); c->inj_noisy.release(); c->inj_labels.release();
+    c->hist_idx.release(); c->hist_run.release(); c->hist_totals.release(); c->hist_keys.release(); c->hist_counts.release();
 #ifdef DSAT_WITH_TCGEN05
     c->VROWb.release(); c->CROWb.release(); c->H1b.release(); c->H2b.release(); c->QSb.release(); c->LITb.release();
     c->CHb.release(); c->COUTb.release(); c->UOUTb.release(); c->U1b.release(); c->U2b.release(); c->SPREb.release();
@@ -1172,22 +1178,36 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
                    const int32_t* lit_rowptr, const int32_t* lit_clause, int n_graphs, const int32_t* var_seg,
                    const int32_t* clause_seg, int n_chains, int group_graphs) {
     if (!c) return DSAT_ERR_ARG;
-    CK_ARG(c, n_vars > 0 && n_clauses >= 0 && nnz >= 0 && n_graphs > 0 && n_chains > 0, "dsat_set_graph: bad sizes");
+    // everything is validated before the context is touched: a rejected call leaves the previous graph bound
+    CK_ARG(c, n_vars > 0 && n_clauses > 0 && nnz >= 0 && n_graphs > 0 && n_chains > 0,
+           "dsat_set_graph: bad sizes (a formula needs at least one variable and one clause)");
     CK_ARG(c, cl_rowptr && lit_rowptr && var_seg && clause_seg && (nnz == 0 || (cl_lit && lit_clause)),
            "dsat_set_graph: null index array");
     CK_ARG(c, cl_rowptr[0] == 0 && cl_rowptr[n_clauses] == nnz && lit_rowptr[0] == 0 && lit_rowptr[2 * n_vars] == nnz,
            "dsat_set_graph: row pointers do not cover nnz");
+    for (int j = 0; j < n_clauses; ++j)
+        CK_ARG(c, cl_rowptr[j + 1] >= cl_rowptr[j], "dsat_set_graph: clause row pointers are not monotone");
+    for (int l = 0; l < 2 * n_vars; ++l)
+        CK_ARG(c, lit_rowptr[l + 1] >= lit_rowptr[l], "dsat_set_graph: literal row pointers are not monotone");
     CK_ARG(c, var_seg[0] == 0 && var_seg[n_graphs] == n_vars && clause_seg[0] == 0 && clause_seg[n_graphs] == n_clauses,
            "dsat_set_graph: graph segments do not cover the unit");
-    for (int e = 0; e < nnz; ++e) {
-        CK_ARG(c, cl_lit[e] >= 0 && cl_lit[e] < 2 * n_vars, "dsat_set_graph: literal code out of range");
-        CK_ARG(c, lit_clause[e] >= 0 && lit_clause[e] < n_clauses, "dsat_set_graph: clause id out of range");
+    {   // the CSR (clause -> literal codes) and the CSC (literal code -> clauses) must describe the same multiset of edges
+        std::vector<int> deg(2 * (size_t)n_vars, 0);
+        for (int e = 0; e < nnz; ++e) {
+            CK_ARG(c, cl_lit[e] >= 0 && cl_lit[e] < 2 * n_vars, "dsat_set_graph: literal code out of range");
+            CK_ARG(c, lit_clause[e] >= 0 && lit_clause[e] < n_clauses, "dsat_set_graph: clause id out of range");
+            deg[cl_lit[e]]++;
+        }
+        for (int l = 0; l < 2 * n_vars; ++l)
+            CK_ARG(c, deg[l] == lit_rowptr[l + 1] - lit_rowptr[l], "dsat_set_graph: CSR and CSC disagree on a literal's degree");
     }
     int max_graph_vars = 0;
     for (int g = 0; g < n_graphs; ++g) {
         CK_ARG(c, var_seg[g + 1] > var_seg[g] && clause_seg[g + 1] >= clause_seg[g], "dsat_set_graph: empty or unordered graph segment");
         if (var_seg[g + 1] - var_seg[g] > max_graph_vars) max_graph_vars = var_seg[g + 1] - var_seg[g];
     }
+    CK_ARG(c, (long long)n_chains * n_vars < (1ll << 31) - 256 && (long long)n_chains * n_clauses < (1ll << 31) - 256,
+           "dsat_set_graph: too many rows for one context; use fewer chains per context");
     CK_CUDA(c, cudaSetDevice(c->device));
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
     // same shape as before (the usual case: the same formula re-bound, or another formula of the same size):
@@ -1198,6 +1218,7 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
                             c->chains == n_chains && c->words == ceil_div(max_graph_vars, 64) &&
                             c->n_groups == ceil_div(total_graphs_new, group_new);
     if (!same_shape) release_buffers(c);
+    c->has_graph = false;               // set again at the end: an upload that fails half way leaves no graph bound
     c->n = n_vars; c->m = n_clauses; c->nnz = nnz; c->n_graphs = n_graphs; c->chains = n_chains;
     c->total_graphs = n_graphs * n_chains;
     c->group_graphs = group_graphs > 0 ? group_graphs : c->total_graphs;
@@ -1205,8 +1226,6 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     c->Nt = (long long)n_chains * n_vars;
     c->Mt = (long long)n_chains * n_clauses;
     c->words = ceil_div(max_graph_vars, 64);
-    CK_ARG(c, c->Nt < (1ll << 31) - 256 && c->Mt < (1ll << 31) - 256,
-           "dsat_set_graph: too many rows for one context; use fewer chains per context");
 
     std::vector<float> deg_w(2 * n_vars), vdeg_w(n_vars), rev_w(n_clauses > 0 ? n_clauses : 1);
     for (int l = 0; l < 2 * n_vars; ++l) {
@@ -1444,6 +1463,40 @@ int dsat_sample(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t 
                              labels ? c->inj_labels.p : nullptr, (normals && n_rounds > 0) ? c->inj_normals.p : nullptr);
     if (rc) return rc;
     return dsat_sample_fetch(c, packed, is_sat, latch_step, sat_any_step);
+}
+
+// ------------------------------------------------------------------------------------- histogram
+int dsat_hist_reduce(dsat_ctx* c, int chain_limit, uint64_t* keys_out, int64_t* counts_out, int capacity, int32_t* n_unique,
+                     int32_t* n_sat) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, c->has_buffers, "dsat_hist_reduce: nothing was sampled");
+    CK_ARG(c, n_unique && capacity >= 0 && (capacity == 0 || (keys_out && counts_out)), "dsat_hist_reduce: null output");
+    CK_CUDA(c, cudaSetDevice(c->device));
+    const int G = c->total_graphs, words = c->words;
+    const int limit = chain_limit > 0 && chain_limit < G ? chain_limit : G;
+    const int n_pad = hist::next_pow2(G < 2 ? 2 : G);
+    if (c->hist_idx.count < (size_t)n_pad) {
+        CK_CUDA(c, c->hist_idx.alloc(n_pad));
+        CK_CUDA(c, c->hist_run.alloc(n_pad));
+        CK_CUDA(c, c->hist_totals.alloc(2));
+        CK_CUDA(c, c->hist_keys.alloc((size_t)G * words));
+        CK_CUDA(c, c->hist_counts.alloc(G));
+    }
+    CK_CUDA(c, hist::enqueue(c->stream, G, limit, words, c->packed.p, c->is_sat.p, c->hist_idx.p, c->hist_run.p, c->hist_keys.p,
+                             c->hist_counts.p, c->hist_totals.p, &c->launches));
+    int totals[2] = {0, 0};
+    CK_CUDA(c, cudaMemcpyAsync(totals, c->hist_totals.p, sizeof(totals), cudaMemcpyDeviceToHost, c->stream));
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_unique = totals[0];
+    if (n_sat) *n_sat = totals[1];
+    const int k = totals[0] < capacity ? totals[0] : capacity;
+    if (k > 0) {
+        CK_CUDA(c, cudaMemcpyAsync(keys_out, c->hist_keys.p, (size_t)k * words * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK_CUDA(c, cudaMemcpyAsync(counts_out, c->hist_counts.p, (size_t)k * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    CK_ARG(c, totals[0] <= capacity, "dsat_hist_reduce: capacity too small (n_unique holds the required size)");
+    return DSAT_OK;
 }
 
 // ------------------------------------------------------------------------------------------ SpMM

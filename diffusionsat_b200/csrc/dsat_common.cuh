@@ -13,6 +13,15 @@ namespace dsat {
 __host__ __device__ inline int pad16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the shared-memory base probe apply to the CURRENT device only:
+// a process that holds one context per GPU has to repeat them per device (every C-ABI entry calls cudaSetDevice first).
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    static int current() { int d = 0; return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64 ? d : -1; }
+    bool done() const { const int d = current(); return d >= 0 && ((mask >> d) & 1ull); }
+    void mark() { const int d = current(); if (d >= 0) mask |= 1ull << d; }
+};
+
 // ---------------------------------------------------------------------------------- math
 // softplus with the usual large-argument guard (log1p(exp(x)) otherwise); reference
 // loss/sat.py:132 uses tf.nn.softplus.

@@ -468,11 +468,11 @@ struct TcLinear {
 
 inline cudaError_t launch_tc_linear(const TcLinear& op, cudaStream_t stream) {
     if (op.rows <= 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     const int n_tiles = ceil_div(op.N, BLOCK_N);
     const unsigned grid = (unsigned)(n_tiles * ceil_div(op.rows, BLOCK_M));

@@ -919,8 +919,13 @@ __global__ void smem_base_probe_kernel(unsigned* out) {
     *out = tc::smem_u32(probe_raw);
 }
 inline int dyn_smem_pad() {
-    static int pad = -1;
-    if (pad >= 0) return pad;
+    static int pads[64];
+    static PerDeviceOnce probed;
+    const int dev_id = PerDeviceOnce::current();
+    if (dev_id < 0) return 1024;
+    int& pad = pads[dev_id];
+    if (probed.done()) return pad;
+    probed.mark();
     pad = 1024;
     unsigned* dev = nullptr;
     unsigned host = 1;
@@ -1085,8 +1090,8 @@ inline bool plan_fused(FusedMlp& f) {
 
 inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t stream) {
     if (f.p.rows <= 0) return cudaSuccess;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (!configured.done()) {
         cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
@@ -1094,7 +1099,7 @@ inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t st
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     const unsigned threads = 64 + 32 * f.p.epi_warps;
     const int last = f.p.n_layers > 2 ? 2 : 1;

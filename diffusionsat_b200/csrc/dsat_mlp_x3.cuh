@@ -463,12 +463,12 @@ inline bool plan_x3(X3Mlp& f) {
     return false;
 }
 
-inline cudaError_t configure_x3_device(int device) {
-    static unsigned long long done_mask = 0;       // MaxDynamicSharedMemorySize is a per-device function attribute
-    if (device >= 0 && device < 64 && ((done_mask >> device) & 1ull)) return cudaSuccess;
+inline cudaError_t configure_x3_device(int) {
+    static PerDeviceOnce configured;                // MaxDynamicSharedMemorySize is a per-device function attribute
+    if (configured.done()) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(x3_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(x3_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e == cudaSuccess && device >= 0 && device < 64) done_mask |= 1ull << device;
+    if (e == cudaSuccess) configured.mark();
     return e;
 }
 

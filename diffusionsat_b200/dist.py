@@ -31,35 +31,65 @@ def shard_chains(total_chains: int, world_size: int, rank: int, multiple_of: int
     return lo, hi - lo
 
 
+def _records(keys: np.ndarray) -> np.ndarray:
+    """[K, words] uint64 (word 0 least significant) -> [K] structured array whose field order is most significant word
+    first, so that numpy's lexicographic order on it is the numeric order of the encoded integers."""
+    k = np.ascontiguousarray(np.asarray(keys, dtype="<u8")[:, ::-1])
+    return k.view(np.dtype([("f%d" % i, "<u8") for i in range(k.shape[1])])).reshape(-1)
+
+
+def _from_records(rec: np.ndarray, words: int) -> np.ndarray:
+    return np.ascontiguousarray(rec.view("<u8").reshape(-1, words)[:, ::-1])
+
+
 def local_histogram(packed: np.ndarray, is_sat: np.ndarray, limit: int | None = None):
-    """Unique satisfying assignments of this rank: ``(keys [K, words] uint64 sorted, counts [K] int64)``.
-    Only SAT samples are counted (reference DiffusionSampler.py:297-303); ``limit`` keeps the first
-    ``limit`` SAT samples in chain order."""
+    """Host restatement of ``dsat_hist_reduce`` (which the sampler uses): unique satisfying assignments of this rank,
+    ``(keys [K, words] uint64 ascending by encoded integer, counts [K] int64)``.  Only SAT samples are counted
+    (reference DiffusionSampler.py:297-303); ``limit`` keeps the first ``limit`` SAT samples in chain order."""
     sel = np.flatnonzero(np.asarray(is_sat) != 0)
     if limit is not None:
         sel = sel[:limit]
     words = packed.shape[1]
     if sel.size == 0:
         return np.zeros((0, words), dtype=np.uint64), np.zeros(0, dtype=np.int64)
-    keys, counts = np.unique(packed[sel], axis=0, return_counts=True)
-    return keys.astype(np.uint64), counts.astype(np.int64)
+    rec, counts = np.unique(_records(packed[sel]), return_counts=True)
+    return _from_records(rec, words).astype(np.uint64), counts.astype(np.int64)
+
+
+def merge_tables(tables, words: int):
+    """Sum several ``(keys, counts)`` tables into one sorted table (vectorised; used across launches and ranks)."""
+    tables = [(k, c) for k, c in tables if len(c)]
+    if not tables:
+        return np.zeros((0, words), dtype=np.uint64), np.zeros(0, dtype=np.int64)
+    rec = np.concatenate([_records(k) for k, _ in tables])
+    cnt = np.concatenate([np.asarray(c, dtype=np.int64) for _, c in tables])
+    uniq, inverse = np.unique(rec, return_inverse=True)
+    total = np.zeros(uniq.shape[0], dtype=np.int64)
+    np.add.at(total, inverse.reshape(-1), cnt)
+    return _from_records(uniq, words).astype(np.uint64), total
 
 
 def keys_to_ints(keys: np.ndarray, n_bits: int):
+    """Packed words -> Python ints (x1 = bit 0, reference utils/VariableAssignment.py:63-69), masked to ``n_bits``."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    if keys.shape[0] == 0:
+        return []
     mask = (1 << n_bits) - 1
-    out = []
-    for row in keys:
-        value = 0
-        for w, word in enumerate(row):
-            value |= int(word) << (64 * w)
-        out.append(value & mask)
-    return out
+    acc = keys[:, 0].astype(object)
+    for w in range(1, keys.shape[1]):
+        acc = acc | (keys[:, w].astype(object) << (64 * w))
+    return [int(v) & mask for v in acc]
+
+
+def table_to_dict(keys: np.ndarray, counts: np.ndarray, n_bits: int) -> dict:
+    return {k: int(c) for k, c in zip(keys_to_ints(keys, n_bits), counts) if c > 0}
 
 
 def merge_histograms(keys: np.ndarray, counts: np.ndarray, n_bits: int, device=None, group=None, dst: int = 0):
-    """All ranks call this; rank ``dst`` gets the merged ``{int: count}``, the others ``None``."""
+    """All ranks call this with their sorted unique-key table; rank ``dst`` gets the merged ``{int: count}``, the
+    others ``None``.  One all-gather of the padded key tables, one reduce(SUM) of a dense count vector."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return dict(zip(keys_to_ints(keys, n_bits), (int(c) for c in counts)))
+        return table_to_dict(keys, counts, n_bits)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     device = device or (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl"
@@ -68,29 +98,31 @@ def merge_histograms(keys: np.ndarray, counts: np.ndarray, n_bits: int, device=N
     n_local = torch.tensor([keys.shape[0]], dtype=torch.int64, device=device)
     sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(sizes, n_local, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = [int(x) for x in torch.cat(sizes).cpu().tolist()]
     kmax = max(max(sizes), 1)
     padded = torch.zeros(kmax, words, dtype=torch.int64, device=device)
     if keys.shape[0]:
-        padded[:keys.shape[0]] = torch.from_numpy(keys.view(np.int64).copy()).to(device)
-    gathered = [torch.zeros_like(padded) for _ in range(world)]
-    dist.all_gather(gathered, padded, group=group)
-    tables = [g[:s].cpu().numpy().view(np.uint64) for g, s in zip(gathered, sizes) if s > 0]
-    if tables:
-        table = np.unique(np.concatenate(tables, axis=0), axis=0)      # identical on every rank
+        padded[:keys.shape[0]] = torch.from_numpy(np.ascontiguousarray(keys).view(np.int64)).to(device)
+    gathered = torch.empty(world * kmax, words, dtype=torch.int64, device=device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(gathered, padded, group=group)
     else:
-        table = np.zeros((0, words), dtype=np.uint64)
-    dense = torch.zeros(max(table.shape[0], 1), dtype=torch.int64, device=device)
+        dist.all_gather(list(gathered.view(world, kmax, words).unbind(0)), padded, group=group)
+    host = gathered.cpu().numpy().view(np.uint64).reshape(world, kmax, words)
+    tables = [host[r, :s] for r, s in enumerate(sizes) if s > 0]
+    if tables:
+        table_rec = np.unique(np.concatenate([_records(t) for t in tables]))      # identical on every rank, sorted
+    else:
+        table_rec = _records(np.zeros((0, words), dtype=np.uint64))
+    dense = torch.zeros(max(table_rec.shape[0], 1), dtype=torch.int64, device=device)
     if keys.shape[0]:
-        # position of each local key in the global table (rows are sorted lexicographically)
-        lookup = {row.tobytes(): i for i, row in enumerate(table)}
-        pos = torch.tensor([lookup[row.tobytes()] for row in keys], dtype=torch.int64, device=device)
-        dense.index_add_(0, pos, torch.from_numpy(counts).to(device))
+        pos = np.searchsorted(table_rec, _records(keys))      # position of each local key in the global table
+        dense.index_add_(0, torch.from_numpy(pos.astype(np.int64)).to(device), torch.from_numpy(np.asarray(counts, np.int64)).to(device))
     dist.reduce(dense, dst=dst, op=dist.ReduceOp.SUM, group=group)
     if rank != dst:
         return None
-    total = dense.cpu().numpy()
-    return {k: int(c) for k, c in zip(keys_to_ints(table, n_bits), total[:table.shape[0]]) if c > 0}
+    total = dense.cpu().numpy()[:table_rec.shape[0]]
+    return table_to_dict(_from_records(table_rec, words), total, n_bits)
 
 
 def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_chains: int, n_bits: int,
@@ -105,8 +137,8 @@ def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_cha
     ctx = make_context(rank)
     if count > 0:
         ctx.set_graph(unit_graph, chains=count, group_graphs=batch_chains)
-        packed, is_sat, _, _ = ctx.sample(steps, rounds, seed=seed, chain_offset=offset)
-        keys, counts = local_histogram(packed, is_sat)
+        ctx.sample_enqueue(steps, rounds, seed=seed, chain_offset=offset)
+        keys, counts, _ = ctx.hist_reduce()
     else:
         words = -(-n_bits // 64)
         keys, counts = np.zeros((0, words), dtype=np.uint64), np.zeros(0, dtype=np.int64)

@@ -118,17 +118,44 @@ def diffusion(N, model, dataset, step_data, verbose=True, prepare_image=True, *,
 
 def unpack_assignments(packed: np.ndarray, n_bits: int) -> list:
     """Packed little-endian 64-bit words [G, words] -> Python ints (x1 = bit 0), masked to n_bits."""
-    mask = (1 << n_bits) - 1
-    out = []
-    for row in packed:
-        value = 0
-        for w, word in enumerate(row):
-            value |= int(word) << (64 * w)
-        out.append(value & mask)
-    return out
+    from .dist import keys_to_ints
+    return keys_to_ints(np.asarray(packed, dtype=np.uint64), n_bits)
+
+
+def consume_batches(is_sat: np.ndarray, batch: int, still_needed: int, total: int, sat_total: int,
+                    min_sat_rate: float = 0.005):
+    """The reference's stop rules (``satuniformity/DiffusionSampler.py:243-307``) applied to the SAT flags of one launch,
+    vectorised.  Chains are consumed reference batch by reference batch, in order; before each batch the run stops if
+    ``sat_total / total < min_sat_rate`` (``:261-263``); inside a batch it stops right after the sample that completes
+    ``still_needed`` (``:305-307``).  Returns ``(chains_consumed, sat_counted, stopped_on_rate)``: the histogram of the
+    launch is that of chains ``[0, chains_consumed)``."""
+    is_sat = np.asarray(is_sat) != 0
+    chains = is_sat.shape[0]
+    csum = np.concatenate([[0], np.cumsum(is_sat, dtype=np.int64)])
+    pos = 0
+    while pos < chains and still_needed > 0:
+        if total > 0 and sat_total / total < min_sat_rate:
+            return pos, int(csum[pos]), True
+        end = min(pos + batch, chains)
+        sat_here = int(csum[end] - csum[pos])
+        if sat_here >= still_needed:        # the sample that completes the request ends the run inside this batch
+            cut = int(np.searchsorted(csum, csum[pos] + still_needed, side="left"))     # first index with that many SAT
+            return cut, int(csum[cut]), False
+        total += end - pos
+        sat_total += sat_here
+        still_needed -= sat_here
+        pos = end
+    return pos, int(csum[pos]), False
 
 
 class DiffusionSampler:
+    """Drop-in for the reference class.  ``precision="fp32"`` (default) runs the Dense layers fp32-accurately on the
+    tensor cores; ``"bf16"`` is the faster, stated-separately path.
+
+    Reproducibility: noise is a counter-based Philox stream keyed by ``(seed, global chain id)``.  Every ``samples()``
+    call continues with fresh chains (the reference draws fresh TF randomness per call too); a new sampler with the same
+    ``seed`` and ``chain_offset`` replays the same chains, and ``reset_chains()`` rewinds this one."""
+
     def __init__(self, model_path, dimacs_filename, *, device: int = 0, precision: str = "fp32",
                  chains_per_launch: int | None = None, seed: int = 0, chain_offset: int = 0,
                  max_nodes_per_batch: int = MAX_NODES_PER_BATCH, verbose: bool = False, context=None):
@@ -149,65 +176,92 @@ class DiffusionSampler:
         self.chains_per_launch = chains_per_launch
         self.seed = int(seed)
         self.chain_offset = int(chain_offset)   # global id of this sampler's first chain (multi-GPU sharding)
+        self.min_sat_rate = 0.005               # reference :261-263; 0 disables the abort (throughput runs)
+        self._chains_consumed = 0               # chains launched by earlier samples() calls
         self.last_stats = {}
 
+    def reset_chains(self, chain_offset: int | None = None):
+        """Rewind the chain counter (and optionally move the block of global chain ids this sampler draws from)."""
+        self._chains_consumed = 0
+        if chain_offset is not None:
+            self.chain_offset = int(chain_offset)
+
     def _prepare_checkpoints(self, model_path):
+        """Reference ``:215-227``: restore the latest checkpoint, or print "Checkpoint not found!" and go on with
+        (seeded) random weights.  Only a missing path counts as "not found": a file that exists but cannot be parsed
+        raises, so a reader bug can never turn into silently random weights."""
+        import os
+        if model_path is None or not (os.path.exists(str(model_path)) or os.path.exists(str(model_path) + ".index")):
+            print("Checkpoint not found!")
+            return init_weights(seed=1234)
         try:
             weights = load_weights(model_path)
-            print(f"Model restored from {model_path}!")
-        except (FileNotFoundError, TypeError):
+        except FileNotFoundError:              # a directory without a `checkpoint` file / ckpt-N.index
             print("Checkpoint not found!")
-            weights = init_weights(seed=1234)
+            return init_weights(seed=1234)
+        print(f"Model restored from {model_path}!")
         return weights
 
-    def _launch_chains(self, still_needed: int) -> int:
+    def _launch_chains(self, still_needed: int, chains_left: int | None = None) -> int:
         """Chains per launch: whole reference batches, enough for the samples still needed, bounded."""
         b = self.batch_chains
         if self.chains_per_launch:
-            return max(b, (self.chains_per_launch // b) * b)
-        batches = max(1, -(-still_needed // b))
-        rows_cap = 600_000                                  # ~12 GB of fp32 activations per launch
-        cap = max(1, rows_cap // max(len(self.clauses), self.n_vars, 1) // b)
-        return b * min(batches, cap)
+            n = max(b, (self.chains_per_launch // b) * b)
+        else:
+            batches = max(1, -(-still_needed // b))
+            rows_cap = 900_000                              # variable/clause rows per launch (~20 GB of activations at n=100)
+            cap = max(1, rows_cap // max(len(self.clauses), self.n_vars, 1) // b)
+            n = b * min(batches, cap)
+        if chains_left is not None:
+            n = min(n, max(chains_left, 1))
+            if chains_left - n < b:             # a remainder smaller than one reference batch rides along as a last, partial group
+                n = max(chains_left, 1)
+        return n
 
-    def samples(self, n_samples):
+    def samples(self, n_samples, *, max_chains: int | None = None):
         """:param n_samples: how many correct samples to generate
+        :param max_chains: (extension) stop after this many chains even if fewer samples were found
         :return: the dict solution-as-int => count"""
-        diffusion_dict = {}
-        total = sat_total = 0
-        still_needed = int(n_samples)
+        from .dist import table_to_dict
+        keys, counts = self.samples_table(n_samples, max_chains=max_chains)
+        return table_to_dict(keys, counts, self.n_vars)
+
+    def samples_table(self, n_samples, *, max_chains: int | None = None):
+        """``samples()`` before the conversion to Python ints: ``(keys [K, words] uint64 ascending, counts [K] int64)``,
+        the form ``dist.merge_histograms`` exchanges between GPUs."""
+        from .dist import merge_tables
         max_lit = max((abs(l) for c in self.clauses for l in c), default=0)
-        launched = 0
+        if self.n_vars > max_lit:
+            # VariableAssignment(clauses=...) sizes its vector by the largest literal (utils/VariableAssignment.py:34-36);
+            # the reference then fails in assign_all_from_bit_list on the first sample -- raised here before any GPU work
+            raise IndexError("list assignment index out of range")
+        tables = []
+        total = sat_total = launched = 0
+        still_needed = int(n_samples)
+        words = -(-self.n_vars // 64)
         stop = False
-        while still_needed > 0 and not stop:
-            chains = self._launch_chains(still_needed)
+        while still_needed > 0 and not stop and (max_chains is None or launched < max_chains):
+            chains = self._launch_chains(still_needed, None if max_chains is None else max_chains - launched)
             if self.ctx.graph is not self.unit or self.ctx.chains != chains:
                 self.ctx.set_graph(self.unit, chains=chains, group_graphs=self.batch_chains)
                 self.model._graph_key = None
-            packed, is_sat, _, _ = self.ctx.sample(diffusion_steps, test_rounds, seed=self.seed,
-                                                   chain_offset=self.chain_offset + launched)
+            self.ctx.sample_enqueue(diffusion_steps, test_rounds, seed=self.seed,
+                                    chain_offset=self.chain_offset + self._chains_consumed + launched)
+            is_sat = self.ctx.sample_fetch_sat()
+            used, sat_used, stop = consume_batches(is_sat, self.batch_chains, still_needed, total, sat_total,
+                                                   self.min_sat_rate)
+            if stop:
+                print("too many unsat samples; stopping diffusion")
+            if sat_used:
+                keys, counts, n_sat = self.ctx.hist_reduce(used)        # sort / unique / count on the device
+                assert n_sat == sat_used
+                tables.append((keys, counts))
+            total += used
+            sat_total += sat_used
+            still_needed -= sat_used
             launched += chains
-            values = unpack_assignments(packed, self.n_vars)
-            for b0 in range(0, chains, self.batch_chains):            # one reference batch at a time (:243-307)
-                if still_needed == 0:
-                    break
-                if total > 0 and sat_total / total < 0.005:           # :261-263
-                    print("too many unsat samples; stopping diffusion")
-                    stop = True
-                    break
-                for i in range(b0, min(b0 + self.batch_chains, chains)):
-                    if self.n_vars > max_lit:
-                        # VariableAssignment(clauses=...) sizes its vector by the largest literal (:34-36);
-                        # the reference then fails in assign_all_from_bit_list
-                        raise IndexError("list assignment index out of range")
-                    total += 1
-                    if is_sat[i]:
-                        sat_total += 1
-                        key = values[i]
-                        diffusion_dict[key] = diffusion_dict.get(key, 0) + 1
-                        still_needed -= 1
-                        if still_needed == 0:
-                            break
-        self.last_stats = {"total": total, "sat": sat_total, "chains_launched": launched}
+        self._chains_consumed += launched
+        keys, counts = merge_tables(tables, words)
+        self.last_stats = {"total": total, "sat": sat_total, "chains_launched": launched, "distinct": int(len(counts))}
         print("success rate: ", sat_total / total if total else 0.0)
-        return diffusion_dict
+        return keys, counts

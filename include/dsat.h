@@ -11,6 +11,7 @@
  * leaves a message for dsat_last_error(); no exceptions cross the ABI; "host" buffers are caller
  * owned and copied, "dev" buffers are device pointers of the context's device; one context per GPU,
  * not thread-safe; all work is issued on the context's stream; there is no CPU fallback.
+ * Profiling, parity and debug hooks (not part of the product surface) live in dsat_debug.h.
  *
  * Row order of every per-variable array is the reference's batch order: variable v of graph g of
  * chain c sits at  c*n_vars + v  with n_vars the unit's variable total (data/dimac.py:239-241,
@@ -43,27 +44,6 @@ enum dsat_status {
  *   DSAT_BF16         plain bf16 operands and bf16 activation storage, one tcgen05 kernel per MLP (stated separately)
  *   DSAT_BF16_UNFUSED the same with one tcgen05 kernel per Dense layer */
 enum dsat_dtype { DSAT_F32 = 0, DSAT_BF16 = 1, DSAT_BF16_UNFUSED = 2, DSAT_F32_TC = 3 };
-
-/* debug/parity access to the activation buffers of one round (dsat_debug_read / dsat_debug_write) */
-enum dsat_buffer {
-    DSAT_BUF_VROW = 0,    /* [N, F+16+3Q]  variables | aux16 | variables_grad | loss_pos | loss_neg */
-    DSAT_BUF_CROW = 1,    /* [M, F+2Q]     clause_state | clause_messages | 4*clauses_loss          */
-    DSAT_BUF_H1 = 2,      /* [N, Hq+4Q]    hidden of variables_query | first hidden of lit_query     */
-    DSAT_BUF_H2 = 3,      /* [N, 4Q]       second hidden of lit_query                                 */
-    DSAT_BUF_QS = 4,      /* [N, 3Q]       query | softplus(query) | softplus(-query)                 */
-    DSAT_BUF_LIT = 5,     /* [N, 2Q]       lit_query output (positive | negative literal features)    */
-    DSAT_BUF_CH = 6,      /* [M, Hc]       hidden of clause_update                                    */
-    DSAT_BUF_COUT = 7,    /* [M, Q+F]      clause_update output (message to literals | new value)     */
-    DSAT_BUF_U1 = 8,      /* [N, Hu] */
-    DSAT_BUF_U2 = 9,      /* [N, Hu] */
-    DSAT_BUF_UOUT = 10,   /* [N, F]        update_gate output before PairNorm                          */
-    DSAT_BUF_SPRE = 11,   /* [N, F]        variables after PairNorm+residual, before the 0.2/0.8 carry  */
-    DSAT_BUF_O1 = 12,     /* [N, Ho] */
-    DSAT_BUF_LOGITS = 13, /* [N, 16]       8 logit maps + padding                                       */
-    DSAT_BUF_OUT = 14,    /* [N]           selected logit per variable (out_logits)                     */
-    DSAT_BUF_X = 15,      /* [N, 2]        diffusion state x                                            */
-    DSAT_BUF_COUNT = 16
-};
 
 int dsat_version(void);
 
@@ -137,34 +117,15 @@ int dsat_words_per_graph(const dsat_ctx* ctx);
  * (tf.sparse.sparse_dense_matmul call sites model/query_sat.py:255,269).  feat in {64,128,256}. */
 int dsat_spmm(dsat_ctx* ctx, int direction, const void* x_dev, void* y_dev, int feat, int dtype, int chains);
 
-/* Per-kernel-class device time of `rounds` message-passing rounds, measured with CUDA events on the
- * context's stream (bench.py roofline).  Classes 0..10 are the eleven linear ops in launch order
- * (v1->hidden, query out, lit 2, lit 3, clause 1, clause 2, update 1, 2, 3, output 1, 2), then
- * clause gather, literal gather, clause PairNorm, variable PairNorm, head, noise.
- * class_ms / class_launches have dsat_profile_classes() entries. */
-int dsat_profile_classes(void);
-/* clock64 wait/work breakdown of CTA 0 of one whole-MLP kernel (0 query .. 4 output); 16 counters */
-int dsat_profile_fused(dsat_ctx* ctx, int which, long long* counters16);
-int dsat_profile_rounds(dsat_ctx* ctx, int rounds, uint64_t seed, float* class_ms, int32_t* class_launches);
-
-/* Stand-alone run of the tcgen05 linear kernel on host data (parity of the tensor-core MLP path,
- * model/mlp.py:42-50): out = epi(bf16(a) @ bf16(w) + bias); a [rows,K], w [K,N], out [rows,N] fp32
- * ([rows,3N] for epi 2 = query epilogue with the softplus pair); epi 0 linear, 1 leaky-relu 0.2. */
-int dsat_tc_linear_test(dsat_ctx* ctx, int rows, int K, int N, const float* a_host, const float* w_host,
-                        const float* bias_host, int epi, int out_bf16, float* out_host);
-
-/* Parity hooks: run the pieces of one model call separately and read/write activation buffers. */
-int dsat_debug_begin(dsat_ctx* ctx, float noise_scale, const float* noisy_num, const int32_t* labels);
-int dsat_debug_round(dsat_ctx* ctx, int round, const float* normals /* [N,4] host */);
-int dsat_debug_dims(const dsat_ctx* ctx, int buffer, long long* rows, int* ld);
-int dsat_debug_read(dsat_ctx* ctx, int buffer, float* host_out, long long count);
-int dsat_debug_write(dsat_ctx* ctx, int buffer, const float* host_in, long long count);
-int dsat_debug_groups(dsat_ctx* ctx, int32_t* done, int32_t* steps_taken, float* loss_sum,
-                      int32_t* graph_sat, int32_t* graph_map);
-/* One MLP alone in the active precision on the current contents of its input buffer (model/query_sat.py:117-122):
- * which = 0 variables_query (VROW -> QS), 1 lit_query (VROW -> LIT), 2 clause_update (CROW -> COUT),
- * 3 update_gate (VROW -> UOUT), 4 variables_output (SPRE -> LOGITS). */
-int dsat_debug_mlp(dsat_ctx* ctx, int which);
+/* Histogram of the last dsat_sample / dsat_sample_enqueue run, reduced on the device: sort, unique and count of the
+ * packed SATISFYING assignments of chains [0, chain_limit) (chain_limit <= 0: all chains of the context).
+ * keys_out [capacity, words] (word 0 = variables 1..64, as in `packed`), ascending by the integer they encode;
+ * counts_out [capacity]; *n_unique = number of distinct assignments, *n_sat = satisfied chains counted (may be NULL).
+ * Returns DSAT_ERR_ARG with *n_unique set when capacity is too small.  Replaces the per-sample dict update of
+ * satuniformity/DiffusionSampler.py:283-307 (int encoding utils/VariableAssignment.py:63-69); the cross-GPU merge of
+ * these tables is diffusionsat_b200/dist.py (NCCL all-gather of keys + reduce of counts). */
+int dsat_hist_reduce(dsat_ctx* ctx, int chain_limit, uint64_t* keys_out, int64_t* counts_out, int capacity,
+                     int32_t* n_unique, int32_t* n_sat);
 
 #ifdef __cplusplus
 }

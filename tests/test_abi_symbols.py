@@ -9,10 +9,19 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "dsat.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(dsat_[a-z_0-9]+)\s*\(", text)))
+def _declared_symbols(headers=("dsat.h", "dsat_debug.h")):
+    found = set()
+    for h in headers:
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        found |= set(re.findall(r"\b(dsat_[a-z_0-9]+)\s*\(", text))
+    return sorted(found)
+
+
+def test_product_header_holds_no_debug_hooks():
+    product = _declared_symbols(("dsat.h",))
+    assert not [s for s in product if "debug" in s or "profile" in s or s.endswith("_test")]
+    assert "dsat_hist_reduce" in product and "dsat_sample" in product
 
 
 def test_library_exports_every_declared_symbol(dsat_lib):

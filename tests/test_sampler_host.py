@@ -1,0 +1,73 @@
+"""Host-side logic of the sampler that needs no GPU: the reference's stop rules applied to a launch's SAT flags
+(satuniformity/DiffusionSampler.py:243-307), histogram table merging, key -> int conversion, checkpoint lookup."""
+import numpy as np
+import pytest
+
+from diffusionsat_b200 import dist as D
+from diffusionsat_b200.sampler import DiffusionSampler, consume_batches
+
+
+def _reference_loop(is_sat, batch, need, total, sat_total, rate=0.005):
+    """The per-sample loop of the reference, one reference batch at a time."""
+    used = sat = 0
+    for b0 in range(0, len(is_sat), batch):
+        if need == 0:
+            break
+        if total > 0 and sat_total / total < rate:          # :261-263
+            return used, sat, True
+        for i in range(b0, min(b0 + batch, len(is_sat))):
+            total += 1
+            used = i + 1
+            if is_sat[i]:                                   # :297-303
+                sat_total += 1
+                sat += 1
+                need -= 1
+                if need == 0:                               # :305-307
+                    break
+    return used, sat, False
+
+
+def test_consume_batches_equals_the_reference_loop():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        n, b = int(rng.integers(1, 60)), int(rng.integers(1, 12))
+        flags = (rng.random(n) < rng.choice([0.0, 0.003, 0.3, 0.9])).astype(np.uint8)
+        need, tot = int(rng.integers(1, 40)), int(rng.integers(0, 300))
+        st = int(rng.integers(0, tot + 1)) if tot and rng.random() < 0.5 else 0
+        assert consume_batches(flags, b, need, tot, st) == _reference_loop(flags, b, need, tot, st)
+
+
+def test_merge_tables_and_key_conversion():
+    rng = np.random.default_rng(1)
+    words, n_bits = 2, 100
+    pool = rng.integers(0, 2**63, size=(9, words), dtype=np.uint64)
+    pool[:, 1] &= np.uint64((1 << (n_bits - 64)) - 1)
+    want = {}
+    tables = []
+    for _ in range(4):
+        pick = rng.integers(0, len(pool), 30)
+        packed = pool[pick]
+        sat = (rng.random(30) < 0.7).astype(np.uint8)
+        tables.append(D.local_histogram(packed, sat))
+        for row, s in zip(packed, sat):
+            if s:
+                k = int(row[0]) | (int(row[1]) << 64)
+                want[k] = want.get(k, 0) + 1
+    keys, counts = D.merge_tables(tables, words)
+    ints = D.keys_to_ints(keys, n_bits)
+    assert ints == sorted(ints)                             # ascending by the encoded integer
+    assert dict(zip(ints, counts.tolist())) == want
+    assert D.table_to_dict(keys, counts, n_bits) == want
+    k0, c0 = D.merge_tables([], words)
+    assert k0.shape == (0, words) and c0.shape == (0,)
+
+
+def test_missing_checkpoint_is_random_init_but_a_broken_one_raises(tmp_path, capsys):
+    s = DiffusionSampler.__new__(DiffusionSampler)
+    w = s._prepare_checkpoints(str(tmp_path / "nothing_here"))
+    assert "Checkpoint not found!" in capsys.readouterr().out
+    assert w.feature_maps == 128
+    bad = tmp_path / "weights.npz"
+    bad.write_bytes(b"not a zip archive")
+    with pytest.raises(Exception):
+        s._prepare_checkpoints(str(bad))
