@@ -263,7 +263,11 @@ def parity_check(ctx, precision, unit, n, clauses, batch, chains, wts, chain_off
             "logit_map_agree": float(same.mean()), "max_abs_err_over_rms": float(err.max() / rms) if err.size else None,
             "tolerance": "%g |z| + %g rms(z) per element" % (tol, tol), "elements_inside": float(inside.mean()) if err.size else None,
             "decisions_equal": float(((got > 0) == (want > 0))[same].mean()) if err.size else None,
-            "steps_taken_equal": bool(steps[g] == out[1]), "ok": bool(err.size and inside.all() and steps[g] == out[1])}
+            "steps_taken_equal": bool(steps[g] == out[1]),
+            # fp32: every element inside; bf16 (stated separately): 99 % of the elements inside and 97 % of the decisions equal
+            "ok": bool(err.size and steps[g] == out[1] and
+                       (inside.all() if precision == "fp32" else
+                        inside.mean() >= 0.99 and ((got > 0) == (want > 0))[same].mean() >= 0.97))}
 
 
 def measure_precision(ctx, precision, args, world, rank, local_rank, unit, batch, chains, chain_offset, barrier, dist, torch, pk):

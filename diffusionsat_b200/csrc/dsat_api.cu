@@ -95,6 +95,7 @@ struct dsat_ctx {
     bool has_graph = false;
     int n = 0, m = 0, nnz = 0, n_graphs = 0, chains = 0, group_graphs = 0, n_groups = 0, total_graphs = 0;
     int words = 0;
+    int max_graph_vars = 0, max_graph_clauses = 0;      // largest formula of the unit (shared-memory PairNorm)
     long long Nt = 0, Mt = 0;
     DevBuf<int> cl_rowptr, cl_lit, lit_rowptr, lit_clause, var_seg, clause_seg;
     DevBuf<float> deg_w, vdeg_w, rev_w;
@@ -242,7 +243,7 @@ int ensure_buffers(dsat_ctx* c) {
 }
 
 #ifdef DSAT_WITH_TCGEN05
-static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int budget_kb);
+static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int budget_kb, int elt_bytes = 2);
 
 __global__ void mirror_cols_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
                                    long long rows, int cols) {
@@ -694,7 +695,7 @@ int run_fused(dsat_ctx* c, int which, int prof_class) {
 #ifdef DSAT_WITH_TCGEN05
 // Shared-memory staged gathers (small formulas): pick the widest feature slice whose two tables fit;
 // returns false when they do not fit (the L2-gather kernels run instead).
-static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int budget_kb) {
+static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int budget_kb, int elt_bytes) {
     // budget_kb: shared memory per CTA we aim for (smaller slices -> more co-resident CTAs, so one CTA's staging
     // overlaps the others' compute); DSAT_GATHER_KB overrides it for experiments
     static const int env_kb = getenv("DSAT_GATHER_KB") ? atoi(getenv("DSAT_GATHER_KB")) : 0;
@@ -703,7 +704,7 @@ static int pick_slice_width(size_t table_rows, int Q, size_t* bytes_out, int bud
     for (int pass = 0; pass < 2; ++pass)
         for (int w : widths) {
             if (w > Q || Q % w) continue;
-            const size_t bytes = 2 * table_rows * (size_t)w * 2;
+            const size_t bytes = 2 * table_rows * (size_t)w * (size_t)elt_bytes;
             if (bytes <= (size_t)(pass == 0 ? budget_kb : 220) * 1024u) { *bytes_out = bytes; return w; }
         }
     return 0;
@@ -755,6 +756,86 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     if (w == 128) return si ? launch(literal_gather_smem_kernel<128, true>) : launch(literal_gather_smem_kernel<128, false>);
     if (w == 64) return si ? launch(literal_gather_smem_kernel<64, true>) : launch(literal_gather_smem_kernel<64, false>);
     return si ? launch(literal_gather_smem_kernel<32, true>) : launch(literal_gather_smem_kernel<32, false>);
+}
+#endif
+
+#ifdef DSAT_WITH_TCGEN05
+// fp32 tables (fp32-accurate tensor-core path): outputs go to the hi/lo planes
+bool launch_clause_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
+    if (c->n_graphs != 1 || !c->use_smem_gather) return false;
+    // DSAT_GATHER_F32_CL1=1: one table per CTA at twice the slice width (the literal side's default) instead of both tables
+    static const bool one_table = getenv("DSAT_GATHER_F32_CL1") && atoi(getenv("DSAT_GATHER_F32_CL1")) != 0;
+    size_t bytes = 0;
+    static const int budget = getenv("DSAT_GATHER_F32_KB_CL") ? atoi(getenv("DSAT_GATHER_F32_KB_CL")) : 110;
+    const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes, budget, one_table ? 2 : 4);
+    if (!w) return false;
+    dim3 grid((unsigned)c->chains, (unsigned)((one_table ? 2 : 1) * (c->Q / w)));
+    const int Q = c->Q;
+    const bool si = c->use_idx16 && idx_fits(bytes, g.cl_idx16_vecs);
+    const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
+    const size_t cplane = (size_t)c->Mt * c->ldc();
+    auto launch = [&](auto kernel) -> bool {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROWp.p, cplane, c->ldc(), c->F);
+        return true;
+    };
+    if (one_table) {
+        if (w == 128) return si ? launch(clause_gather_smem_f32_kernel<128, true>) : launch(clause_gather_smem_f32_kernel<128, false>);
+        if (w == 64) return si ? launch(clause_gather_smem_f32_kernel<64, true>) : launch(clause_gather_smem_f32_kernel<64, false>);
+        return si ? launch(clause_gather_smem_f32_kernel<32, true>) : launch(clause_gather_smem_f32_kernel<32, false>);
+    }
+    if (w == 128) return si ? launch(clause_gather_smem_f32x2_kernel<128, true>) : launch(clause_gather_smem_f32x2_kernel<128, false>);
+    if (w == 64) return si ? launch(clause_gather_smem_f32x2_kernel<64, true>) : launch(clause_gather_smem_f32x2_kernel<64, false>);
+    return si ? launch(clause_gather_smem_f32x2_kernel<32, true>) : launch(clause_gather_smem_f32x2_kernel<32, false>);
+}
+
+bool launch_literal_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
+    if (c->n_graphs != 1 || !c->use_smem_gather) return false;
+    size_t bytes = 0;
+    static const int budget = getenv("DSAT_GATHER_F32_KB_LIT") ? atoi(getenv("DSAT_GATHER_F32_KB_LIT")) : 112;
+    const int w = pick_slice_width((size_t)c->m, c->Q, &bytes, budget, 2);          // one fp32 table per CTA
+    if (!w) return false;
+    dim3 grid((unsigned)c->chains, (unsigned)(2 * (c->Q / w)));
+    const int Q = c->Q, F = c->F;
+    const bool si = c->use_idx16 && idx_fits(bytes, g.lit_idx16_vecs);
+    const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
+    const size_t cplane = (size_t)c->Mt * c->ldc(), vplane = (size_t)c->Nt * c->ldv();
+    auto launch = [&](auto kernel) -> bool {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWp.p, cplane, c->ldc(), F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q,
+                                                c->VROWp.p, vplane, c->ldv(), F + DSAT_AUX_PAD);
+        return true;
+    };
+    if (w == 128) return si ? launch(literal_gather_smem_f32_kernel<128, true>) : launch(literal_gather_smem_f32_kernel<128, false>);
+    if (w == 64) return si ? launch(literal_gather_smem_f32_kernel<64, true>) : launch(literal_gather_smem_f32_kernel<64, false>);
+    return si ? launch(literal_gather_smem_f32_kernel<32, true>) : launch(literal_gather_smem_f32_kernel<32, false>);
+}
+#endif
+
+#ifdef DSAT_WITH_TCGEN05
+// PairNorm with the graph resident in shared memory (split-plane path); false when a graph does not fit
+template <int V>
+bool launch_pairnorm_smem(dsat_ctx* c, const int* seg, int rows_per_chain, int max_graph_rows, const float* src, int ld_src, int src_off,
+                          __nv_bfloat16* state_hi, size_t state_plane, int ld_state, __nv_bfloat16* pre_hi, size_t pre_plane, int ld_pre) {
+    static const bool off = getenv("DSAT_PN_SMEM") && atoi(getenv("DSAT_PN_SMEM")) == 0;
+    if (off) return false;
+    constexpr int F = 32 * V;
+    // small graphs: several CTAs of 256 threads per SM; large ones: one CTA of 1024 threads
+    const size_t row_bytes = (size_t)max_graph_rows * F * 4;
+    const int threads = row_bytes > 100 * 1024 ? 1024 : row_bytes > 48 * 1024 ? 512 : 256;
+    const int groups = threads / F > 0 ? threads / F : 1;
+    const size_t smem = (size_t)(F + groups * F) * 4 + row_bytes;
+    if (smem > 227 * 1024) return false;
+    if (cudaFuncSetAttribute(pairnorm_smem_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
+    int per_sm = (int)((228 * 1024) / (smem + 1024));
+    const int by_threads = 2048 / threads;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm < 1) per_sm = 1;
+    int grid = c->sm_count * per_sm;
+    if (grid > c->total_graphs) grid = c->total_graphs;
+    pairnorm_smem_kernel<V><<<grid, threads, smem, c->stream>>>(seg, c->n_graphs, rows_per_chain, c->total_graphs, src, ld_src, src_off,
+                                                                state_hi, state_plane, ld_state, pre_hi, pre_plane, ld_pre);
+    return true;
 }
 #endif
 
@@ -812,10 +893,13 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         const int grid = tcp ? gather_grid(clause_gather_kernel<V, __nv_bfloat16>, Mt, GATHER_WARPS, c->sm_count)
                              : gather_grid(clause_gather_kernel<V, float>, Mt, GATHER_WARPS, c->sm_count);
-        if (x3p)
+        if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+            if (!launch_clause_gather_smem_f32(c, g))
+#endif
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, nullptr, ldc, F, crow_b(c), cplane);
-        else if (!tcp)
+        } else if (!tcp)
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
 #ifdef DSAT_WITH_TCGEN05
@@ -852,11 +936,14 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         constexpr int V = decltype(v)::value;
         const int grid = tcp ? gather_grid(literal_gather_kernel<V, __nv_bfloat16>, Nt, GATHER_WARPS, c->sm_count)
                              : gather_grid(literal_gather_kernel<V, float>, Nt, GATHER_WARPS, c->sm_count);
-        if (x3p)    // 4*clauses_loss is read back as hi + lo from the clause rows' planes
+        if (x3p) {  // 4*clauses_loss is read back as hi + lo from the clause rows' planes
+#ifdef DSAT_WITH_TCGEN05
+            if (!launch_literal_gather_smem_f32(c, g))
+#endif
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, nullptr, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, nullptr, ldv, F + DSAT_AUX_PAD,
                 vrow_b(c), vplane, crow_b(c), cplane);
-        else if (!tcp)
+        } else if (!tcp)
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
 #ifdef DSAT_WITH_TCGEN05
@@ -872,11 +959,24 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     rc = dispatch_width(c, F, [&](auto v) {
         constexpr int V = decltype(v)::value;
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
-        if (x3p)
+        {   // both passes of a CTA should find their graph in L2: cap the graphs in flight at about half of L2
+            static const int l2_mb = getenv("DSAT_PN_L2_MB") ? atoi(getenv("DSAT_PN_L2_MB")) : 0;
+            if (l2_mb > 0) {
+                const double per_graph = (double)c->m / c->n_graphs * F * (tcp ? 2 : 4);
+                int cap = (int)(l2_mb * 1048576.0 / (per_graph > 1 ? per_graph : 1));
+                cap = cap < c->sm_count ? c->sm_count : cap;
+                if (grid > cap) grid = cap;
+            }
+        }
+        if (x3p) {
+#ifdef DSAT_WITH_TCGEN05
+            if (!launch_pairnorm_smem<V>(c, c->clause_seg.p, c->m, c->max_graph_clauses, c->COUT.p, Q + F, Q, crow_b(c), cplane, ldc,
+                                         nullptr, 0, 0))
+#endif
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, nullptr, ldc, nullptr, 0,
                 crow_b(c), cplane, nullptr, 0);
-        else if (!tcp)
+        } else if (!tcp)
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
 #ifdef DSAT_WITH_TCGEN05
@@ -915,6 +1015,8 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         int grid = c->total_graphs < c->sm_count * 8 ? c->total_graphs : c->sm_count * 8;
         if (x3p) {
 #ifdef DSAT_WITH_TCGEN05
+            if (!launch_pairnorm_smem<V>(c, c->var_seg.p, c->n, c->max_graph_vars, c->UOUT.p, F, 0, vrow_b(c), vplane, ldv,
+                                         c->SPREp.p, (size_t)Nt * F, F))
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, nullptr, ldv, nullptr, F,
                 vrow_b(c), vplane, c->SPREp.p, (size_t)Nt * F);
@@ -1201,10 +1303,11 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
         for (int l = 0; l < 2 * n_vars; ++l)
             CK_ARG(c, deg[l] == lit_rowptr[l + 1] - lit_rowptr[l], "dsat_set_graph: CSR and CSC disagree on a literal's degree");
     }
-    int max_graph_vars = 0;
+    int max_graph_vars = 0, max_graph_clauses = 0;
     for (int g = 0; g < n_graphs; ++g) {
         CK_ARG(c, var_seg[g + 1] > var_seg[g] && clause_seg[g + 1] >= clause_seg[g], "dsat_set_graph: empty or unordered graph segment");
         if (var_seg[g + 1] - var_seg[g] > max_graph_vars) max_graph_vars = var_seg[g + 1] - var_seg[g];
+        if (clause_seg[g + 1] - clause_seg[g] > max_graph_clauses) max_graph_clauses = clause_seg[g + 1] - clause_seg[g];
     }
     CK_ARG(c, (long long)n_chains * n_vars < (1ll << 31) - 256 && (long long)n_chains * n_clauses < (1ll << 31) - 256,
            "dsat_set_graph: too many rows for one context; use fewer chains per context");
@@ -1226,6 +1329,7 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     c->Nt = (long long)n_chains * n_vars;
     c->Mt = (long long)n_chains * n_clauses;
     c->words = ceil_div(max_graph_vars, 64);
+    c->max_graph_vars = max_graph_vars; c->max_graph_clauses = max_graph_clauses;
 
     std::vector<float> deg_w(2 * n_vars), vdeg_w(n_vars), rev_w(n_clauses > 0 ? n_clauses : 1);
     for (int l = 0; l < 2 * n_vars; ++l) {

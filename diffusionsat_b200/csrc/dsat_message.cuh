@@ -515,4 +515,275 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
 #endif
 }
 
+// ------------------------------------------------------------------ fp32 tables (fp32-accurate tensor-core path)
+// The same shared-memory design with fp32 tables: the gathered operands of that path are the fp32 outputs of the x3 MLP
+// kernels (LIT, softplus pair, clause messages) and the 4*clauses_loss columns of the clause rows' hi/lo planes; the
+// outputs go straight into the hi/lo planes the next MLP reads as its A operand.  A lane owns 4 features (16 bytes);
+// sums run in edge order from zero, so they are bit-identical to clause_gather_kernel / literal_gather_kernel.
+struct Acc4 { float v[4]; };
+__device__ __forceinline__ void acc4_add(Acc4& a, const float4& w) { a.v[0] += w.x; a.v[1] += w.y; a.v[2] += w.z; a.v[3] += w.w; }
+__device__ __forceinline__ void store_split4(__nv_bfloat16* dst_hi, size_t plane, int li, const float (&f)[4]) {
+    uint2 hi, lo;
+    split_bf16x2(f[0], f[1], hi.x, lo.x);
+    split_bf16x2(f[2], f[3], hi.y, lo.y);
+    reinterpret_cast<uint2*>(dst_hi)[li] = hi;
+    reinterpret_cast<uint2*>(dst_hi + plane)[li] = lo;
+}
+
+// One table per CTA: blockIdx.y = slice * 2 + role.  The two sums of a side are independent, so a CTA stages only ONE of
+// the two tables and can afford a slice twice as wide: the adjacency walk (index loads, address arithmetic) is amortised
+// over twice the features -- these kernels are issue-bound, not bandwidth-bound -- and the rows it fetches are twice as
+// long (512-byte segments on the clause side).
+//   clause side  role 0: table LIT -> clause_messages            role 1: table softplus pair -> 4*clauses_loss
+//   literal side role 0: table 4*clauses_loss -> variables_grad   role 1: table messages -> loss_pos | loss_neg
+template <int W, bool SI>
+__global__ void __launch_bounds__(512, 2)
+clause_gather_smem_f32_kernel(UnitGraphDev g, int Q,
+                              const float* __restrict__ LIT, int ld_lit,
+                              const float* __restrict__ SP, int ld_sp, int sp_off,
+                              __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off) {
+    constexpr int LPR = W / 4, RPW = 32 / LPR;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    float* tab = reinterpret_cast<float*>(gsm);
+    const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(tab + (size_t)2 * g.n * W);
+    const int chain = blockIdx.x, slice = blockIdx.y >> 1, role = blockIdx.y & 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
+    const size_t vbase = (size_t)chain * g.n;
+    {
+        const float* src = role ? SP + sp_off : LIT;
+        const int ld = role ? ld_sp : ld_lit;
+        const int total = 2 * g.n * LPR;                    // (variable, sign, 16-byte piece)
+        for (int i = tid; i < total; i += blockDim.x) {
+            const int code = i / LPR, k = i % LPR, v = code >> 1, sgn = code & 1;
+            cp_async16(reinterpret_cast<uint4*>(tab + (size_t)code * W) + k,
+                       reinterpret_cast<const uint4*>(src + (vbase + v) * ld + sgn * Q + slice * W) + k);
+        }
+    }
+    if constexpr (SI) {
+        uint4* d = reinterpret_cast<uint4*>(const_cast<unsigned short*>(s_idx));
+        for (int i = tid; i < g.cl_idx16_vecs; i += blockDim.x) d[i] = __ldg(reinterpret_cast<const uint4*>(g.cl_idx16) + i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int j0 = warp * RPW; j0 < g.m; j0 += nwarps * RPW) {
+        const int j = j0 + sub;
+        const bool live = j < g.m;
+        int e0 = 0, e1 = 0;
+        if (live) {
+            if constexpr (SI) { e0 = s_idx[j]; e1 = s_idx[j + 1]; }
+            else { e0 = __ldg(g.cl_rowptr + j); e1 = __ldg(g.cl_rowptr + j + 1); }
+        }
+        Acc4 acc = {{0.f, 0.f, 0.f, 0.f}};
+        int e = e0;
+        for (; e + 3 <= e1; e += 3) {
+            const int c0 = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
+            const int c1 = SI ? (int)s_idx[g.cl_col_off + e + 1] : __ldg(g.cl_lit + e + 1);
+            const int c2 = SI ? (int)s_idx[g.cl_col_off + e + 2] : __ldg(g.cl_lit + e + 2);
+            const float4 l0 = reinterpret_cast<const float4*>(tab + (size_t)c0 * W)[li];
+            const float4 l1 = reinterpret_cast<const float4*>(tab + (size_t)c1 * W)[li];
+            const float4 l2 = reinterpret_cast<const float4*>(tab + (size_t)c2 * W)[li];
+            acc4_add(acc, l0); acc4_add(acc, l1); acc4_add(acc, l2);
+        }
+        for (; e < e1; ++e) {
+            const int code = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
+            acc4_add(acc, reinterpret_cast<const float4*>(tab + (size_t)code * W)[li]);
+        }
+        if (live) {
+            float o[4];
+            if (role) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = 4.0f * expf(-acc.v[i]);
+            } else {
+                const float rw = __ldg(g.rev_w + j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = acc.v[i] * rw;
+            }
+            store_split4(OUT_HI + ((size_t)chain * g.m + j) * ld_out + out_off + role * Q + slice * W, out_plane, li, o);
+        }
+    }
+}
+
+template <int W, bool SI>
+__global__ void __launch_bounds__(512, 2)
+literal_gather_smem_f32_kernel(UnitGraphDev g, int Q,
+                               const __nv_bfloat16* __restrict__ CL4_HI, size_t cl_plane, int ld_cl, int cl_off,
+                               const float* __restrict__ MSG, int ld_msg,
+                               const float* __restrict__ QRY, int ld_q,
+                               __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off) {
+    constexpr int LPR = W / 4, RPW = 32 / LPR;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    float* tab = reinterpret_cast<float*>(gsm);
+    const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(tab + (size_t)g.m * W);
+    const int chain = blockIdx.x, slice = blockIdx.y >> 1, role = blockIdx.y & 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
+    const size_t cbase = (size_t)chain * g.m;
+    if (role) {
+        stage_rows_async<float>(tab, MSG + cbase * ld_msg + slice * W, g.m, ld_msg, W, tid, blockDim.x);
+    } else {   // 4*clauses_loss = hi + lo, widened while staging (8 features per piece; four pieces in flight per thread)
+        constexpr int PPR = W / 8;
+        const int total = g.m * PPR;
+        const __nv_bfloat16* src = CL4_HI + cbase * ld_cl + cl_off + slice * W;
+        for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
+            uint4 hi[4], lo[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    const __nv_bfloat16* p = src + (size_t)(i / PPR) * ld_cl + (i % PPR) * 8;
+                    hi[u] = ldg_stream(reinterpret_cast<const uint4*>(p));
+                    lo[u] = ldg_stream(reinterpret_cast<const uint4*>(p + cl_plane));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < total) {
+                    float a[8], b[8];
+                    unpack8(hi[u], a); unpack8(lo[u], b);
+                    float4* d = reinterpret_cast<float4*>(tab + (size_t)(i / PPR) * W + (i % PPR) * 8);
+                    d[0] = make_float4(a[0] + b[0], a[1] + b[1], a[2] + b[2], a[3] + b[3]);
+                    d[1] = make_float4(a[4] + b[4], a[5] + b[5], a[6] + b[6], a[7] + b[7]);
+                }
+            }
+        }
+    }
+    if constexpr (SI) {
+        uint4* d = reinterpret_cast<uint4*>(const_cast<unsigned short*>(s_idx));
+        for (int i = tid; i < g.lit_idx16_vecs; i += blockDim.x) d[i] = __ldg(reinterpret_cast<const uint4*>(g.lit_idx16) + i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int v0 = warp * RPW; v0 < g.n; v0 += nwarps * RPW) {
+        const bool live = v0 + sub < g.n;
+        int v = 0;
+        if (live) v = SI ? (int)s_idx[g.lit_ord_off + v0 + sub] : __ldg(g.var_order + v0 + sub);
+        const size_t row = (size_t)chain * g.n + v;
+        __nv_bfloat16* dst = OUT_HI + row * ld_out + out_off + slice * W;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        float vw = 0.f, dw[2] = {0.f, 0.f};
+        if (live) {
+            if (role) { dw[0] = __ldg(g.deg_w + 2 * v); dw[1] = __ldg(g.deg_w + 2 * v + 1); }
+            else { q = __ldg(reinterpret_cast<const float4*>(QRY + row * ld_q + slice * W) + li); vw = __ldg(g.vdeg_w + v); }
+        }
+        Acc4 sum[2];
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            Acc4 acc = {{0.f, 0.f, 0.f, 0.f}};
+            const int code = 2 * v + sgn;
+            int e0 = 0, e1 = 0;
+            if (live) {
+                if constexpr (SI) { e0 = s_idx[code]; e1 = s_idx[code + 1]; }
+                else { e0 = __ldg(g.lit_rowptr + code); e1 = __ldg(g.lit_rowptr + code + 1); }
+            }
+            auto col = [&](int e) { return SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e); };
+            int e = e0;
+            for (; e + 4 <= e1; e += 4) {
+                const int j0 = col(e), j1 = col(e + 1), j2 = col(e + 2), j3 = col(e + 3);
+                const float4 a0 = reinterpret_cast<const float4*>(tab + (size_t)j0 * W)[li];
+                const float4 a1 = reinterpret_cast<const float4*>(tab + (size_t)j1 * W)[li];
+                const float4 a2 = reinterpret_cast<const float4*>(tab + (size_t)j2 * W)[li];
+                const float4 a3 = reinterpret_cast<const float4*>(tab + (size_t)j3 * W)[li];
+                acc4_add(acc, a0); acc4_add(acc, a1); acc4_add(acc, a2); acc4_add(acc, a3);
+            }
+            for (; e < e1; ++e) acc4_add(acc, reinterpret_cast<const float4*>(tab + (size_t)col(e) * W)[li]);
+            sum[sgn] = acc;
+        }
+        if (!live) continue;
+        if (role) {
+#pragma unroll
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = sum[sgn].v[i] * dw[sgn];
+                store_split4(dst + (1 + sgn) * Q, out_plane, li, o);
+            }
+        } else {
+            const float qv[4] = {q.x, q.y, q.z, q.w};
+            float grad[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float sg = sigmoid_f(qv[i]), sgn_ = sigmoid_f(-qv[i]);
+                grad[i] = (-sg * sum[0].v[i] + sgn_ * sum[1].v[i]) * vw;
+            }
+            store_split4(dst, out_plane, li, grad);
+        }
+    }
+}
+
+// clause side, both tables in one CTA (slice W): measured faster than one table per CTA at cfg2 (0.52 vs 0.61 ms per round):
+// with a row per warp pass the single-table walk is latency-bound on its index -> table-row chain
+template <int W, bool SI>
+__global__ void __launch_bounds__(512, 3)
+clause_gather_smem_f32x2_kernel(UnitGraphDev g, int Q,
+                                const float* __restrict__ LIT, int ld_lit,
+                                const float* __restrict__ SP, int ld_sp, int sp_off,
+                                __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off) {
+    constexpr int LPR = W / 4, RPW = 32 / LPR;
+    extern __shared__ __align__(16) uint8_t gsm[];
+    float* t_lit = reinterpret_cast<float*>(gsm);
+    float* t_sp = t_lit + (size_t)2 * g.n * W;
+    const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(t_sp + (size_t)2 * g.n * W);
+    const int chain = blockIdx.x, slice = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
+    const size_t vbase = (size_t)chain * g.n;
+    {
+        const int total = 2 * g.n * LPR;                    // (variable, sign, 16-byte piece)
+        for (int i = tid; i < total; i += blockDim.x) {
+            const int code = i / LPR, k = i % LPR, v = code >> 1, sgn = code & 1;
+            cp_async16(reinterpret_cast<uint4*>(t_lit + (size_t)code * W) + k,
+                       reinterpret_cast<const uint4*>(LIT + (vbase + v) * ld_lit + sgn * Q + slice * W) + k);
+            cp_async16(reinterpret_cast<uint4*>(t_sp + (size_t)code * W) + k,
+                       reinterpret_cast<const uint4*>(SP + (vbase + v) * ld_sp + sp_off + sgn * Q + slice * W) + k);
+        }
+    }
+    if constexpr (SI) {
+        uint4* d = reinterpret_cast<uint4*>(const_cast<unsigned short*>(s_idx));
+        for (int i = tid; i < g.cl_idx16_vecs; i += blockDim.x) d[i] = __ldg(reinterpret_cast<const uint4*>(g.cl_idx16) + i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int j0 = warp * RPW; j0 < g.m; j0 += nwarps * RPW) {
+        const int j = j0 + sub;
+        const bool live = j < g.m;
+        int e0 = 0, e1 = 0;
+        if (live) {
+            if constexpr (SI) { e0 = s_idx[j]; e1 = s_idx[j + 1]; }
+            else { e0 = __ldg(g.cl_rowptr + j); e1 = __ldg(g.cl_rowptr + j + 1); }
+        }
+        Acc4 al = {{0.f, 0.f, 0.f, 0.f}}, as = {{0.f, 0.f, 0.f, 0.f}};
+        int e = e0;
+        for (; e + 3 <= e1; e += 3) {
+            const int c0 = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
+            const int c1 = SI ? (int)s_idx[g.cl_col_off + e + 1] : __ldg(g.cl_lit + e + 1);
+            const int c2 = SI ? (int)s_idx[g.cl_col_off + e + 2] : __ldg(g.cl_lit + e + 2);
+            const float4 l0 = reinterpret_cast<const float4*>(t_lit + (size_t)c0 * W)[li];
+            const float4 p0 = reinterpret_cast<const float4*>(t_sp + (size_t)c0 * W)[li];
+            const float4 l1 = reinterpret_cast<const float4*>(t_lit + (size_t)c1 * W)[li];
+            const float4 p1 = reinterpret_cast<const float4*>(t_sp + (size_t)c1 * W)[li];
+            const float4 l2 = reinterpret_cast<const float4*>(t_lit + (size_t)c2 * W)[li];
+            const float4 p2 = reinterpret_cast<const float4*>(t_sp + (size_t)c2 * W)[li];
+            acc4_add(al, l0); acc4_add(as, p0);
+            acc4_add(al, l1); acc4_add(as, p1);
+            acc4_add(al, l2); acc4_add(as, p2);
+        }
+        for (; e < e1; ++e) {
+            const int code = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
+            acc4_add(al, reinterpret_cast<const float4*>(t_lit + (size_t)code * W)[li]);
+            acc4_add(as, reinterpret_cast<const float4*>(t_sp + (size_t)code * W)[li]);
+        }
+        if (live) {
+            const float rw = __ldg(g.rev_w + j);
+            float ol[4], os[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ol[i] = al.v[i] * rw; os[i] = 4.0f * expf(-as.v[i]); }
+            __nv_bfloat16* dst = OUT_HI + ((size_t)chain * g.m + j) * ld_out + out_off + slice * W;
+            store_split4(dst, out_plane, li, ol);
+            store_split4(dst + Q, out_plane, li, os);
+        }
+    }
+}
+
 }  // namespace dsat

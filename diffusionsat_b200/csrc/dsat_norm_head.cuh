@@ -126,6 +126,82 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
     }
 }
 
+// The same operation for graphs whose rows fit in shared memory (fp32-accurate tensor-core path: fp32 input, hi/lo-plane
+// state).  pairnorm_kernel reads its input twice and relies on L2 for the second pass, with only a few 512-byte rows in
+// flight per warp; here a CTA pulls the whole graph in with asynchronous copies (every byte of the graph in flight at
+// once, each read from HBM exactly once), takes the column means out of shared memory, and the second pass needs global
+// memory only for the old state and the stores.  blockDim.x = any multiple of 32 up to 1024.
+template <int V>
+__global__ void __launch_bounds__(1024)
+pairnorm_smem_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
+                     const float* __restrict__ SRC, int ld_src, int src_off,
+                     __nv_bfloat16* STATE_HI, size_t state_plane, int ld_state,
+                     __nv_bfloat16* __restrict__ PRE_HI, size_t pre_plane, int ld_pre) {
+    constexpr int F = 32 * V;
+    constexpr int PPR = F / 4;                         // 16-byte pieces per row
+    extern __shared__ __align__(16) uint8_t pn_smem[];
+    float* mean_s = reinterpret_cast<float*>(pn_smem);             // [F]
+    float* part = mean_s + F;                                       // [groups][F]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int groups = blockDim.x / F > 0 ? blockDim.x / F : 1;     // thread groups that sum interleaved rows of one column
+    float* rows = part + groups * F;                                // [graph rows][F]
+    for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
+        const int chain = gid / n_graphs_unit, lg = gid % n_graphs_unit;
+        const size_t base = (size_t)chain * rows_per_chain;
+        const size_t r0 = base + __ldg(seg + lg);
+        const int nrows = __ldg(seg + lg + 1) - __ldg(seg + lg);
+        const float wgt = 1.0f / (float)nrows;
+        for (int i = tid; i < nrows * PPR; i += blockDim.x) {
+            const int r = i / PPR, k = i % PPR;
+            cp_async16(rows + (size_t)r * F + 4 * k, SRC + (r0 + r) * ld_src + src_off + 4 * k);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (tid < groups * F) {                                     // column sums: thread = (row group, column)
+            const int col = tid % F, grp = tid / F;
+            float s = 0.f;
+            for (int r = grp; r < nrows; r += groups) s += rows[(size_t)r * F + col] * wgt;
+            part[grp * F + col] = s;
+        }
+        __syncthreads();
+        if (tid < F) {
+            float s = 0.f;
+            for (int k = 0; k < groups; ++k) s += part[k * F + tid];
+            mean_s[tid] = s;
+        }
+        __syncthreads();
+        LaneVec<V> mean;
+#pragma unroll
+        for (int i = 0; i < V; ++i) mean.v[i] = mean_s[lane_col<V>(lane, i)];
+        auto finish_row = [&](int r, const LaneVec<V>& old) {
+            LaneVec<V> x = lane_load_rw<V>(rows + (size_t)r * F, lane);
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < V; ++i) { x.v[i] -= mean.v[i]; ss += x.v[i] * x.v[i]; }
+            ss = warp_sum(ss);
+            const float inv = rsqrtf(ss / (float)F + 1.0e-6f);
+            LaneVec<V> nw, carried;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                nw.v[i] = __fadd_rn(__fmul_rn(x.v[i] * inv, 0.25f), __fmul_rn(0.1f, old.v[i]));
+                carried.v[i] = __fadd_rn(__fmul_rn(nw.v[i], 0.2f), __fmul_rn(nw.v[i], 0.8f));
+            }
+            if (PRE_HI) lane_store_split<V>(PRE_HI + (r0 + r) * ld_pre, pre_plane, lane, nw);
+            lane_store_split<V>(STATE_HI + (r0 + r) * ld_state, state_plane, lane, carried);
+        };
+        int r = warp;
+        for (; r + (PN_UNROLL - 1) * nwarps < nrows; r += PN_UNROLL * nwarps) {
+            LaneVec<V> old[PN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PN_UNROLL; ++u) old[u] = lane_load_split_rw<V>(STATE_HI + (r0 + r + u * nwarps) * ld_state, state_plane, lane);
+#pragma unroll
+            for (int u = 0; u < PN_UNROLL; ++u) finish_row(r + u * nwarps, old[u]);
+        }
+        for (; r < nrows; r += nwarps) finish_row(r, lane_load_split_rw<V>(STATE_HI + (r0 + r) * ld_state, state_plane, lane));
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------- head
 // KL(Bernoulli(pa) || Bernoulli(pb)), probabilities as parameters (TFP's registered Bernoulli KL,
 // external): pa*(log pa - log pb) + (1-pa)*(log1p(-pa) - log1p(-pb)), 0*inf := 0.
