@@ -142,6 +142,15 @@ struct dsat_ctx {
 #endif
     bool has_simt_buffers = false;
     float last_noise_scale = 0.f;
+    // one captured denoising step (dsat_sample_enqueue without injected noise): replayed once per step, the step's scalars
+    // come from step_tab[*step_cur] on the device
+    DevBuf<StepParams> step_tab;
+    DevBuf<int> step_cur;
+    std::vector<StepParams> step_tab_host;
+    cudaGraphExec_t step_graph = nullptr;
+    long long generation = 0, step_graph_generation = -1;   // bumped whenever a pointer or plan baked into the graph changes
+    int step_graph_rounds = -1, step_graph_precision = -1, step_launches = 0;
+    bool use_graph = true;
 
     int ldv() const { return F + DSAT_AUX_PAD + 3 * Q; }
     int ldc() const { return F + 2 * Q; }
@@ -169,6 +178,40 @@ struct dsat_ctx {
     } while (0)
 
 namespace {
+
+// Opt every kernel that uses more than 48 KB of dynamic shared memory in, once per device (the attribute is per device),
+// at context creation: nothing on the launch path calls cudaFuncSetAttribute, so launches can be captured into a graph.
+cudaError_t configure_kernels_for_device() {
+    static PerDeviceOnce configured;
+    if (configured.done()) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](auto kernel) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    };
+#ifdef DSAT_WITH_TCGEN05
+    opt_in(clause_gather_smem_kernel<128, true>); opt_in(clause_gather_smem_kernel<128, false>);
+    opt_in(clause_gather_smem_kernel<64, true>); opt_in(clause_gather_smem_kernel<64, false>);
+    opt_in(clause_gather_smem_kernel<32, true>); opt_in(clause_gather_smem_kernel<32, false>);
+    opt_in(literal_gather_smem_kernel<128, true>); opt_in(literal_gather_smem_kernel<128, false>);
+    opt_in(literal_gather_smem_kernel<64, true>); opt_in(literal_gather_smem_kernel<64, false>);
+    opt_in(literal_gather_smem_kernel<32, true>); opt_in(literal_gather_smem_kernel<32, false>);
+    opt_in(clause_gather_smem_f32_kernel<128, true>); opt_in(clause_gather_smem_f32_kernel<128, false>);
+    opt_in(clause_gather_smem_f32_kernel<64, true>); opt_in(clause_gather_smem_f32_kernel<64, false>);
+    opt_in(clause_gather_smem_f32_kernel<32, true>); opt_in(clause_gather_smem_f32_kernel<32, false>);
+    opt_in(clause_gather_smem_f32x2_kernel<128, true>); opt_in(clause_gather_smem_f32x2_kernel<128, false>);
+    opt_in(clause_gather_smem_f32x2_kernel<64, true>); opt_in(clause_gather_smem_f32x2_kernel<64, false>);
+    opt_in(clause_gather_smem_f32x2_kernel<32, true>); opt_in(clause_gather_smem_f32x2_kernel<32, false>);
+    opt_in(literal_gather_smem_f32_kernel<128, true>); opt_in(literal_gather_smem_f32_kernel<128, false>);
+    opt_in(literal_gather_smem_f32_kernel<64, true>); opt_in(literal_gather_smem_f32_kernel<64, false>);
+    opt_in(literal_gather_smem_f32_kernel<32, true>); opt_in(literal_gather_smem_f32_kernel<32, false>);
+    opt_in(pairnorm_smem_kernel<2>); opt_in(pairnorm_smem_kernel<4>); opt_in(pairnorm_smem_kernel<8>);
+    if (e == cudaSuccess) e = fm::configure_fused_device();
+    if (e == cudaSuccess) e = x3::configure_x3_device(0);
+    if (e == cudaSuccess) e = tc::configure_tc_device();
+#endif
+    if (e == cudaSuccess) configured.mark();
+    return e;
+}
 
 UnitGraphDev graph_view(const dsat_ctx* c) {
     UnitGraphDev g;
@@ -395,6 +438,7 @@ int tc_pack_weights(dsat_ctx* c) {
 #endif
 
 void release_buffers(dsat_ctx* c) {
+    c->generation++;        // every pointer a captured step holds may change
     c->VROW.release(); c->CROW.release(); c->H1.release(); c->H2.release(); c->QS.release(); c->LIT.release();
     c->CH.release(); c->COUT.release(); c->U1.release(); c->U2.release(); c->UOUT.release(); c->SPRE.release();
     c->O1.release(); c->LOGITS.release(); c->OUT.release(); c->X.release(); c->labels.release();
@@ -616,7 +660,7 @@ int ensure_active_buffers(dsat_ctx* c) {
 }
 
 int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const float* uniforms_dev,
-               const int* labels_dev, bool use_x, NoiseSource ns) {
+               const int* labels_dev, bool use_x, NoiseSource ns, const StepParams* sp_tab = nullptr, const int* sp_cur = nullptr) {
     const long long Nt = c->Nt;
     const int threads = 256;
     const bool x3p = use_x3(c);
@@ -624,7 +668,7 @@ int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const flo
     c->last_noise_scale = noise_scale;
     step_begin_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
         Nt, noise_scale, use_x ? c->X.p : nullptr, noisy_dev, uniforms_dev, labels_dev, c->labels.p,
-        x3p ? nullptr : c->VROW.p, c->ldv(), c->F, vrow_b(c), ns, vplane);
+        x3p ? nullptr : c->VROW.p, c->ldv(), c->F, vrow_b(c), ns, vplane, sp_tab, sp_cur);
     LAUNCHED(c);
     {   // variables_state = ones, clauses_state = ones (reference model/query_sat.py:141,148)
         long long tot;
@@ -729,7 +773,6 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     const bool si = c->use_idx16 && idx_fits(bytes, g.cl_idx16_vecs);
     const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
     auto launch = [&](auto kernel) -> bool {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, c->ldc(), c->F);
         return true;
     };
@@ -748,7 +791,6 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     const bool si = c->use_idx16 && idx_fits(bytes, g.lit_idx16_vecs);
     const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
     auto launch = [&](auto kernel) -> bool {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F, c->QSb.p, 3 * Q, c->VROWb.p,
                                                c->ldv(), F + DSAT_AUX_PAD);
         return true;
@@ -775,7 +817,6 @@ bool launch_clause_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
     const size_t cplane = (size_t)c->Mt * c->ldc();
     auto launch = [&](auto kernel) -> bool {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROWp.p, cplane, c->ldc(), c->F);
         return true;
     };
@@ -801,7 +842,6 @@ bool launch_literal_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
     const size_t cplane = (size_t)c->Mt * c->ldc(), vplane = (size_t)c->Nt * c->ldv();
     auto launch = [&](auto kernel) -> bool {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWp.p, cplane, c->ldc(), F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q,
                                                 c->VROWp.p, vplane, c->ldv(), F + DSAT_AUX_PAD);
         return true;
@@ -826,7 +866,6 @@ bool launch_pairnorm_smem(dsat_ctx* c, const int* seg, int rows_per_chain, int m
     const int groups = threads / F > 0 ? threads / F : 1;
     const size_t smem = (size_t)(F + groups * F) * 4 + row_bytes;
     if (smem > 227 * 1024) return false;
-    if (cudaFuncSetAttribute(pairnorm_smem_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return false;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     const int by_threads = 2048 / threads;
     if (per_sm > by_threads) per_sm = by_threads;
@@ -840,7 +879,8 @@ bool launch_pairnorm_smem(dsat_ctx* c, const int* seg, int rows_per_chain, int m
 #endif
 
 // One message-passing round (reference model/query_sat.py:225-348).
-int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, LossScalars ls) {
+int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, LossScalars ls,
+              const StepParams* sp_tab = nullptr, const int* sp_cur = nullptr) {
     const long long Nt = c->Nt, Mt = c->Mt;
     const int F = c->F, Q = c->Q, ldv = c->ldv(), ldc = c->ldc(), ldh1 = c->ldh1();
     const UnitGraphDev g = graph_view(c);
@@ -856,7 +896,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         const int threads = 256;
         prof_mark(c, PROF_NOISE);
         round_noise_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
-            Nt, normals_dev, x3p ? nullptr : c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round, vplane);
+            Nt, normals_dev, x3p ? nullptr : c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round, vplane, sp_tab, sp_cur);
         LAUNCHED(c);
     }
     // v1 -> [hidden of variables_query | first hidden of lit_query]   (:240, :252)
@@ -1056,7 +1096,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     head_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->group_graphs, c->LOGITS.p,
                                                          DSAT_LOGIT_PAD, c->labels.p, ls.t, ls.ts, ls.norm_plus,
                                                          c->done.p, c->OUT.p, c->BITS.p, c->graph_sat.p,
-                                                         c->graph_loss.p, c->graph_map.p);
+                                                         c->graph_loss.p, c->graph_map.p, sp_tab, sp_cur);
     LAUNCHED(c);
     group_finalize_kernel<<<(c->n_groups + 127) / 128, 128, 0, c->stream>>>(
         c->n_groups, c->group_graphs, c->total_graphs, round, c->graph_sat.p, c->graph_loss.p, c->done.p,
@@ -1128,6 +1168,12 @@ int pack_weights(dsat_ctx* c, const float* const* kernels, const float* const* b
 }  // namespace
 
 // =================================================================================== C ABI
+static void drop_step_graph(dsat_ctx* c) {
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    c->step_graph = nullptr;
+    c->step_graph_generation = -1;
+}
+
 extern "C" {
 
 int dsat_version(void) { return 1; }
@@ -1141,6 +1187,7 @@ int dsat_create(int device, dsat_ctx** out) {
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (configure_kernels_for_device() != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
     c->stream = c->own_stream;
     cudaEventCreate(&c->ev0);
@@ -1155,6 +1202,8 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e) c->use_idx16 = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
         if (e && e[0] == '0') c->use_smem_gather = false;
+        e = getenv("DSAT_GRAPH");
+        if (e && e[0] == '0') c->use_graph = false;
     }
 #endif
     *out = c;
@@ -1165,6 +1214,8 @@ void dsat_destroy(dsat_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    drop_step_graph(c);
+    c->step_tab.release(); c->step_cur.release();
     release_buffers(c);
     for (auto& op : c->ops) {
         op.w.release(); op.b.release();
@@ -1190,6 +1241,7 @@ const char* dsat_last_error(const dsat_ctx* c) { return c ? c->err.c_str() : "nu
 
 int dsat_set_stream(dsat_ctx* c, void* s) {
     if (!c) return DSAT_ERR_ARG;
+    c->generation++;
     c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
     return DSAT_OK;
 }
@@ -1263,6 +1315,11 @@ int dsat_set_model(dsat_ctx* c, int n_layers, const float* const* kernels, const
     CK_ARG(c, ok, "dsat_set_model: layer dimensions do not form the QuerySAT MLPs");
     CK_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->has_buffers && (c->F != F || c->Q != Q)) release_buffers(c);
+    c->generation++;        // weight buffers are re-allocated
+#ifdef DSAT_WITH_TCGEN05
+    // the whole-MLP plans hold the weight pointers and their TMA descriptors: rebuild them with the next launch
+    c->has_tc_buffers = false; c->has_x3_buffers = false; c->fused_ready = false; c->x3_ready = false;
+#endif
     c->F = F; c->Q = Q;
     int rc = pack_weights(c, kernels, biases, in_dims, out_dims);
     if (rc) return rc;
@@ -1321,6 +1378,7 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
                             c->chains == n_chains && c->words == ceil_div(max_graph_vars, 64) &&
                             c->n_groups == ceil_div(total_graphs_new, group_new);
     if (!same_shape) release_buffers(c);
+    c->generation++;        // the index arrays are re-allocated
     c->has_graph = false;               // set again at the end: an upload that fails half way leaves no graph bound
     c->n = n_vars; c->m = n_clauses; c->nnz = nnz; c->n_graphs = n_graphs; c->chains = n_chains;
     c->total_graphs = n_graphs * n_chains;
@@ -1470,6 +1528,49 @@ int dsat_model_call(dsat_ctx* c, float noise_scale, const float* noisy_num, cons
 }
 
 // --------------------------------------------------------------------------------------- sampler
+// scalars of denoising step t of n_steps, computed on the host exactly as the by-value launch path does
+static StepParams step_params(int t, int n_steps, uint64_t seed, uint64_t element_offset) {
+    StepParams sp;
+    const double ns_d = 1.0 - (double)t / (double)n_steps;       // Python float (DiffusionSampler.py:106)
+    sp.noise_scale = (float)ns_d;
+    const LossScalars ls = loss_scalars(sp.noise_scale);
+    sp.t = ls.t; sp.ts = ls.ts; sp.norm_plus = ls.norm_plus;
+    // posterior scalars (reference DiffusionSampler.py:30-33): pow in fp32, max() in Python floats
+    const float t1 = powf(sp.noise_scale, 0.5f);
+    const double t_prev = ns_d - 1.0 / (double)n_steps;
+    const float t2 = powf((float)(t_prev > 0.0 ? t_prev : 0.0), 0.5f);
+    const float alpha = (1.0f - t1) / (1.0f - t2);
+    sp.t1 = t1;
+    sp.one_minus_alpha = 1.0f - alpha;
+    sp.step = (unsigned)t; sp.pad_ = 0;
+    sp.seed = seed; sp.element_offset = element_offset;
+    return sp;
+}
+
+// launches of one denoising step; with sp_tab the step's scalars are read on the device (graph capture)
+static int enqueue_step(dsat_ctx* c, const StepParams& sp, int n_rounds, const float* uniforms_dev, const int* labels_dev,
+                        const float* normals_dev, const StepParams* sp_tab, const int* sp_cur) {
+    const UnitGraphDev g = graph_view(c);
+    NoiseSource ns{sp.seed, sp.element_offset, sp.step};
+    int rc = begin_call(c, sp.noise_scale, nullptr, uniforms_dev, labels_dev, true, ns, sp_tab, sp_cur);
+    if (rc) return rc;
+    LossScalars ls; ls.t = sp.t; ls.ts = sp.ts; ls.norm_plus = sp.norm_plus;
+    for (int r = 0; r < n_rounds; ++r) {
+        const float* nrm = normals_dev ? normals_dev + (size_t)r * c->Nt * 4 : nullptr;
+        if ((rc = run_round(c, r, nrm, ns, ls, sp_tab, sp_cur))) return rc;
+    }
+    PosteriorScalars ps;
+    ps.t1 = sp.t1; ps.one_minus_alpha = sp.one_minus_alpha;
+    step_end_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->OUT.p, c->X.p, ps, (int)sp.step,
+                                                             c->LAST.p, c->LATCH.p, c->latch_step.p, c->sat_now.p, sp_tab, sp_cur);
+    LAUNCHED(c);
+    if (sp_tab) {
+        step_advance_kernel<<<1, 1, 0, c->stream>>>(const_cast<int*>(sp_cur));
+        LAUNCHED(c);
+    }
+    return DSAT_OK;
+}
+
 static int sample_enqueue_impl(dsat_ctx* c, int n_steps, int n_rounds, uint64_t seed, uint64_t chain_offset,
                                const float* uniforms_dev, const int* labels_dev, const float* normals_dev) {
     int rc = ensure_active_buffers(c);
@@ -1484,29 +1585,49 @@ static int sample_enqueue_impl(dsat_ctx* c, int n_steps, int n_rounds, uint64_t 
     }
     CK_CUDA(c, cudaMemsetAsync(c->latch_step.p, 0xff, c->latch_step.count * sizeof(int), c->stream));
     CK_CUDA(c, cudaMemsetAsync(c->sat_any.p, 0, c->sat_any.count, c->stream));
-    for (int t = 0; t < n_steps; ++t) {
-        const double ns_d = 1.0 - (double)t / (double)n_steps;       // Python float (:106)
-        const float noise_scale = (float)ns_d;
-        NoiseSource ns{seed, chain_offset * (uint64_t)c->n, (unsigned)t};
-        if ((rc = begin_call(c, noise_scale, nullptr, uniforms_dev ? uniforms_dev + (size_t)t * Nt : nullptr,
-                             labels_dev ? labels_dev + (size_t)t * Nt : nullptr, true, ns)))
-            return rc;
-        const LossScalars ls = loss_scalars(noise_scale);
-        for (int r = 0; r < n_rounds; ++r) {
-            const float* nrm = normals_dev ? normals_dev + ((size_t)t * n_rounds + r) * Nt * 4 : nullptr;
-            if ((rc = run_round(c, r, nrm, ns, ls))) return rc;
+    const uint64_t element_offset = chain_offset * (uint64_t)c->n;
+    const bool injected = uniforms_dev || labels_dev || normals_dev;
+    if (c->use_graph && !injected && !c->profiling) {
+        // One denoising step is captured once and replayed n_steps times: the ~12 launches per round are issued by the
+        // graph executor back to back instead of one cudaLaunchKernel each (small formulas are launch-bound: 12.5 k launches
+        // per run).  Everything that differs between steps lives in step_tab[*step_cur].
+        c->step_tab_host.resize(n_steps);
+        for (int t = 0; t < n_steps; ++t) c->step_tab_host[t] = step_params(t, n_steps, seed, element_offset);
+        if (c->step_tab.count < (size_t)n_steps) { CK_CUDA(c, c->step_tab.alloc(n_steps)); c->generation++; }
+        if (!c->step_cur.p) { CK_CUDA(c, c->step_cur.alloc(1)); c->generation++; }
+        CK_CUDA(c, cudaMemcpyAsync(c->step_tab.p, c->step_tab_host.data(), n_steps * sizeof(StepParams), cudaMemcpyHostToDevice, c->stream));
+        CK_CUDA(c, cudaMemsetAsync(c->step_cur.p, 0, sizeof(int), c->stream));
+        if (!c->step_graph || c->step_graph_generation != c->generation || c->step_graph_rounds != n_rounds ||
+            c->step_graph_precision != c->precision) {
+            drop_step_graph(c);
+            cudaGraph_t graph = nullptr;
+            CK_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            const long long launches_before = c->launches;
+            rc = enqueue_step(c, c->step_tab_host[0], n_rounds, nullptr, nullptr, nullptr, c->step_tab.p, c->step_cur.p);
+            const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+            c->step_launches = (int)(c->launches - launches_before);
+            c->launches = launches_before;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CK_CUDA(c, ce);
+            const cudaError_t ie = cudaGraphInstantiate(&c->step_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            CK_CUDA(c, ie);
+            c->step_graph_generation = c->generation;
+            c->step_graph_rounds = n_rounds;
+            c->step_graph_precision = c->precision;
         }
-        // posterior scalars (reference DiffusionSampler.py:30-33): pow in fp32, max() in Python floats
-        PosteriorScalars ps;
-        const float t1 = powf(noise_scale, 0.5f);
-        const double t_prev = ns_d - 1.0 / (double)n_steps;
-        const float t2 = powf((float)(t_prev > 0.0 ? t_prev : 0.0), 0.5f);
-        const float alpha = (1.0f - t1) / (1.0f - t2);
-        ps.t1 = t1;
-        ps.one_minus_alpha = 1.0f - alpha;
-        step_end_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->OUT.p, c->X.p, ps, t,
-                                                                 c->LAST.p, c->LATCH.p, c->latch_step.p, c->sat_now.p);
-        LAUNCHED(c);
+        for (int t = 0; t < n_steps; ++t) {
+            CK_CUDA(c, cudaGraphLaunch(c->step_graph, c->stream));
+            c->launches += c->step_launches;
+        }
+    } else {
+        for (int t = 0; t < n_steps; ++t) {
+            const StepParams sp = step_params(t, n_steps, seed, element_offset);
+            if ((rc = enqueue_step(c, sp, n_rounds, uniforms_dev ? uniforms_dev + (size_t)t * Nt : nullptr,
+                                   labels_dev ? labels_dev + (size_t)t * Nt : nullptr,
+                                   normals_dev ? normals_dev + (size_t)t * n_rounds * Nt * 4 : nullptr, nullptr, nullptr)))
+                return rc;
+        }
     }
     pack_assignments_kernel<<<c->total_graphs, 128, 0, c->stream>>>(g, c->total_graphs, c->words, c->LAST.p, c->LATCH.p,
                                                                      c->latch_step.p, c->packed.p, c->is_sat.p, c->FINAL.p);

@@ -466,13 +466,19 @@ struct TcLinear {
     int a_box_rows, b_box_rows;     // TMA box heights the descriptors were encoded with
 };
 
+inline cudaError_t configure_tc_device() {
+    static PerDeviceOnce configured;
+    if (configured.done()) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) configured.mark();
+    return e;
+}
+
 inline cudaError_t launch_tc_linear(const TcLinear& op, cudaStream_t stream) {
     if (op.rows <= 0) return cudaSuccess;
-    static PerDeviceOnce configured;
-    if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    {
+        cudaError_t e = configure_tc_device();
         if (e != cudaSuccess) return e;
-        configured.mark();
     }
     const int n_tiles = ceil_div(op.N, BLOCK_N);
     const unsigned grid = (unsigned)(n_tiles * ceil_div(op.rows, BLOCK_M));

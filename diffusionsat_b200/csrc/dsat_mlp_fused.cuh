@@ -1088,18 +1088,24 @@ inline bool plan_fused(FusedMlp& f) {
     return false;
 }
 
+inline cudaError_t configure_fused_device() {
+    static PerDeviceOnce configured;        // MaxDynamicSharedMemorySize is a per-device function attribute
+    if (configured.done()) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) configured.mark();
+    return e;
+}
+
 inline cudaError_t launch_fused(const FusedMlp& f, int sm_count, cudaStream_t stream) {
     if (f.p.rows <= 0) return cudaSuccess;
-    static PerDeviceOnce configured;
-    if (!configured.done()) {
-        cudaError_t e = cudaFuncSetAttribute(fused_mlp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_mlp_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    {
+        cudaError_t e = configure_fused_device();
         if (e != cudaSuccess) return e;
-        configured.mark();
     }
     const unsigned threads = 64 + 32 * f.p.epi_warps;
     const int last = f.p.n_layers > 2 ? 2 : 1;

@@ -328,6 +328,19 @@ __device__ __forceinline__ int graph_clauses_unsat(const UnitGraphDev& g, int lg
     return unsat;
 }
 
+// Scalars of one denoising step, resident on the device: a captured CUDA graph of one step is replayed for every step of a
+// run, so whatever changes from step to step is read through (table, cursor) instead of being baked into the launch.
+// The host fills the table with exactly the values it would otherwise pass by value.
+struct StepParams {
+    float noise_scale;                   // 1 - t/N                                  (DiffusionSampler.py:106)
+    float t, ts, norm_plus;              // train_loss scalars                       (model/query_sat.py:41-53)
+    float t1, one_minus_alpha;           // posterior scalars                        (DiffusionSampler.py:30-33)
+    unsigned int step;                   // denoising step index (Philox counter, latch step)
+    int pad_;
+    unsigned long long seed, element_offset;
+};
+__global__ void step_advance_kernel(int* cursor) { *cursor += 1; }
+
 // Logit-map selection (reference model/query_sat.py:289-292,317-320,328-329 with train_loss :40-53)
 // and is_batch_sat's per-clause test (utils/sat.py:118-124), one CTA per graph.  Graphs whose
 // early-exit group already finished are skipped: their OUT keeps the logits of the round that broke.
@@ -336,9 +349,11 @@ head_kernel(UnitGraphDev g, int total_graphs, int group_graphs,
             const float* __restrict__ LOGITS, int ld_logits, const int* __restrict__ labels,
             float t, float ts, float norm_plus,
             const int* __restrict__ done, float* __restrict__ OUT, unsigned char* BITS,
-            int* __restrict__ graph_sat, float* __restrict__ graph_loss, int* __restrict__ graph_map) {
+            int* __restrict__ graph_sat, float* __restrict__ graph_loss, int* __restrict__ graph_map,
+            const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr) {
     __shared__ float red[4][DSAT_LOGIT_MAPS];
     __shared__ int best_s;
+    if (sp_tab) { const StepParams sp = sp_tab[*sp_cur]; t = sp.t; ts = sp.ts; norm_plus = sp.norm_plus; }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = blockIdx.x;
     if (gid >= total_graphs) return;
@@ -438,9 +453,14 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
                                   const int* __restrict__ labels_in,       // [n_rows] or null -> Philox
                                   int* __restrict__ labels,
                                   float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
-                                  NoiseSource ns, size_t lo_plane = 0) {   // lo_plane > 0: VROW_B is a hi plane with its lo plane that far on
+                                  NoiseSource ns, size_t lo_plane = 0,     // lo_plane > 0: VROW_B is a hi plane with its lo plane that far on
+                                  const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
+    if (sp_tab) {
+        const StepParams sp = sp_tab[*sp_cur];
+        noise_scale = sp.noise_scale; ns.seed = sp.seed; ns.element_offset = sp.element_offset; ns.step = sp.step;
+    }
     float a, b;
     if (noisy_in) {
         a = noisy_in[2 * r]; b = noisy_in[2 * r + 1];
@@ -482,9 +502,14 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
 // Fresh N(0,1)[.,4] every round (reference model/query_sat.py:239).
 __global__ void round_noise_kernel(long long n_rows, const float* __restrict__ normals_in /*[n_rows,4] or null*/,
                                    float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
-                                   NoiseSource ns, unsigned int round, size_t lo_plane = 0) {
+                                   NoiseSource ns, unsigned int round, size_t lo_plane = 0,
+                                   const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
+    if (sp_tab) {
+        const StepParams sp = sp_tab[*sp_cur];
+        ns.seed = sp.seed; ns.element_offset = sp.element_offset; ns.step = sp.step;
+    }
     float4 nrm;
     if (normals_in) {
         nrm = __ldg(reinterpret_cast<const float4*>(normals_in) + r);
@@ -533,10 +558,15 @@ struct PosteriorScalars { float t1, one_minus_alpha; };
 __global__ void __launch_bounds__(128)
 step_end_kernel(UnitGraphDev g, int total_graphs, const float* __restrict__ OUT, float2* X,
                 PosteriorScalars ps, int step, unsigned char* LAST, unsigned char* LATCH,
-                int* __restrict__ latch_step, int* __restrict__ sat_now) {
+                int* __restrict__ latch_step, int* __restrict__ sat_now,
+                const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr) {
     const int tid = threadIdx.x;
     const int gid = blockIdx.x;
     if (gid >= total_graphs) return;
+    if (sp_tab) {
+        const StepParams sp = sp_tab[*sp_cur];
+        ps.t1 = sp.t1; ps.one_minus_alpha = sp.one_minus_alpha; step = (int)sp.step;
+    }
     const int chain = gid / g.n_graphs, lg = gid % g.n_graphs;
     const int v0 = __ldg(g.var_seg + lg), v1 = __ldg(g.var_seg + lg + 1);
     const size_t rowbase = (size_t)chain * g.n;

@@ -202,16 +202,23 @@ class DiffusionSampler:
         print(f"Model restored from {model_path}!")
         return weights
 
-    def _launch_chains(self, still_needed: int, chains_left: int | None = None) -> int:
-        """Chains per launch: whole reference batches, enough for the samples still needed, bounded."""
+    def _launch_chains(self, still_needed: int, chains_left: int | None = None, sat_rate: float | None = None) -> int:
+        """Chains per launch: whole reference batches, bounded by the activation memory.  The reference runs one batch at a
+        time until it has enough samples; a launch here holds as many batches as the samples still needed are expected to
+        take at the SAT rate seen so far (first launch: 50 %, at least four batches -- small launches are latency-bound, so
+        spare chains cost nothing), and batches are consumed in order with the reference's stop rules, so the histogram does
+        not depend on the launch size."""
         b = self.batch_chains
         if self.chains_per_launch:
             n = max(b, (self.chains_per_launch // b) * b)
         else:
-            batches = max(1, -(-still_needed // b))
+            rate = max(sat_rate if sat_rate is not None else 0.5, 0.02)
+            batches = max(4, -(-int(still_needed / rate * 1.15 + 1) // b))
             rows_cap = 900_000                              # variable/clause rows per launch (~20 GB of activations at n=100)
             cap = max(1, rows_cap // max(len(self.clauses), self.n_vars, 1) // b)
             n = b * min(batches, cap)
+            if self.ctx.graph is self.unit and n <= self.ctx.chains <= 2 * n:
+                n = self.ctx.chains                         # same shape as the previous launch: buffers and the captured step are kept
         if chains_left is not None:
             n = min(n, max(chains_left, 1))
             if chains_left - n < b:             # a remainder smaller than one reference batch rides along as a last, partial group
@@ -241,7 +248,8 @@ class DiffusionSampler:
         words = -(-self.n_vars // 64)
         stop = False
         while still_needed > 0 and not stop and (max_chains is None or launched < max_chains):
-            chains = self._launch_chains(still_needed, None if max_chains is None else max_chains - launched)
+            chains = self._launch_chains(still_needed, None if max_chains is None else max_chains - launched,
+                                         sat_total / total if total else None)
             if self.ctx.graph is not self.unit or self.ctx.chains != chains:
                 self.ctx.set_graph(self.unit, chains=chains, group_graphs=self.batch_chains)
                 self.model._graph_key = None

@@ -1,15 +1,19 @@
-"""Wall-clock of the reference's own small case (BASELINE configs[0]: 3-SAT n=30, samples(256)) through the public API."""
-import os, sys, time, tempfile
+"""Small-launch regime (BASELINE configs[0]): wall time of DiffusionSampler.samples(256) at n=30 through the public API.
+python scripts/small_case_latency.py [precision]"""
+import contextlib, io, os, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from diffusionsat_b200 import synth, weights
+from diffusionsat_b200 import synth
 from diffusionsat_b200.sampler import DiffusionSampler
-n, clauses = synth.random_3sat(30, seed=0)
-d = tempfile.mkdtemp()
-cnf = os.path.join(d, "f.cnf"); open(cnf, "w").write(synth.dimacs_text(n, clauses))
-wp = os.path.join(d, "w.npz"); weights.save_weights(wp, weights.init_weights(seed=1234))
-for prec in ("bf16", "fp32"):
-    t0 = time.perf_counter(); s = DiffusionSampler(wp, cnf, precision=prec, seed=1); t1 = time.perf_counter()
-    for rep in range(3):
-        t2 = time.perf_counter(); hist = s.samples(256); t3 = time.perf_counter()
-        print("%s: ctor %.3f s, samples(256) call %d: %.3f s, sat %d of %d chains, distinct %d" %
-              (prec, t1 - t0, rep, t3 - t2, s.last_stats["sat"], s.last_stats["total"], len(hist)))
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+fixture = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "trained_small.npz")
+n, clauses, _ = synth.planted_3sat(30, 133, seed=0)
+cnf = os.path.join(tempfile.mkdtemp(), "f.cnf")
+open(cnf, "w").write(synth.dimacs_text(n, clauses))
+with contextlib.redirect_stdout(io.StringIO()):
+    s = DiffusionSampler(fixture, cnf, precision=prec, seed=5)
+    t0 = time.perf_counter(); s.samples(256); cold = time.perf_counter() - t0
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter(); h = s.samples(256); times.append(time.perf_counter() - t0)
+print("%s: samples(256) n=30: cold %.3f s, warm %s s, %d chains launched per call, launches %d, graph %s" % (
+    prec, cold, ["%.3f" % t for t in times], s.last_stats["chains_launched"], s.ctx.launch_count(), os.environ.get("DSAT_GRAPH", "1")))
