@@ -228,6 +228,13 @@ UnitGraphDev graph_view(const dsat_ctx* c) {
     return g;
 }
 
+// rows of finished early-exit groups are skipped when the groups consist of whole chains (DSAT_SKIP_DONE=0 turns it off)
+SkipInfo skip_info(const dsat_ctx* c) {
+    static const bool off = getenv("DSAT_SKIP_DONE") && atoi(getenv("DSAT_SKIP_DONE")) == 0;
+    if (off || c->n_graphs <= 0 || c->group_graphs % c->n_graphs != 0) return SkipInfo{nullptr, 1};
+    return SkipInfo{c->done.p, c->group_graphs / c->n_graphs};
+}
+
 // buffers every precision uses: the fp32 outputs of the MLPs, the diffusion state and the per-graph bookkeeping
 int ensure_common_buffers(dsat_ctx* c) {
     if (c->has_buffers) return DSAT_OK;
@@ -534,6 +541,11 @@ int ensure_x3_buffers(dsat_ctx* c) {
         p.qmaps = Q;
         p.prof = nullptr;
         p.out_mode = out_mode; p.out0 = out0; p.out1 = out1; p.ld_out = ld_out;
+        {
+            const SkipInfo sk = skip_info(c);
+            p.done = sk.done; p.chains_per_group = sk.chains_per_group;
+            p.rows_per_chain = rows == c->Mt ? c->m : c->n;
+        }
         f.pair_mode = ((pair_mask >> which) & 1) != 0;
         if (!tc::make_bf16_map(&f.map_a_hi, a_hi, rows, k, lda, p.a_box_rows)) return false;
         if (!tc::make_bf16_map(&f.map_a_lo, a_hi + a_plane, rows, k, lda, p.a_box_rows)) return false;
@@ -620,6 +632,7 @@ int dispatch_width(dsat_ctx* c, int width, KernelLauncher&& fn) {
 }
 
 struct LossScalars { float t, ts, norm_plus; };
+
 
 // host-side fp32 scalars of train_loss (reference model/query_sat.py:41-42,48-53)
 float kl_host(float pa, float pb) {
@@ -773,7 +786,7 @@ bool launch_clause_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     const bool si = c->use_idx16 && idx_fits(bytes, g.cl_idx16_vecs);
     const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
     auto launch = [&](auto kernel) -> bool {
-        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, c->ldc(), c->F);
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, c->ldc(), c->F, skip_info(c));
         return true;
     };
     if (w == 128) return si ? launch(clause_gather_smem_kernel<128, true>) : launch(clause_gather_smem_kernel<128, false>);
@@ -792,7 +805,7 @@ bool launch_literal_gather_smem(dsat_ctx* c, const UnitGraphDev& g) {
     const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
     auto launch = [&](auto kernel) -> bool {
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWb.p, c->ldc(), F + Q, c->COUTb.p, Q + F, c->QSb.p, 3 * Q, c->VROWb.p,
-                                               c->ldv(), F + DSAT_AUX_PAD);
+                                               c->ldv(), F + DSAT_AUX_PAD, skip_info(c));
         return true;
     };
     if (w == 128) return si ? launch(literal_gather_smem_kernel<128, true>) : launch(literal_gather_smem_kernel<128, false>);
@@ -817,7 +830,7 @@ bool launch_clause_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     const size_t smem = bytes + (si ? (size_t)g.cl_idx16_vecs * 16 : 0);
     const size_t cplane = (size_t)c->Mt * c->ldc();
     auto launch = [&](auto kernel) -> bool {
-        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROWp.p, cplane, c->ldc(), c->F);
+        kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROWp.p, cplane, c->ldc(), c->F, skip_info(c));
         return true;
     };
     if (one_table) {
@@ -843,7 +856,7 @@ bool launch_literal_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     const size_t cplane = (size_t)c->Mt * c->ldc(), vplane = (size_t)c->Nt * c->ldv();
     auto launch = [&](auto kernel) -> bool {
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWp.p, cplane, c->ldc(), F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q,
-                                                c->VROWp.p, vplane, c->ldv(), F + DSAT_AUX_PAD);
+                                                c->VROWp.p, vplane, c->ldv(), F + DSAT_AUX_PAD, skip_info(c));
         return true;
     };
     if (w == 128) return si ? launch(literal_gather_smem_f32_kernel<128, true>) : launch(literal_gather_smem_f32_kernel<128, false>);
@@ -873,7 +886,7 @@ bool launch_pairnorm_smem(dsat_ctx* c, const int* seg, int rows_per_chain, int m
     int grid = c->sm_count * per_sm;
     if (grid > c->total_graphs) grid = c->total_graphs;
     pairnorm_smem_kernel<V><<<grid, threads, smem, c->stream>>>(seg, c->n_graphs, rows_per_chain, c->total_graphs, src, ld_src, src_off,
-                                                                state_hi, state_plane, ld_state, pre_hi, pre_plane, ld_pre);
+                                                                state_hi, state_plane, ld_state, pre_hi, pre_plane, ld_pre, skip_info(c));
     return true;
 }
 #endif
@@ -887,6 +900,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
     const bool tcp = use_tc(c);
     const bool x3p = use_x3(c);
     const size_t vplane = x3p ? (size_t)Nt * ldv : 0, cplane = x3p ? (size_t)Mt * ldc : 0;
+    const SkipInfo skip = skip_info(c);
 #ifdef DSAT_WITH_TCGEN05
     const bool fusedp = tcp && c->precision == DSAT_BF16 && c->fused_ready && c->use_fused;
     enum { XQ = 0, XL1, XL2, XL3, XC, XU, XO };
@@ -896,7 +910,7 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
         const int threads = 256;
         prof_mark(c, PROF_NOISE);
         round_noise_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
-            Nt, normals_dev, x3p ? nullptr : c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round, vplane, sp_tab, sp_cur);
+            Nt, normals_dev, x3p ? nullptr : c->VROW.p, ldv, F, vrow_b(c), ns, (unsigned)round, vplane, sp_tab, sp_cur, skip, c->n);
         LAUNCHED(c);
     }
     // v1 -> [hidden of variables_query | first hidden of lit_query]   (:240, :252)
@@ -938,14 +952,14 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
             if (!launch_clause_gather_smem_f32(c, g))
 #endif
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
-                g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, nullptr, ldc, F, crow_b(c), cplane);
+                g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, nullptr, ldc, F, crow_b(c), cplane, skip);
         } else if (!tcp)
             clause_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
-                g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F);
+                g, c->chains, c->LIT.p, 2 * Q, c->QS.p, 3 * Q, Q, c->CROW.p, ldc, F, nullptr, 0, skip);
 #ifdef DSAT_WITH_TCGEN05
         else if (!launch_clause_gather_smem(c, g))
             clause_gather_kernel<V, __nv_bfloat16><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
-                g, c->chains, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, ldc, F);
+                g, c->chains, c->LITb.p, 2 * Q, c->QSb.p, 3 * Q, Q, c->CROWb.p, ldc, F, nullptr, 0, skip);
 #endif
     });
     if (rc) return rc;
@@ -982,14 +996,16 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
 #endif
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
                 g, c->chains, nullptr, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, nullptr, ldv, F + DSAT_AUX_PAD,
-                vrow_b(c), vplane, crow_b(c), cplane);
+                vrow_b(c), vplane, crow_b(c), cplane, skip);
         } else if (!tcp)
             literal_gather_kernel<V, float><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
-                g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD);
+                g, c->chains, c->CROW.p, ldc, F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q, c->VROW.p, ldv, F + DSAT_AUX_PAD,
+                nullptr, 0, nullptr, 0, skip);
 #ifdef DSAT_WITH_TCGEN05
         else if (!launch_literal_gather_smem(c, g))
             literal_gather_kernel<V, __nv_bfloat16><<<grid, GATHER_WARPS * 32, 0, c->stream>>>(
-                g, c->chains, c->CROWb.p, ldc, F + Q, c->COUTb.p, Q + F, c->QSb.p, 3 * Q, c->VROWb.p, ldv, F + DSAT_AUX_PAD);
+                g, c->chains, c->CROWb.p, ldc, F + Q, c->COUTb.p, Q + F, c->QSb.p, 3 * Q, c->VROWb.p, ldv, F + DSAT_AUX_PAD,
+                nullptr, 0, nullptr, 0, skip);
 #endif
     });
     if (rc) return rc;
@@ -1015,14 +1031,15 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
 #endif
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, nullptr, ldc, nullptr, 0,
-                crow_b(c), cplane, nullptr, 0);
+                crow_b(c), cplane, nullptr, 0, skip);
         } else if (!tcp)
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
-                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0);
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUT.p, Q + F, Q, c->CROW.p, ldc, nullptr, 0,
+                nullptr, 0, nullptr, 0, skip);
 #ifdef DSAT_WITH_TCGEN05
         else
             pairnorm_bf16_kernel<32 * V><<<grid, PN_WARPS * 32, 0, c->stream>>>(
-                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUTb.p, Q + F, Q, c->CROWb.p, ldc, nullptr, 0);
+                c->clause_seg.p, c->n_graphs, c->m, c->total_graphs, c->COUTb.p, Q + F, Q, c->CROWb.p, ldc, nullptr, 0, skip);
 #endif
     });
     if (rc) return rc;
@@ -1059,15 +1076,16 @@ int run_round(dsat_ctx* c, int round, const float* normals_dev, NoiseSource ns, 
                                          c->SPREp.p, (size_t)Nt * F, F))
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
                 c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, nullptr, ldv, nullptr, F,
-                vrow_b(c), vplane, c->SPREp.p, (size_t)Nt * F);
+                vrow_b(c), vplane, c->SPREp.p, (size_t)Nt * F, skip);
 #endif
         } else if (!tcp)
             pairnorm_kernel<V, float, float><<<grid, PN_WARPS * 32, 0, c->stream>>>(
-                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F);
+                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUT.p, F, 0, c->VROW.p, ldv, c->SPRE.p, F,
+                nullptr, 0, nullptr, 0, skip);
 #ifdef DSAT_WITH_TCGEN05
         else
             pairnorm_bf16_kernel<32 * V><<<grid, PN_WARPS * 32, 0, c->stream>>>(
-                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUTb.p, F, 0, c->VROWb.p, ldv, c->SPREb.p, F);
+                c->var_seg.p, c->n_graphs, c->n, c->total_graphs, c->UOUTb.p, F, 0, c->VROWb.p, ldv, c->SPREb.p, F, skip);
 #endif
     });
     if (rc) return rc;
@@ -1376,7 +1394,7 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
     const int group_new = group_graphs > 0 ? group_graphs : total_graphs_new;
     const bool same_shape = c->has_graph && c->n == n_vars && c->m == n_clauses && c->n_graphs == n_graphs &&
                             c->chains == n_chains && c->words == ceil_div(max_graph_vars, 64) &&
-                            c->n_groups == ceil_div(total_graphs_new, group_new);
+                            c->group_graphs == group_new;
     if (!same_shape) release_buffers(c);
     c->generation++;        // the index arrays are re-allocated
     c->has_graph = false;               // set again at the end: an upload that fails half way leaves no graph bound

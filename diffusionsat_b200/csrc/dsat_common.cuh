@@ -22,6 +22,18 @@ struct PerDeviceOnce {
     void mark() { const int d = current(); if (d >= 0) mask |= 1ull << d; }
 };
 
+// Early exit of a reference batch (model/query_sat.py:330-338): once every graph of an early-exit group is satisfied the
+// group's round loop breaks.  `done[group]` is set on the device at the end of the breaking round; every later kernel of the
+// same model call skips the rows of that group's chains (their buffers keep the state of the breaking round, which nothing
+// reads any more).  done == nullptr: groups do not consist of whole chains, nothing is skipped.
+struct SkipInfo {
+    const int* done;
+    int chains_per_group;
+};
+__device__ __forceinline__ bool chain_done(const SkipInfo& s, int chain) {
+    return s.done != nullptr && __ldg(s.done + chain / s.chains_per_group) != 0;
+}
+
 // ---------------------------------------------------------------------------------- math
 // softplus with the usual large-argument guard (log1p(exp(x)) otherwise); reference
 // loss/sat.py:132 uses tf.nn.softplus.

@@ -70,13 +70,15 @@ clause_gather_kernel(UnitGraphDev g, int chains,
                      const T* __restrict__ LIT, int ld_lit,
                      const T* __restrict__ SP, int ld_sp, int sp_off,
                      T* __restrict__ OUT, int ld_out, int out_off,
-                     __nv_bfloat16* __restrict__ OUT_HI = nullptr, size_t out_plane = 0) {   // split-plane output instead of OUT
+                     __nv_bfloat16* __restrict__ OUT_HI = nullptr, size_t out_plane = 0,    // split-plane output instead of OUT
+                     SkipInfo skip = SkipInfo{nullptr, 1}) {
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
     RowCursor cur = row_cursor((long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5),
                                (long long)gridDim.x * GATHER_WARPS, g.m);
     for (; cur.c < chains; row_cursor_step(cur, g.m)) {
         const int c = cur.c, j = cur.pos;
+        if (chain_done(skip, c)) continue;
         const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
         const size_t vbase = (size_t)c * g.n;
         LaneVec<V> acc_l, acc_s;
@@ -139,13 +141,15 @@ literal_gather_kernel(UnitGraphDev g, int chains,
                       const T* __restrict__ QRY, int ld_q,
                       T* __restrict__ OUT, int ld_out, int out_off,
                       __nv_bfloat16* __restrict__ OUT_HI = nullptr, size_t out_plane = 0,    // split-plane output instead of OUT
-                      const __nv_bfloat16* __restrict__ CL4_HI = nullptr, size_t cl_plane = 0) {   // split-plane CL4 instead of CL4
+                      const __nv_bfloat16* __restrict__ CL4_HI = nullptr, size_t cl_plane = 0,    // split-plane CL4 instead of CL4
+                      SkipInfo skip = SkipInfo{nullptr, 1}) {
     constexpr int Q = 32 * V;
     const int lane = threadIdx.x & 31;
     RowCursor cur = row_cursor((long long)blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5),
                                (long long)gridDim.x * GATHER_WARPS, g.n);
     for (; cur.c < chains; row_cursor_step(cur, g.n)) {
         const int c = cur.c, v = cur.pos;
+        if (chain_done(skip, c)) continue;
         const size_t cbase = (size_t)c * g.m;
         LaneVec<V> s4[2], ms[2];
 #pragma unroll
@@ -333,7 +337,8 @@ __global__ void __launch_bounds__(512, 3)     // 40 registers: three CTAs per SM
 clause_gather_smem_kernel(UnitGraphDev g, int Q,
                           const __nv_bfloat16* __restrict__ LIT, int ld_lit,
                           const __nv_bfloat16* __restrict__ SP, int ld_sp, int sp_off,
-                          __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off) {
+                          __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1}) {
+    if (chain_done(skip, (int)blockIdx.x)) return;     // the whole CTA works on one chain
     using T = __nv_bfloat16;
     constexpr int LPR = W / 8, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -411,7 +416,8 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
                            const __nv_bfloat16* __restrict__ CL4, int ld_cl, int cl_off,
                            const __nv_bfloat16* __restrict__ MSG, int ld_msg,
                            const __nv_bfloat16* __restrict__ QRY, int ld_q,
-                           __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off) {
+                           __nv_bfloat16* __restrict__ OUT, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1}) {
+    if (chain_done(skip, (int)blockIdx.x)) return;     // the whole CTA works on one chain
     using T = __nv_bfloat16;
     constexpr int LPR = W / 8, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
@@ -541,7 +547,8 @@ __global__ void __launch_bounds__(512, 2)
 clause_gather_smem_f32_kernel(UnitGraphDev g, int Q,
                               const float* __restrict__ LIT, int ld_lit,
                               const float* __restrict__ SP, int ld_sp, int sp_off,
-                              __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off) {
+                              __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1}) {
+    if (chain_done(skip, (int)blockIdx.x)) return;     // the whole CTA works on one chain
     constexpr int LPR = W / 4, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
     float* tab = reinterpret_cast<float*>(gsm);
@@ -610,7 +617,8 @@ literal_gather_smem_f32_kernel(UnitGraphDev g, int Q,
                                const __nv_bfloat16* __restrict__ CL4_HI, size_t cl_plane, int ld_cl, int cl_off,
                                const float* __restrict__ MSG, int ld_msg,
                                const float* __restrict__ QRY, int ld_q,
-                               __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off) {
+                               __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1}) {
+    if (chain_done(skip, (int)blockIdx.x)) return;     // the whole CTA works on one chain
     constexpr int LPR = W / 4, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
     float* tab = reinterpret_cast<float*>(gsm);
@@ -719,7 +727,8 @@ __global__ void __launch_bounds__(512, 3)
 clause_gather_smem_f32x2_kernel(UnitGraphDev g, int Q,
                                 const float* __restrict__ LIT, int ld_lit,
                                 const float* __restrict__ SP, int ld_sp, int sp_off,
-                                __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off) {
+                                __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1}) {
+    if (chain_done(skip, (int)blockIdx.x)) return;     // the whole CTA works on one chain
     constexpr int LPR = W / 4, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
     float* t_lit = reinterpret_cast<float*>(gsm);

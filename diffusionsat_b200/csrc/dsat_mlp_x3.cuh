@@ -58,6 +58,9 @@ struct X3Params {
     int out_mode;          // OUT_F32: out0 = fp32 [rows, ld_out]; OUT_SPLIT: out0 / out1 = bf16 hi / lo planes [rows, ld_out]
     void* out0; void* out1; int ld_out;
     long long* prof;       // optional [8] cycle counters of CTA 0's issue warp (nullptr = off)
+    // early exit (reference model/query_sat.py:330-338): rows of chain c belong to early-exit group c / chains_per_group;
+    // a work unit all of whose rows belong to finished groups is skipped by every warp role (nullptr = never skip)
+    const int* done; int rows_per_chain, chains_per_group;
 };
 
 // v -> (hi, lo) bf16 pairs of two neighbouring values (dsat_common.cuh)
@@ -201,11 +204,25 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int nt = unit0 < n_units ? (n_units - unit0 + unit_stride - 1) / unit_stride : 0;
     auto tile_of = [&](int j) { const int u = (unit0 + j * unit_stride) / G; return PAIR ? 2 * u + (int)rank : u; };
     auto group_of = [&](int j) { return (unit0 + j * unit_stride) % G; };
+    // every role evaluates the same predicate on the same (macro) tile, so the rings and the accumulator parities, which
+    // count PROCESSED units, stay in step; `done` is written by an earlier kernel and constant during this one
+    auto unit_done = [&](int j) -> bool {
+        if (p.done == nullptr) return false;
+        const int u = (unit0 + j * unit_stride) / G;
+        const int r0 = (PAIR ? 2 * u : u) * BLOCK_M;
+        int r1 = r0 + (PAIR ? 2 * BLOCK_M : BLOCK_M);
+        r1 = (r1 < p.rows ? r1 : p.rows) - 1;
+        const int g0 = (r0 / p.rows_per_chain) / p.chains_per_group, g1 = (r1 / p.rows_per_chain) / p.chains_per_group;
+        for (int g = g0; g <= g1; ++g)
+            if (__ldg(p.done + g) == 0) return false;
+        return true;
+    };
 
     if (warp == 0) {
         if (lane == 0) {   // ================================ TMA producer
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
             for (int j = 0; j < nt; ++j) {
+                if (unit_done(j)) continue;
                 const int tile = tile_of(j), grp = group_of(j);
                 for (int l = 0; l < L; ++l) {
                     const X3Layer& ly = p.layer[l];
@@ -267,11 +284,13 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 }
             };
 #define X3_WAIT(acc_t, call) do { if (timing) { const long long t0__ = clock64(); call; acc_t += clock64() - t0__; } else { call; } } while (0)
-            for (int j = 0; j < nt; ++j)
+            int jp = 0;         // processed units
+            for (int j = 0; j < nt; ++j) {
+                if (unit_done(j)) continue;
                 for (int l = 0; l < L; ++l) {
-                    const int g = j * L + l, buf = g & 1, use = g >> 1;
+                    const int g = jp * L + l, buf = g & 1, use = g >> 1;
                     X3_WAIT(t_wait_acc, mbar_wait(&tmem_empty[buf], (uint32_t)((use & 1) ^ 1)));
-                    if (l > 0) X3_WAIT(t_wait_h, mbar_wait(h_full, (uint32_t)((j * (L - 1) + (l - 1)) & 1)));
+                    if (l > 0) X3_WAIT(t_wait_h, mbar_wait(h_full, (uint32_t)((jp * (L - 1) + (l - 1)) & 1)));
                     tcgen05_fence_after();
                     const int K = p.layer[l].K, N = p.layer[l].N;
                     const int kbs = (K + BLOCK_K - 1) / BLOCK_K;
@@ -309,6 +328,8 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     }
                     commit(&tmem_full[buf]);
                 }
+                ++jp;
+            }
 #undef X3_WAIT
             if (timing && lane == 0) {
                 p.prof[0] = clock64() - t_begin; p.prof[1] = t_wait_acc; p.prof[2] = t_wait_h; p.prof[3] = t_wait_a; p.prof[4] = t_wait_w;
@@ -328,13 +349,16 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const uint32_t bias_addr0 = smem_u32(bias_s);
         e.stage_addr = (p.stage_in_h ? smem_u32(hid) : smem_u32(stage_all)) + (uint32_t)(warp - 2) * (32 * STAGE_ROW);
         long long t_wait_full = 0, t_hidden = 0, t_final = 0;
+        int jp = -1;
         for (int j = 0; j < nt; ++j) {
+            if (unit_done(j)) continue;
+            ++jp;
             const int tile = tile_of(j), grp = group_of(j);
             e.row_first = (size_t)tile * BLOCK_M + quad * 32;
             e.rows_left = p.rows - (int)e.row_first;
             e.col0 = grp * 256;
             for (int l = 0; l < L; ++l) {
-                const int g = j * L + l, buf = g & 1, use = g >> 1;
+                const int g = jp * L + l, buf = g & 1, use = g >> 1;
                 e.N = p.layer[l].N; e.epi = p.layer[l].epi;
                 e.bl_addr = bias_addr0 + 4u * (uint32_t)(p.layer[l].bias_off + grp * 256);
                 e.lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * 256);

@@ -36,13 +36,15 @@ pairnorm_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_cha
                 TX* __restrict__ PRE, int ld_pre,
                 // split-plane state (fp32-accurate tensor-core path): hi planes + distance to the lo planes, instead of STATE / PRE
                 __nv_bfloat16* STATE_HI = nullptr, size_t state_plane = 0,
-                __nv_bfloat16* __restrict__ PRE_HI = nullptr, size_t pre_plane = 0) {
+                __nv_bfloat16* __restrict__ PRE_HI = nullptr, size_t pre_plane = 0,
+                SkipInfo skip = SkipInfo{nullptr, 1}) {
     constexpr int F = 32 * V;
     __shared__ float red[PN_WARPS][F];
     __shared__ float mean_s[F];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
         const int chain = gid / n_graphs_unit, lg = gid % n_graphs_unit;
+        if (chain_done(skip, chain)) continue;
         const size_t base = (size_t)chain * rows_per_chain;
         const size_t r0 = base + __ldg(seg + lg), r1 = base + __ldg(seg + lg + 1);
         const float wgt = 1.0f / (float)(r1 - r0);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(1024)
 pairnorm_smem_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
                      const float* __restrict__ SRC, int ld_src, int src_off,
                      __nv_bfloat16* STATE_HI, size_t state_plane, int ld_state,
-                     __nv_bfloat16* __restrict__ PRE_HI, size_t pre_plane, int ld_pre) {
+                     __nv_bfloat16* __restrict__ PRE_HI, size_t pre_plane, int ld_pre, SkipInfo skip = SkipInfo{nullptr, 1}) {
     constexpr int F = 32 * V;
     constexpr int PPR = F / 4;                         // 16-byte pieces per row
     extern __shared__ __align__(16) uint8_t pn_smem[];
@@ -147,6 +149,7 @@ pairnorm_smem_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_pe
     float* rows = part + groups * F;                                // [graph rows][F]
     for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
         const int chain = gid / n_graphs_unit, lg = gid % n_graphs_unit;
+        if (chain_done(skip, chain)) continue;
         const size_t base = (size_t)chain * rows_per_chain;
         const size_t r0 = base + __ldg(seg + lg);
         const int nrows = __ldg(seg + lg + 1) - __ldg(seg + lg);
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(PN_WARPS * 32, PN_BF16_CTAS)
 pairnorm_bf16_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_per_chain, int total_graphs,
                      const __nv_bfloat16* __restrict__ SRC, int ld_src, int src_off,
                      __nv_bfloat16* __restrict__ STATE, int ld_state,
-                     __nv_bfloat16* __restrict__ PRE, int ld_pre) {
+                     __nv_bfloat16* __restrict__ PRE, int ld_pre, SkipInfo skip = SkipInfo{nullptr, 1}) {
     constexpr int LPR = F / 8, RPW = 32 / LPR, GROUP = PN_WARPS * RPW;     // rows covered by one load of the whole CTA
     __shared__ float red[PN_WARPS][F];
     __shared__ float mean_s[F];
@@ -229,6 +232,7 @@ pairnorm_bf16_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_pe
     const int sub = lane / LPR, li = lane % LPR;
     for (int gid = blockIdx.x; gid < total_graphs; gid += gridDim.x) {
         const int chain = gid / n_graphs_unit, lg = gid % n_graphs_unit;
+        if (chain_done(skip, chain)) continue;
         const size_t base = (size_t)chain * rows_per_chain;
         const size_t r0 = base + __ldg(seg + lg), r1 = base + __ldg(seg + lg + 1);
         const float wgt = 1.0f / (float)(r1 - r0);
@@ -503,9 +507,11 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
 __global__ void round_noise_kernel(long long n_rows, const float* __restrict__ normals_in /*[n_rows,4] or null*/,
                                    float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
                                    NoiseSource ns, unsigned int round, size_t lo_plane = 0,
-                                   const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr) {
+                                   const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr,
+                                   SkipInfo skip = SkipInfo{nullptr, 1}, int rows_per_chain = 1) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
+    if (chain_done(skip, (int)(r / rows_per_chain))) return;
     if (sp_tab) {
         const StepParams sp = sp_tab[*sp_cur];
         ns.seed = sp.seed; ns.element_offset = sp.element_offset; ns.step = sp.step;

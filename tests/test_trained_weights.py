@@ -44,24 +44,28 @@ def test_fixture_loads_and_oracle_solves_small_formulas():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_vars,n_clauses,chains,group,seed", [(14, 50, 6, 6, 9), (12, 44, 6, 6, 0), (20, 80, 8, 4, 1)])
-def test_cuda_sample_matches_oracle_with_trained_weights(ctx, n_vars, n_clauses, chains, group, seed):
+@pytest.mark.parametrize("precision", ["fp32", "fp32_simt"])
+@pytest.mark.parametrize("n_vars,n_clauses,chains,group,seed", [(14, 50, 6, 6, 9), (12, 44, 6, 6, 0), (20, 80, 8, 4, 1), (16, 60, 300, 3, 2)])
+def test_cuda_sample_matches_oracle_with_trained_weights(ctx, n_vars, n_clauses, chains, group, seed, precision):
     """Bit-exact reverse diffusion under injected noise where formulas DO get satisfied: first-SAT latch, per-group
-    early exit (steps_taken < rounds) and SAT flags all take their non-trivial branches."""
+    early exit (steps_taken < rounds) and SAT flags all take their non-trivial branches.  Groups that exit early are
+    skipped by every later kernel of the model call (tile-wise in the whole-MLP kernels: the 300-chain case has tiles that
+    are skipped, tiles that straddle finished and live groups, and live tiles), so this is also the test of that skipping."""
     from diffusionsat_b200 import _lib
     from diffusionsat_b200.sampler import unpack_assignments
     _, clauses, _ = synth.planted_3sat(n_vars, n_clauses, seed=seed)
     wts = trained()
     steps, rounds = 10, 6
     ctx.set_model(wts)
-    ctx.set_precision(_lib.F32)
+    ctx.set_precision(_lib.PRECISIONS[precision])
     ctx.set_graph(G.build_unit_graph(n_vars, clauses), chains=chains, group_graphs=group)
     noise = H.noise_for(n_vars * chains, rounds, 50 + seed, steps=steps)
     packed, is_sat, latch_step, sat_any = ctx.sample(steps, rounds, uniforms=noise["uniforms"], labels=noise["labels"],
                                                      normals=noise["normals"])
     got = unpack_assignments(packed, n_vars)
     checked = satisfied = 0
-    for g0 in range(0, chains, group):               # the oracle runs one early-exit group (reference batch) at a time
+    oracle_groups = range(0, chains, group) if chains <= 16 else list(range(0, chains, group))[::9]
+    for g0 in oracle_groups:                         # the oracle runs one early-exit group (reference batch) at a time
         rows = slice(g0 * n_vars, (g0 + group) * n_vars)
         sub = dict(uniforms=noise["uniforms"][:, rows], labels=noise["labels"][:, rows], normals=noise["normals"][:, :, rows])
         graph, final, latch, trace = _oracle_run(n_vars, clauses, group, wts, sub, steps, rounds)
@@ -76,7 +80,7 @@ def test_cuda_sample_matches_oracle_with_trained_weights(ctx, n_vars, n_clauses,
             ok = O._satisfiable_py([bool(b) for b in bits], clauses)
             assert bool(is_sat[g0 + c]) == ok
             satisfied += ok
-    assert checked >= chains // 2 and satisfied >= 1
+    assert checked >= (len(oracle_groups) * group) // 2 and satisfied >= 1
 
 
 @pytest.mark.gpu
