@@ -504,6 +504,131 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_uf250(args):
+    """BASELINE configs[2]: SATLIB-style uf250 shape (n=250, m=1065), `--total-chains` (65536) chains in total sharded over the
+    ranks (STRONG scaling), every rank reduces its launches' histograms on the device, one NCCL all-gather + reduce at the end.
+    One step = the whole job; wall clock around the public entry (dist.sample_chains_sharded), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from diffusionsat_b200 import _lib, build, graph, synth, weights
+    from diffusionsat_b200 import dist as D
+    from diffusionsat_b200.graph import chains_per_reference_batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    build.build()
+    n, m = 250, 1065
+    _, clauses = synth.random_3sat(n, m, seed=250)
+    unit = graph.build_unit_graph(n, clauses)
+    batch = chains_per_reference_batch(n, m)          # 12
+    wts = weights.init_weights(seed=1234)
+    ctx = _lib.Context(local_rank)
+    ctx.set_model(wts)
+    ctx.set_precision(_lib.PRECISIONS[args.precision])
+    total = args.total_chains
+    per_launch = args.chains_per_launch or 8184
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: one launch of the launch size (buffers, plans, the captured step)
+    ctx.set_graph(unit, chains=min(per_launch, D.shard_chains(total, world, rank, batch)[1]) or batch, group_graphs=batch)
+    ctx.sample_enqueue(2, ROUNDS, seed=1, chain_offset=0)
+    ctx.synchronize()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    times = []
+    stats = None
+    for i in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        merged, stats = D.sample_chains_sharded(lambda r: ctx, unit, total, batch, n, DIFFUSION_STEPS, ROUNDS, seed=100 + i,
+                                                chains_per_launch=per_launch, return_stats=True)
+        barrier()
+        times.append(time.perf_counter() - t0)
+    clock_info = clocks.stop()
+    t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item()) / args.steps
+    if rank == 0:
+        line = {"metric": "diffusion samples/sec, uf250-shaped 3-SAT n=250 m=1065, %d chains in total" % total,
+                "value": total / secs, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": 1,
+                "ms_per_step": secs * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": PRECISION_DTYPE[args.precision], "data": "synthetic",
+                "config": {"workload": "BASELINE configs[2]: uf250 shape, %d chains sharded over %d GPUs in launches of <= %d, "
+                                       "32 x 32, random-init QuerySAT, early-exit groups of %d, device histogram + NCCL merge"
+                                       % (total, world, per_launch, batch), "precision": args.precision},
+                "e2e": {"value": total / secs, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "api": "dist.sample_chains_sharded (host formula in, merged {int: count} out)"},
+                "rank0": stats, "clocks": clock_info, "histogram_size": len(merged)}
+        _RESTORE_STDOUT()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_mixed(args):
+    """BASELINE configs[3]: training-shape forward of mixed k-SAT formulas packed into reference batches (<= 20000 nodes), the
+    batches dealt to the ranks, logits gathered on rank 0 (dist.forward_formulas_sharded).  Metric: formulas per second."""
+    import torch
+    import torch.distributed as dist
+    from diffusionsat_b200 import _lib, build, synth, weights
+    from diffusionsat_b200 import dist as D
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    build.build()
+    rng = np.random.default_rng(0)
+    formulas = []
+    for i in range(args.formulas):          # n ~ U[3,100], k = {1 w.p. .3 | 2} + Geom(.4) (data/k_sat.py:45-46), ratio ~ 4.3
+        nv = int(rng.integers(3, 101))
+        formulas.append(synth.random_ksat_mixed(nv, max(1, int(4.3 * nv)), seed=1000 + i))
+    ctx = _lib.Context(local_rank)
+    ctx.set_model(weights.init_weights(seed=1234))
+    ctx.set_precision(_lib.PRECISIONS[args.precision])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    D.forward_formulas_sharded(lambda r: ctx, formulas[:200], 0.5, rounds=ROUNDS, seed=0)       # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = D.forward_formulas_sharded(lambda r: ctx, formulas, 0.5, rounds=ROUNDS, seed=1 + i)
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item()) / args.steps
+    if rank == 0:
+        batches = D.pack_batches(formulas)
+        nodes = sum(2 * nv + len(cl) for nv, cl in formulas)
+        line = {"metric": "training-shape forward, mixed k-SAT formulas/sec", "value": len(formulas) / secs, "unit": "formulas/s",
+                "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": secs * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": PRECISION_DTYPE[args.precision], "data": "synthetic",
+                "config": {"workload": "BASELINE configs[3]: %d mixed k-SAT formulas (n ~ U[3,100]) = %d nodes in %d reference batches "
+                                       "of <= 20000 nodes, one model call (32 rounds) per batch, batches dealt to %d GPUs"
+                                       % (len(formulas), nodes, len(batches), world), "precision": args.precision},
+                "nodes_per_s": nodes / secs, "batches": len(batches)}
+        _RESTORE_STDOUT()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -516,6 +641,11 @@ def main():
     ap.add_argument("--single-precision", action="store_true", help="measure only --precision")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--config", default="n100", choices=["n100", "uf250", "mixed"],
+                    help="n100 = BASELINE configs[1] (the bench contract); uf250 = configs[2] strong scaling; mixed = configs[3]")
+    ap.add_argument("--total-chains", type=int, default=65536, help="uf250: chains in total over all GPUs")
+    ap.add_argument("--chains-per-launch", type=int, default=0, help="uf250: chains per launch and GPU (default 8184)")
+    ap.add_argument("--formulas", type=int, default=4000, help="mixed: number of formulas")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-message-pass", action="store_true")
     ap.add_argument("--skip-trained", action="store_true")
@@ -531,6 +661,10 @@ def main():
         os.dup2(saved_stdout, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "uf250":
+        run_uf250(args)
+    elif args.config == "mixed":
+        run_mixed(args)
     else:
         run_ours(args)
 

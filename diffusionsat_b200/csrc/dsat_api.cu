@@ -1781,11 +1781,28 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
 // Cycle breakdown of CTA 0 of one whole-MLP kernel (0 query, 1 literal, 2 clause, 3 update, 4 output): 16 counters,
 // see dsat_mlp_fused.cuh.  The activations must have been produced by a previous round.
 int dsat_profile_fused(dsat_ctx* c, int which, long long* counters16) {
-    if (!c || !counters16 || which < 0 || which > 4) return DSAT_ERR_ARG;
+    if (!c || !counters16 || which < 0 || which > 6) return DSAT_ERR_ARG;
 #ifndef DSAT_WITH_TCGEN05
     return DSAT_ERR_UNSUPPORTED;
 #else
     CK_CUDA(c, cudaSetDevice(c->device));
+    if (use_x3(c)) {    // the seven x3 launches (query, lit 1, lit 2, lit 3, clause, update, output): 8 counters, see dsat_mlp_x3.cuh
+        int rc = ensure_x3_buffers(c);
+        if (rc) return rc;
+        DevBuf<long long> d;
+        CK_CUDA(c, d.alloc(16));
+        CK_CUDA(c, cudaMemsetAsync(d.p, 0, 16 * sizeof(long long), c->stream));
+        x3::X3Mlp f = c->x3[which];
+        f.p.prof = d.p;
+        cudaError_t e = x3::launch_x3(f, c->device, c->sm_count, c->stream);
+        c->launches++;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = dsat_memcpy_sync(counters16, d.p, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+        d.release();
+        CK_CUDA(c, e);
+        return DSAT_OK;
+    }
+    if (which > 4) return DSAT_ERR_ARG;
     int rc = ensure_tc_buffers(c);
     if (rc) return rc;
     CK_ARG(c, c->fused_ready, "fused kernels unavailable");

@@ -130,7 +130,7 @@ __device__ __forceinline__ void epi_final(const Epi& e, const uint32_t (&raw)[32
 }
 
 template <bool PAIR>
-__global__ void __launch_bounds__(fm::MAX_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * 8, 1)      // producer + issuer + at most 8 epilogue warps
 x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_w0, const __grid_constant__ CUtensorMap map_w1,
               const __grid_constant__ CUtensorMap map_w2, X3Params p) {
@@ -204,19 +204,32 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int nt = unit0 < n_units ? (n_units - unit0 + unit_stride - 1) / unit_stride : 0;
     auto tile_of = [&](int j) { const int u = (unit0 + j * unit_stride) / G; return PAIR ? 2 * u + (int)rank : u; };
     auto group_of = [&](int j) { return (unit0 + j * unit_stride) % G; };
-    // every role evaluates the same predicate on the same (macro) tile, so the rings and the accumulator parities, which
-    // count PROCESSED units, stay in step; `done` is written by an earlier kernel and constant during this one
-    auto unit_done = [&](int j) -> bool {
-        if (p.done == nullptr) return false;
-        const int u = (unit0 + j * unit_stride) / G;
-        const int r0 = (PAIR ? 2 * u : u) * BLOCK_M;
-        int r1 = r0 + (PAIR ? 2 * BLOCK_M : BLOCK_M);
-        r1 = (r1 < p.rows ? r1 : p.rows) - 1;
-        const int g0 = (r0 / p.rows_per_chain) / p.chains_per_group, g1 = (r1 / p.rows_per_chain) / p.chains_per_group;
-        for (int g = g0; g <= g1; ++g)
-            if (__ldg(p.done + g) == 0) return false;
-        return true;
-    };
+    // Units all of whose rows belong to finished early-exit groups are skipped.  Every role must take the same decision (the
+    // rings and the accumulator parities count PROCESSED units), and nobody should wait for an L2 round trip per unit on its
+    // issue path: the flags of this CTA's units are evaluated once, by all threads, into shared memory (`done` is written by
+    // an earlier kernel and constant during this one).  More than SKIP_UNITS units per CTA: no skipping in this launch.
+    constexpr int SKIP_UNITS = 1024;
+    uint32_t* skip_bits = reinterpret_cast<uint32_t*>(tail + 384);      // 128 spare bytes of the barrier block
+    const bool skipping = p.done != nullptr && nt <= SKIP_UNITS;
+    if (skipping) {
+        for (int base = 32 * warp; base < nt; base += (int)blockDim.x) {      // one unit per thread, one 32-bit word per warp pass
+            const int j = base + lane;
+            bool all = false;
+            if (j < nt) {
+                const int u = (unit0 + j * unit_stride) / G;
+                const int r0 = (PAIR ? 2 * u : u) * BLOCK_M;
+                int r1 = r0 + (PAIR ? 2 * BLOCK_M : BLOCK_M);
+                r1 = (r1 < p.rows ? r1 : p.rows) - 1;
+                const int g0 = (r0 / p.rows_per_chain) / p.chains_per_group, g1 = (r1 / p.rows_per_chain) / p.chains_per_group;
+                all = true;
+                for (int g = g0; g <= g1 && all; ++g) all = __ldg(p.done + g) != 0;
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, all);
+            if (lane == 0) skip_bits[base >> 5] = bits;
+        }
+        __syncthreads();
+    }
+    auto unit_done = [&](int j) -> bool { return skipping && ((skip_bits[j >> 5] >> (j & 31)) & 1u) != 0; };
 
     if (warp == 0) {
         if (lane == 0) {   // ================================ TMA producer

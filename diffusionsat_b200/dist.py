@@ -126,20 +126,115 @@ def merge_histograms(keys: np.ndarray, counts: np.ndarray, n_bits: int, device=N
 
 
 def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_chains: int, n_bits: int,
-                          steps: int = 32, rounds: int = 32, seed: int = 0, group=None):
+                          steps: int = 32, rounds: int = 32, seed: int = 0, group=None, chains_per_launch: int | None = None,
+                          return_stats: bool = False):
     """One process per GPU: every rank samples its contiguous block of the `total_chains` global chains
-    (whole reference batches), then the histograms are merged on rank 0.  `make_context(local_rank)` returns a
-    ready `_lib.Context` (model set).  Returns the merged ``{int: count}`` on rank 0, ``None`` elsewhere.
-    The result does not depend on the number of ranks: noise is keyed by the global chain id."""
+    (whole reference batches) in launches of at most `chains_per_launch` chains, reduces every launch's histogram on the
+    device, then the ranks' tables are merged on rank 0.  `make_context(local_rank)` returns a ready `_lib.Context`
+    (model set).  Returns the merged ``{int: count}`` on rank 0, ``None`` elsewhere.
+    The result does not depend on the number of ranks or on the launch size: noise is keyed by the global chain id and
+    launches hold whole reference batches."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     offset, count = shard_chains(total_chains, world, rank, multiple_of=batch_chains)
     ctx = make_context(rank)
-    if count > 0:
-        ctx.set_graph(unit_graph, chains=count, group_graphs=batch_chains)
-        ctx.sample_enqueue(steps, rounds, seed=seed, chain_offset=offset)
-        keys, counts, _ = ctx.hist_reduce()
+    words = -(-n_bits // 64)
+    tables, n_sat, launches = [], 0, 0
+    per_launch = count if not chains_per_launch else max(batch_chains, chains_per_launch // batch_chains * batch_chains)
+    done = 0
+    while done < count:
+        now = min(per_launch, count - done)
+        if ctx.graph is not unit_graph or ctx.chains != now:
+            ctx.set_graph(unit_graph, chains=now, group_graphs=batch_chains)
+        ctx.sample_enqueue(steps, rounds, seed=seed, chain_offset=offset + done)
+        keys, counts, sat = ctx.hist_reduce()
+        tables.append((keys, counts))
+        n_sat += sat
+        done += now
+        launches += 1
+    keys, counts = merge_tables(tables, words)
+    merged = merge_histograms(keys, counts, n_bits, group=group)
+    if return_stats:
+        return merged, {"chains": count, "offset": offset, "sat": n_sat, "launches": launches}
+    return merged
+
+
+# --------------------------------------------------------------------------- formulas sharded over ranks
+def pack_batches(formulas, max_nodes: int = 20000):
+    """Reference batches of a list of ``(n_vars, clauses)`` formulas: greedy packing in the given order while the node
+    total ``sum(2n + m)`` stays <= ``max_nodes`` (reference ``data/dimac.py:172-174,267-293``; the first formula of a
+    batch always fits).  The reference drops the formula that overflows a batch (``:281-287``, SURVEY Appendix A.16);
+    here it opens the next batch, so no formula is lost.  Returns a list of lists of formula indices."""
+    batches, cur, nodes = [], [], 0
+    for i, (n_vars, clauses) in enumerate(formulas):
+        cost = 2 * int(n_vars) + len(clauses)
+        if cur and nodes + cost > max_nodes:
+            batches.append(cur)
+            cur, nodes = [], 0
+        cur.append(i)
+        nodes += cost
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+def forward_formulas_sharded(make_context, formulas, noise_scale: float, rounds: int = 32, seed: int = 0,
+                             max_nodes: int = 20000, group=None, dst: int = 0):
+    """Training-shape forward of a set of mixed formulas (BASELINE configs[3]): the formulas are packed into reference
+    batches, batch b goes to rank ``b % world``, every batch is ONE disjoint-union graph and one model call (reference
+    ``QuerySAT.call``, ``model/query_sat.py:133-184`` on the batches of ``data/dimac.py:213-293``), and the per-variable
+    logits are gathered on rank ``dst`` (outputs are disjoint: no reduction).  Noise and the noisy inputs are keyed by
+    ``(seed, batch index)``, so the result does not depend on the number of ranks.
+    Returns on ``dst`` ``(logits per formula [list of float32 arrays], steps_taken per batch [int array])``."""
+    from .graph import build_union_graph
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    batches = pack_batches(formulas, max_nodes)
+    sizes = [sum(int(formulas[i][0]) for i in b) for b in batches]
+    ctx = make_context(rank)
+    mine = {}
+    for b in range(rank, len(batches), world):
+        unit = build_union_graph([formulas[i] for i in batches[b]])
+        ctx.set_graph(unit, chains=1, group_graphs=0)            # the whole batch is one early-exit group
+        bits = np.random.default_rng([seed, b]).integers(0, 2, unit.n_vars).astype(np.float32)
+        noisy = np.stack([bits, 1.0 - bits], axis=1)
+        pred, steps, _ = ctx.model_call(noise_scale, noisy, rounds=rounds, seed=seed + 7919 * (b + 1))
+        mine[b] = (pred, int(steps[0]))
+    if world == 1:
+        flat = {b: mine[b] for b in mine}
     else:
-        words = -(-n_bits // 64)
-        keys, counts = np.zeros((0, words), dtype=np.uint64), np.zeros(0, dtype=np.int64)
-    return merge_histograms(keys, counts, n_bits, group=group)
+        backend = dist.get_backend(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        per_rank = [sum(sizes[b] + 1 for b in range(r, len(batches), world)) for r in range(world)]
+        width = max(max(per_rank), 1)
+        buf = torch.zeros(width, dtype=torch.float32, device=device)
+        pos = 0
+        for b in range(rank, len(batches), world):                # [steps_taken, logits...] per batch, back to back
+            pred, steps = mine[b]
+            buf[pos] = float(steps)
+            buf[pos + 1:pos + 1 + sizes[b]] = torch.from_numpy(pred).to(device)
+            pos += 1 + sizes[b]
+        gathered = torch.empty(world * width, dtype=torch.float32, device=device)
+        if backend == "nccl":
+            dist.all_gather_into_tensor(gathered, buf, group=group)
+        else:
+            dist.all_gather(list(gathered.view(world, width).unbind(0)), buf, group=group)
+        if rank != dst:
+            return None
+        host = gathered.cpu().numpy().reshape(world, width)
+        flat = {}
+        for r in range(world):
+            pos = 0
+            for b in range(r, len(batches), world):
+                flat[b] = (host[r, pos + 1:pos + 1 + sizes[b]].copy(), int(host[r, pos]))
+                pos += 1 + sizes[b]
+    logits = [None] * len(formulas)
+    steps_taken = np.zeros(len(batches), dtype=np.int32)
+    for b, idxs in enumerate(batches):
+        pred, steps_taken[b] = flat[b]
+        pos = 0
+        for i in idxs:
+            n = int(formulas[i][0])
+            logits[i] = pred[pos:pos + n]
+            pos += n
+    return logits, steps_taken

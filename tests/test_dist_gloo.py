@@ -76,3 +76,17 @@ def test_local_histogram_limit_and_empty():
     keys, counts = D.local_histogram(packed, np.zeros(12, dtype=np.uint8))
     assert keys.shape == (0, 2) and counts.shape == (0,)
     assert D.merge_histograms(keys, counts, 70) == {}
+
+
+def test_pack_batches_follows_the_node_budget_and_loses_nothing():
+    from diffusionsat_b200 import synth
+    rng = np.random.default_rng(2)
+    formulas = [synth.random_ksat_mixed(int(rng.integers(3, 100)), int(rng.integers(5, 400)), seed=i) for i in range(300)]
+    batches = D.pack_batches(formulas, 20000)
+    assert [i for b in batches for i in b] == list(range(300))          # order kept, nothing dropped
+    cost = lambda i: 2 * formulas[i][0] + len(formulas[i][1])
+    for k, b in enumerate(batches):
+        assert sum(cost(i) for i in b) <= 20000
+        if k + 1 < len(batches):                                         # greedy: the next formula did not fit
+            assert sum(cost(i) for i in b) + cost(batches[k + 1][0]) > 20000
+    assert D.pack_batches([(5, [[1, 2]])] * 3, max_nodes=1) == [[0], [1], [2]]      # a formula always fits an empty batch

@@ -134,7 +134,13 @@ n_vars, clauses, _ = synth.planted_3sat(14, 50, seed=9)
 unit = G.build_unit_graph(n_vars, clauses)
 def make(_):
     c = _lib.Context(dev); c.set_model(load_weights(%(fixture)r)); c.set_precision("bf16"); return c
-merged = D.sample_chains_sharded(make, unit, total_chains=410, batch_chains=20, n_bits=n_vars, steps=8, rounds=6, seed=21)
+if sys.argv[3] == "chains":
+    merged = D.sample_chains_sharded(make, unit, total_chains=410, batch_chains=20, n_bits=n_vars, steps=8, rounds=6, seed=21,
+                                     chains_per_launch=100)
+else:
+    rng = np.random.default_rng(0)
+    formulas = [synth.random_ksat_mixed(int(rng.integers(3, 60)), int(rng.integers(10, 200)), seed=i) for i in range(70)]
+    merged = D.forward_formulas_sharded(make, formulas, 0.4, rounds=6, seed=3, max_nodes=2500)
 if rank == 0:
     pickle.dump(merged, open(out, "wb"))
 else:
@@ -143,7 +149,7 @@ dist.destroy_process_group()
 """
 
 
-def test_two_rank_histogram_equals_single_gpu_histogram(tmp_path):
+def _run_two_ranks(tmp_path, mode):
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % {"root": ROOT, "fixture": FIXTURE})
@@ -152,11 +158,35 @@ def test_two_rank_histogram_equals_single_gpu_histogram(tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(script), backend, str(out)]
+           "--master-port", str(port), str(script), backend, str(out), mode]
     proc = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert proc.returncode == 0, proc.stdout[-3000:]
     import pickle
-    merged = pickle.load(open(out, "rb"))
+    return pickle.load(open(out, "rb"))
+
+
+def test_two_rank_formula_sharding_equals_single_gpu(tmp_path):
+    """BASELINE configs[3]: mixed k-SAT formulas packed into reference batches, batches dealt to the ranks, logits gathered
+    on rank 0 -- equal to the single-process result (noise keyed by the batch, not by the rank)."""
+    logits2, steps2 = _run_two_ranks(tmp_path, "formulas")
+    rng = np.random.default_rng(0)
+    formulas = [synth.random_ksat_mixed(int(rng.integers(3, 60)), int(rng.integers(10, 200)), seed=i) for i in range(70)]
+
+    def make(_):
+        c = _lib.Context(0)
+        c.set_model(load_weights(FIXTURE))
+        c.set_precision("bf16")
+        return c
+    logits1, steps1 = D.forward_formulas_sharded(make, formulas, 0.4, rounds=6, seed=3, max_nodes=2500)
+    assert len(D.pack_batches(formulas, 2500)) >= 4
+    np.testing.assert_array_equal(steps1, steps2)
+    for a, b, (n, _) in zip(logits1, logits2, formulas):
+        assert a.shape == (n,) and np.isfinite(a).all()
+        np.testing.assert_array_equal(a, b)
+
+
+def test_two_rank_histogram_equals_single_gpu_histogram(tmp_path):
+    merged = _run_two_ranks(tmp_path, "chains")
     # the same 410 global chains on one GPU in one launch
     n_vars, clauses, _ = synth.planted_3sat(14, 50, seed=9)
     c = _lib.Context(0)
