@@ -530,7 +530,7 @@ def run_uf250(args):
     ctx.set_model(wts)
     ctx.set_precision(_lib.PRECISIONS[args.precision])
     total = args.total_chains
-    per_launch = args.chains_per_launch or 8184
+    per_launch = args.chains_per_launch or 8400
 
     def barrier():
         if world > 1:
@@ -644,7 +644,7 @@ def main():
     ap.add_argument("--config", default="n100", choices=["n100", "uf250", "mixed"],
                     help="n100 = BASELINE configs[1] (the bench contract); uf250 = configs[2] strong scaling; mixed = configs[3]")
     ap.add_argument("--total-chains", type=int, default=65536, help="uf250: chains in total over all GPUs")
-    ap.add_argument("--chains-per-launch", type=int, default=0, help="uf250: chains per launch and GPU (default 8184)")
+    ap.add_argument("--chains-per-launch", type=int, default=0, help="uf250: cap on the chains per launch and GPU (default 8400)")
     ap.add_argument("--formulas", type=int, default=4000, help="mixed: number of formulas")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-message-pass", action="store_true")

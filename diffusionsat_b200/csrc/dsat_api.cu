@@ -157,11 +157,20 @@ struct dsat_ctx {
     int ldh1() const { return HQ + HL; }
 };
 
+#ifdef DSAT_ASSERT
+static int* g_assert_host = nullptr;     // host view of g_dsat_assert_slot (mapped memory: readable after a trap)
+static std::string assert_note() {
+    return g_assert_host && g_assert_host[0] ? " [DSAT_ASSERT failed at line " + std::to_string(g_assert_host[0]) + " of a kernel header]" : "";
+}
+#else
+static std::string assert_note() { return ""; }
+#endif
+
 #define CK_CUDA(ctx, expr)                                                              \
     do {                                                                                \
         cudaError_t e__ = (expr);                                                       \
         if (e__ != cudaSuccess) {                                                       \
-            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);           \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__) + assert_note(); \
             return DSAT_ERR_CUDA;                                                       \
         }                                                                               \
     } while (0)
@@ -547,6 +556,8 @@ int ensure_x3_buffers(dsat_ctx* c) {
             p.rows_per_chain = rows == c->Mt ? c->m : c->n;
         }
         f.pair_mode = ((pair_mask >> which) & 1) != 0;
+        static const int epi4_mask = getenv("DSAT_X3_EPI4") ? atoi(getenv("DSAT_X3_EPI4")) : 0;
+        f.four_epilogue_warps = ((epi4_mask >> which) & 1) != 0;
         if (!tc::make_bf16_map(&f.map_a_hi, a_hi, rows, k, lda, p.a_box_rows)) return false;
         if (!tc::make_bf16_map(&f.map_a_lo, a_hi + a_plane, rows, k, lda, p.a_box_rows)) return false;
         int i = 0;
@@ -1206,6 +1217,14 @@ int dsat_create(int device, dsat_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (configure_kernels_for_device() != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
+#ifdef DSAT_ASSERT
+    if (!g_assert_host && cudaHostAlloc(reinterpret_cast<void**>(&g_assert_host), 2 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+        g_assert_host[0] = g_assert_host[1] = 0;
+        int* dev_view = nullptr;
+        if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_view), g_assert_host, 0) == cudaSuccess)
+            cudaMemcpyToSymbol(g_dsat_assert_slot, &dev_view, sizeof(dev_view));
+    }
+#endif
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return DSAT_ERR_CUDA; }
     c->stream = c->own_stream;
     cudaEventCreate(&c->ev0);

@@ -3,10 +3,30 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define DSAT_AUX_PAD 16      // aux columns of v1 (9 used: normal4, noisy2, noise_scale, denoised2)
 #define DSAT_LOGIT_MAPS 8    // reference model/query_sat.py:99
 #define DSAT_LOGIT_PAD 16
+
+// Debug build (`DSAT_NVCC_FLAGS=-DDSAT_ASSERT python -m diffusionsat_b200.build --force`): bounds checks on every index the
+// gathers read and on the tile / row ranges of the whole-MLP kernels; a violated check traps (the launch fails with
+// cudaErrorLaunchFailure instead of reading or writing out of range).  compute-sanitizer is not available on this pool; the
+// GPU test-suite is run once per round under this build instead (profiles/r2_assert_build.txt).
+#ifdef DSAT_ASSERT
+// a trap discards the device printf buffer and poisons the context, so the failing check leaves its line number in
+// host-mapped memory first (dsat_create allocates it; CK_CUDA appends it to the error message)
+__device__ int* g_dsat_assert_slot = nullptr;
+#define DSAT_CHECK(cond)                                                                    \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            if (g_dsat_assert_slot) { g_dsat_assert_slot[0] = __LINE__; __threadfence_system(); } \
+            __trap();                                                                       \
+        }                                                                                   \
+    } while (0)
+#else
+#define DSAT_CHECK(cond) do { } while (0)
+#endif
 
 namespace dsat {
 

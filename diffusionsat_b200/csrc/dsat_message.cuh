@@ -80,6 +80,7 @@ clause_gather_kernel(UnitGraphDev g, int chains,
         const int c = cur.c, j = cur.pos;
         if (chain_done(skip, c)) continue;
         const int e0 = __ldg(g.cl_rowptr + j), e1 = __ldg(g.cl_rowptr + j + 1);
+        DSAT_CHECK(j >= 0 && j < g.m && 0 <= e0 && e0 <= e1 && e1 <= g.nnz);
         const size_t vbase = (size_t)c * g.n;
         LaneVec<V> acc_l, acc_s;
 #pragma unroll
@@ -87,6 +88,7 @@ clause_gather_kernel(UnitGraphDev g, int chains,
         int e = e0;
         for (; e + 3 <= e1; e += 3) {   // 3-SAT fast path: three edges in flight
             int c0 = __ldg(g.cl_lit + e), c1 = __ldg(g.cl_lit + e + 1), c2 = __ldg(g.cl_lit + e + 2);
+            DSAT_CHECK((unsigned)c0 < 2u * g.n && (unsigned)c1 < 2u * g.n && (unsigned)c2 < 2u * g.n);
             const size_t r0 = vbase + (c0 >> 1), r1 = vbase + (c1 >> 1), r2 = vbase + (c2 >> 1);
             LaneVec<V> l0 = lane_load_t<V, T>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
             LaneVec<V> l1 = lane_load_t<V, T>(LIT + r1 * ld_lit + (c1 & 1) * Q, lane);
@@ -102,6 +104,7 @@ clause_gather_kernel(UnitGraphDev g, int chains,
         }
         for (; e < e1; ++e) {
             int c0 = __ldg(g.cl_lit + e);
+            DSAT_CHECK((unsigned)c0 < 2u * g.n);
             const size_t r0 = vbase + (c0 >> 1);
             LaneVec<V> l0 = lane_load_t<V, T>(LIT + r0 * ld_lit + (c0 & 1) * Q, lane);
             LaneVec<V> s0 = lane_load_t<V, T>(SP + r0 * ld_sp + sp_off + (c0 & 1) * Q, lane);
@@ -158,8 +161,10 @@ literal_gather_kernel(UnitGraphDev g, int chains,
             for (int i = 0; i < V; ++i) { s4[sgn].v[i] = 0.f; ms[sgn].v[i] = 0.f; }
             const int code = 2 * v + sgn;
             const int e0 = __ldg(g.lit_rowptr + code), e1 = __ldg(g.lit_rowptr + code + 1);
+            DSAT_CHECK(code < 2 * g.n && 0 <= e0 && e0 <= e1 && e1 <= g.nnz);
             int e = e0;
             for (; e + 2 <= e1; e += 2) {
+                DSAT_CHECK((unsigned)__ldg(g.lit_clause + e) < (unsigned)g.m && (unsigned)__ldg(g.lit_clause + e + 1) < (unsigned)g.m);
                 const size_t j0 = cbase + __ldg(g.lit_clause + e), j1 = cbase + __ldg(g.lit_clause + e + 1);
                 LaneVec<V> a0 = CL4_HI ? lane_load_split_rw<V>(CL4_HI + j0 * ld_cl + cl_off, cl_plane, lane)
                                        : lane_load_t<V, T>(CL4 + j0 * ld_cl + cl_off, lane);
@@ -382,6 +387,7 @@ clause_gather_smem_kernel(UnitGraphDev g, int Q,
             const int c0 = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
             const int c1 = SI ? (int)s_idx[g.cl_col_off + e + 1] : __ldg(g.cl_lit + e + 1);
             const int c2 = SI ? (int)s_idx[g.cl_col_off + e + 2] : __ldg(g.cl_lit + e + 2);
+            DSAT_CHECK((unsigned)c0 < 2u * g.n && (unsigned)c1 < 2u * g.n && (unsigned)c2 < 2u * g.n && e + 3 <= g.nnz);
             const uint4 l0 = reinterpret_cast<const uint4*>(t_lit + (size_t)c0 * W)[li];
             const uint4 p0 = reinterpret_cast<const uint4*>(t_sp + (size_t)c0 * W)[li];
             const uint4 l1 = reinterpret_cast<const uint4*>(t_lit + (size_t)c1 * W)[li];
@@ -481,6 +487,7 @@ literal_gather_smem_kernel(UnitGraphDev g, int Q,
             int e = e0;
             for (; e + 3 <= e1; e += 3) {      // three entries = six table reads in flight
                 const int j0 = col(e), j1 = col(e + 1), j2 = col(e + 2);
+                DSAT_CHECK((unsigned)j0 < (unsigned)g.m && (unsigned)j1 < (unsigned)g.m && (unsigned)j2 < (unsigned)g.m && e + 3 <= g.nnz);
                 const uint4 a0 = reinterpret_cast<const uint4*>(t_cl + (size_t)j0 * W)[li];
                 const uint4 b0 = reinterpret_cast<const uint4*>(t_ms + (size_t)j0 * W)[li];
                 const uint4 a1 = reinterpret_cast<const uint4*>(t_cl + (size_t)j1 * W)[li];
@@ -587,6 +594,7 @@ clause_gather_smem_f32_kernel(UnitGraphDev g, int Q,
             const int c0 = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
             const int c1 = SI ? (int)s_idx[g.cl_col_off + e + 1] : __ldg(g.cl_lit + e + 1);
             const int c2 = SI ? (int)s_idx[g.cl_col_off + e + 2] : __ldg(g.cl_lit + e + 2);
+            DSAT_CHECK((unsigned)c0 < 2u * g.n && (unsigned)c1 < 2u * g.n && (unsigned)c2 < 2u * g.n && e + 3 <= g.nnz);
             const float4 l0 = reinterpret_cast<const float4*>(tab + (size_t)c0 * W)[li];
             const float4 l1 = reinterpret_cast<const float4*>(tab + (size_t)c1 * W)[li];
             const float4 l2 = reinterpret_cast<const float4*>(tab + (size_t)c2 * W)[li];
@@ -689,6 +697,8 @@ literal_gather_smem_f32_kernel(UnitGraphDev g, int Q,
             int e = e0;
             for (; e + 4 <= e1; e += 4) {
                 const int j0 = col(e), j1 = col(e + 1), j2 = col(e + 2), j3 = col(e + 3);
+                DSAT_CHECK((unsigned)j0 < (unsigned)g.m && (unsigned)j1 < (unsigned)g.m && (unsigned)j2 < (unsigned)g.m &&
+                           (unsigned)j3 < (unsigned)g.m && e + 4 <= g.nnz);
                 const float4 a0 = reinterpret_cast<const float4*>(tab + (size_t)j0 * W)[li];
                 const float4 a1 = reinterpret_cast<const float4*>(tab + (size_t)j1 * W)[li];
                 const float4 a2 = reinterpret_cast<const float4*>(tab + (size_t)j2 * W)[li];
@@ -768,6 +778,7 @@ clause_gather_smem_f32x2_kernel(UnitGraphDev g, int Q,
             const int c0 = SI ? (int)s_idx[g.cl_col_off + e] : __ldg(g.cl_lit + e);
             const int c1 = SI ? (int)s_idx[g.cl_col_off + e + 1] : __ldg(g.cl_lit + e + 1);
             const int c2 = SI ? (int)s_idx[g.cl_col_off + e + 2] : __ldg(g.cl_lit + e + 2);
+            DSAT_CHECK((unsigned)c0 < 2u * g.n && (unsigned)c1 < 2u * g.n && (unsigned)c2 < 2u * g.n && e + 3 <= g.nnz);
             const float4 l0 = reinterpret_cast<const float4*>(t_lit + (size_t)c0 * W)[li];
             const float4 p0 = reinterpret_cast<const float4*>(t_sp + (size_t)c0 * W)[li];
             const float4 l1 = reinterpret_cast<const float4*>(t_lit + (size_t)c1 * W)[li];

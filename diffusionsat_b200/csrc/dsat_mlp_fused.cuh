@@ -612,6 +612,7 @@ fused_mlp_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     const Step st = make_step(j0, s, l);
                     e.row_first = (size_t)st.tile * BLOCK_M + quad * 32;
                     e.rows_left = p.rows - (int)e.row_first;
+                    DSAT_CHECK(st.tile >= 0 && st.tile <= p.n_tiles);
                     e.ah_addr = smem_u32(ah + (size_t)st.hidx * h_bytes);
                     e.stage_addr = (p.stage_in_h ? e.ah_addr + (uint32_t)p.stage_off : smem_u32(stage_all)) + stage_off;
                     e.N = p.layer[l].N; e.epi = p.layer[l].epi;

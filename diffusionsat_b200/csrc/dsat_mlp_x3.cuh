@@ -186,7 +186,7 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
     }
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 2 + p.epi_warps) {
         for (int l = 0; l < p.n_layers; ++l)
             for (int i = threadIdx.x - 64; i < p.layer[l].n_total; i += epi_threads) bias_s[p.layer[l].bias_off + i] = __ldg(p.layer[l].bias + i);
     }
@@ -348,7 +348,7 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 p.prof[0] = clock64() - t_begin; p.prof[1] = t_wait_acc; p.prof[2] = t_wait_h; p.prof[3] = t_wait_a; p.prof[4] = t_wait_w;
             }
         }
-    } else {               // ================================ epilogue warps
+    } else if (warp < 2 + p.epi_warps) {               // ================================ epilogue warps
         const int quad = warp & 3;
         Epi e;
         e.r = quad * 32 + lane;
@@ -367,6 +367,7 @@ x3_mlp_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             if (unit_done(j)) continue;
             ++jp;
             const int tile = tile_of(j), grp = group_of(j);
+            DSAT_CHECK(tile >= 0 && (tile < p.n_tiles || (PAIR && tile == p.n_tiles)) && grp >= 0 && grp < G);
             e.row_first = (size_t)tile * BLOCK_M + quad * 32;
             e.rows_left = p.rows - (int)e.row_first;
             e.col0 = grp * 256;
@@ -447,6 +448,7 @@ struct X3Mlp {
     X3Params p;
     int smem_bytes = 0;
     bool pair_mode = false;     // request the CTA-pair instantiation
+    bool four_epilogue_warps = false;   // one epilogue warp per TMEM lane quadrant instead of two
     bool ready = false;
 };
 
@@ -474,6 +476,7 @@ inline bool plan_x3(X3Mlp& f) {
     p.n_tiles = ceil_div(p.rows, BLOCK_M);
     p.w_slot_bytes = ((pair ? max_n / 2 : max_n) * BLOCK_K * 2 + 1023) / 1024 * 1024;
     for (int ew : {8, 4}) {
+        if (ew == 8 && f.four_epilogue_warps) continue;
         const int stage_bytes = ew * 32 * STAGE_ROW;
         const int in_h = 2 * h_blocks * BLK_BYTES >= stage_bytes;
         const int fixed = pad + 2 * h_blocks * BLK_BYTES + (in_h ? 0 : stage_bytes) + BAR_BYTES + bias_total * 4;
@@ -481,13 +484,23 @@ inline bool plan_x3(X3Mlp& f) {
         int a = 2, w = 2;
         if (avail < a * BLK_BYTES + w * p.w_slot_bytes) continue;
         avail -= a * BLK_BYTES + w * p.w_slot_bytes;
-        // grow the rings in turn (the input comes from HBM, the weights from L2: the input ring first)
-        while (true) {
-            bool grew = false;
-            if (a <= w && a < MAX_RING && avail >= BLK_BYTES) { ++a; avail -= BLK_BYTES; grew = true; }
-            else if (w < MAX_RING && avail >= p.w_slot_bytes) { ++w; avail -= p.w_slot_bytes; grew = true; }
-            else if (a < MAX_RING && avail >= BLK_BYTES) { ++a; avail -= BLK_BYTES; grew = true; }
-            if (!grew) break;
+        if (p.n_layers > 1) {
+            // MLPs with hidden layers have little shared memory left, and their first layer is bound by the latency of the
+            // input stream from HBM (clock64 breakdown at cfg2: the issue warp of the clause / update MLPs waited 36 / 40 %
+            // of its time for input with a 3 + 3 split; 4 + 2: clause 1.60 -> 1.48 ms, update 0.64 -> 0.54 ms).  The weights
+            // come from L2 and are the same for every tile: two slots suffice, the input ring takes the rest (up to a tile).
+            const int a_want = min(MAX_RING, 2 * ((p.layer[0].K + BLOCK_K - 1) / BLOCK_K));
+            while (a < a_want && avail >= BLK_BYTES) { ++a; avail -= BLK_BYTES; }
+            while (w < MAX_RING && avail >= p.w_slot_bytes) { ++w; avail -= p.w_slot_bytes; }
+        } else {
+            // single wide layers: grow the rings in turn (the input comes from HBM, the weights from L2: the input ring first)
+            while (true) {
+                bool grew = false;
+                if (a <= w && a < MAX_RING && avail >= BLK_BYTES) { ++a; avail -= BLK_BYTES; grew = true; }
+                else if (w < MAX_RING && avail >= p.w_slot_bytes) { ++w; avail -= p.w_slot_bytes; grew = true; }
+                else if (a < MAX_RING && avail >= BLK_BYTES) { ++a; avail -= BLK_BYTES; grew = true; }
+                if (!grew) break;
+            }
         }
         const int ea = env_int("DSAT_X3_A_SLOTS", 0), ewn = env_int("DSAT_X3_W_SLOTS", 0);
         if (ea >= 2 && ewn >= 2 && ea <= MAX_RING && ewn <= MAX_RING &&

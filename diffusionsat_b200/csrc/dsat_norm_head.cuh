@@ -154,6 +154,7 @@ pairnorm_smem_kernel(const int* __restrict__ seg, int n_graphs_unit, int rows_pe
         const size_t r0 = base + __ldg(seg + lg);
         const int nrows = __ldg(seg + lg + 1) - __ldg(seg + lg);
         const float wgt = 1.0f / (float)nrows;
+        DSAT_CHECK(nrows > 0 && r0 + nrows <= (size_t)(chain + 1) * rows_per_chain);
         for (int i = tid; i < nrows * PPR; i += blockDim.x) {
             const int r = i / PPR, k = i % PPR;
             cp_async16(rows + (size_t)r * F + 4 * k, SRC + (r0 + r) * ld_src + src_off + 4 * k);

@@ -140,7 +140,11 @@ def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_cha
     ctx = make_context(rank)
     words = -(-n_bits // 64)
     tables, n_sat, launches = [], 0, 0
-    per_launch = count if not chains_per_launch else max(batch_chains, chains_per_launch // batch_chains * batch_chains)
+    if chains_per_launch and count > chains_per_launch:      # equal launches of whole reference batches, none larger than the cap
+        n_launch = -(-count // chains_per_launch)
+        per_launch = -(-(-(-count // n_launch)) // batch_chains) * batch_chains
+    else:
+        per_launch = max(count, 1)
     done = 0
     while done < count:
         now = min(per_launch, count - done)
