@@ -129,27 +129,22 @@ class UnitGraph:
         return np.concatenate([pos, neg], axis=0), (2 * n_total, chains * m)
 
 
-def build_unit_graph(n_vars: int, clauses, var_seg=None, clause_seg=None) -> UnitGraph:
-    """CSR/CSC arrays of one formula (or of a union, when the segments are given)."""
-    n = int(n_vars)
-    m = len(clauses)
-    lens = np.fromiter((len(c) for c in clauses), dtype=np.int64, count=m)
+def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause_seg, clauses) -> UnitGraph:
+    """CSR/CSC arrays from the literals of all clauses laid end to end (``lens[j]`` literals for clause j)."""
+    m = int(lens.shape[0])
     cl_rowptr = np.zeros(m + 1, dtype=np.int64)
     np.cumsum(lens, out=cl_rowptr[1:])
-    nnz = int(cl_rowptr[-1])
-    cl_lit = np.empty(nnz, dtype=np.int64)
-    for j, clause in enumerate(clauses):
-        if not clause:
-            continue
-        arr = np.asarray(clause, dtype=np.int64)
-        if np.any(arr == 0) or np.any(np.abs(arr) > n):
-            raise ValueError("literal out of range in clause %d: %r" % (j, clause))
-        var = np.abs(arr) - 1
-        sign = (arr < 0).astype(np.int64)
-        order = np.argsort(sign * n + var, kind="stable")  # reference literal-row order
-        cl_lit[cl_rowptr[j]:cl_rowptr[j + 1]] = (2 * var + sign)[order]
-    # literal -> clauses: stable counting sort by literal code keeps clause ids ascending
+    if flat.size and (np.any(flat == 0) or np.any(np.abs(flat) > n)):
+        bad = int(np.flatnonzero((flat == 0) | (np.abs(flat) > n))[0])
+        j = int(np.searchsorted(cl_rowptr, bad, side="right") - 1)
+        raise ValueError("literal out of range in clause %d: %r" % (j, flat[cl_rowptr[j]:cl_rowptr[j + 1]].tolist()))
+    var = np.abs(flat) - 1
+    sign = (flat < 0).astype(np.int64)
     clause_of_edge = np.repeat(np.arange(m, dtype=np.int64), lens)
+    # inside a clause: reference literal-row order (positives by variable, then negatives), stable for repeated literals
+    order = np.lexsort((var, sign, clause_of_edge))
+    cl_lit = (2 * var + sign)[order]
+    # literal -> clauses: stable counting sort by literal code keeps clause ids ascending
     order = np.argsort(cl_lit, kind="stable")
     lit_clause = clause_of_edge[order]
     lit_rowptr = np.zeros(2 * n + 1, dtype=np.int64)
@@ -163,22 +158,42 @@ def build_unit_graph(n_vars: int, clauses, var_seg=None, clause_seg=None) -> Uni
         cl_rowptr=cl_rowptr.astype(np.int32), cl_lit=cl_lit.astype(np.int32),
         lit_rowptr=lit_rowptr.astype(np.int32), lit_clause=lit_clause.astype(np.int32),
         var_seg=np.asarray(var_seg, dtype=np.int32), clause_seg=np.asarray(clause_seg, dtype=np.int32),
-        clauses=[list(map(int, c)) for c in clauses],
+        clauses=clauses,
     )
+
+
+def _flatten(clauses):
+    m = len(clauses)
+    lens = np.fromiter((len(c) for c in clauses), dtype=np.int64, count=m)
+    flat = np.fromiter((lit for c in clauses for lit in c), dtype=np.int64, count=int(lens.sum()))
+    return lens, flat
+
+
+def build_unit_graph(n_vars: int, clauses, var_seg=None, clause_seg=None) -> UnitGraph:
+    """CSR/CSC arrays of one formula (or of a union, when the segments are given)."""
+    lens, flat = _flatten(clauses)
+    return _graph_from_flat(int(n_vars), lens, flat, var_seg, clause_seg, [list(map(int, c)) for c in clauses])
 
 
 def build_union_graph(formulas) -> UnitGraph:
     """Disjoint union of ``[(n_vars, clauses), ...]`` with the reference's variable shift
     (``data/dimac.py:165-170,239-241``): one unit whose graphs are the formulas."""
-    shifted, var_seg, clause_seg = [], [0], [0]
+    lens_all, flat_all, var_seg, clause_seg = [], [], [0], [0]
     off = 0
     for n_vars, clauses in formulas:
-        for clause in clauses:
-            shifted.append([lit + off if lit > 0 else lit - off for lit in clause])
+        lens, flat = _flatten(clauses)
+        if flat.size and np.any(np.abs(flat) > int(n_vars)):
+            raise ValueError("literal out of range in a formula with %d variables" % int(n_vars))
+        lens_all.append(lens)
+        flat_all.append(flat + np.sign(flat) * off)
         off += int(n_vars)
         var_seg.append(off)
-        clause_seg.append(len(shifted))
-    return build_unit_graph(off, shifted, var_seg, clause_seg)
+        clause_seg.append(clause_seg[-1] + len(clauses))
+    lens = np.concatenate(lens_all) if lens_all else np.zeros(0, dtype=np.int64)
+    flat = np.concatenate(flat_all) if flat_all else np.zeros(0, dtype=np.int64)
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    shifted = [flat[ptr[j]:ptr[j + 1]].tolist() for j in range(len(lens))]
+    return _graph_from_flat(off, lens, flat, var_seg, clause_seg, shifted)
 
 
 def unit_graph_from_reference_coo(indices, dense_shape, variables_graph=None, clauses_graph=None):

@@ -46,14 +46,15 @@ def main(report, summary_path, traffic_path=None):
     with open(summary_path, "w") as f:
         json.dump(launches, f, indent=1)
     if traffic_path:
-        mlp = [e for e in launches if "fused_mlp" in e["kernel"]]      # fused_mlp_kernel and fused_mlp_split_kernel
         out = {}
-        if mlp:
-            out["fused_mlp_kernel"] = {
-                "dram_bytes_per_launch": sum(e["dram_bytes"] for e in mlp) / len(mlp), "launches_captured": len(mlp),
-                "per_launch": [{"duration_us": e["duration_us"], "dram_bytes": e["dram_bytes"],
-                                "tensor_active_pct": e["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]}
-                               for e in mlp]}
+        for key, pattern in (("fused_mlp_kernel", "fused_mlp"), ("x3_mlp_kernel", "x3_mlp")):   # bf16 / fp32-accurate whole-MLP kernels
+            mlp = [e for e in launches if pattern in e["kernel"]]
+            if mlp:
+                out[key] = {
+                    "dram_bytes_per_launch": sum(e["dram_bytes"] for e in mlp) / len(mlp), "launches_captured": len(mlp),
+                    "per_launch": [{"duration_us": e["duration_us"], "dram_bytes": e["dram_bytes"],
+                                    "tensor_active_pct": e["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]}
+                                   for e in mlp]}
         for name in ("clause_gather", "literal_gather", "pairnorm", "spmm_rows"):
             sel = [e for e in launches if name in e["kernel"]]
             if sel:
