@@ -42,6 +42,8 @@ _SIGNATURES = {
     "dsat_launch_count": (C.c_longlong, [_vp]),
     "dsat_set_model": (C.c_int, [_vp, C.c_int, C.POINTER(_f32p), C.POINTER(_f32p), _i32p, _i32p]),
     "dsat_set_precision": (C.c_int, [_vp, C.c_int]),
+    "dsat_set_sampling": (C.c_int, [_vp, C.c_int]),
+    "dsat_debug_rounding": (C.c_int, [_vp, C.c_uint64, C.c_int]),
     "dsat_get_precision": (C.c_int, [_vp]),
     "dsat_set_graph": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, C.c_int, _i32p, _i32p,
                                  C.c_int, C.c_int]),
@@ -178,6 +180,15 @@ class Context:
         if isinstance(dtype, str):
             dtype = PRECISIONS[dtype]
         self._check(self._lib.dsat_set_precision(self._h, int(dtype)))
+
+    SAMPLING = {"inverse_cdf": 0, "gumbel": 1}
+
+    def set_sampling(self, mode):
+        """"inverse_cdf" = floor(x0 + U) (the reference's live code, default) or "gumbel" = Gumbel-argmax."""
+        self._check(self._lib.dsat_set_sampling(self._h, self.SAMPLING[mode] if isinstance(mode, str) else int(mode)))
+
+    def debug_rounding(self, seed=0, step=0):
+        self._check(self._lib.dsat_debug_rounding(self._h, C.c_uint64(seed), int(step)))
 
     def get_precision(self) -> int:
         return int(self._lib.dsat_get_precision(self._h))

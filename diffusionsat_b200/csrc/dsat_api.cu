@@ -142,6 +142,7 @@ struct dsat_ctx {
 #endif
     bool has_simt_buffers = false;
     float last_noise_scale = 0.f;
+    int sampling = DSAT_SAMPLE_INVERSE_CDF;
     // one captured denoising step (dsat_sample_enqueue without injected noise): replayed once per step, the step's scalars
     // come from step_tab[*step_cur] on the device
     DevBuf<StepParams> step_tab;
@@ -692,7 +693,7 @@ int begin_call(dsat_ctx* c, float noise_scale, const float* noisy_dev, const flo
     c->last_noise_scale = noise_scale;
     step_begin_kernel<<<(unsigned)((Nt + threads - 1) / threads), threads, 0, c->stream>>>(
         Nt, noise_scale, use_x ? c->X.p : nullptr, noisy_dev, uniforms_dev, labels_dev, c->labels.p,
-        x3p ? nullptr : c->VROW.p, c->ldv(), c->F, vrow_b(c), ns, vplane, sp_tab, sp_cur);
+        x3p ? nullptr : c->VROW.p, c->ldv(), c->F, vrow_b(c), ns, vplane, sp_tab, sp_cur, c->sampling == DSAT_SAMPLE_GUMBEL ? 1 : 0);
     LAUNCHED(c);
     {   // variables_state = ones, clauses_state = ones (reference model/query_sat.py:141,148)
         long long tot;
@@ -1333,6 +1334,14 @@ int dsat_set_precision(dsat_ctx* c, int dtype) {
 #endif
     c->err = "precision not available in this build";
     return DSAT_ERR_UNSUPPORTED;
+}
+
+int dsat_set_sampling(dsat_ctx* c, int mode) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_ARG(c, mode == DSAT_SAMPLE_INVERSE_CDF || mode == DSAT_SAMPLE_GUMBEL, "dsat_set_sampling: unknown mode");
+    if (mode != c->sampling) c->generation++;        // baked into the captured step
+    c->sampling = mode;
+    return DSAT_OK;
 }
 
 int dsat_set_model(dsat_ctx* c, int n_layers, const float* const* kernels, const float* const* biases,
@@ -2055,6 +2064,19 @@ int dsat_tc_linear_test(dsat_ctx* c, int rows, int K, int N, const float* a_host
     CK_CUDA(c, e);
     return DSAT_OK;
 #endif
+}
+
+// Randomized rounding of the CURRENT diffusion state X alone (dsat_debug_write of DSAT_BUF_X first): X <- one-hot sample
+// drawn with the context's sampling mode and the Philox stream (seed, step).
+int dsat_debug_rounding(dsat_ctx* c, uint64_t seed, int step) {
+    if (!c) return DSAT_ERR_ARG;
+    CK_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_active_buffers(c);
+    if (rc) return rc;
+    NoiseSource ns{seed, 0ull, (unsigned)step};
+    if ((rc = begin_call(c, 0.5f, nullptr, nullptr, nullptr, true, ns))) return rc;
+    CK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return DSAT_OK;
 }
 
 int dsat_debug_begin(dsat_ctx* c, float noise_scale, const float* noisy_num, const int32_t* labels) {

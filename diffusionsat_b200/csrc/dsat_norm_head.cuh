@@ -459,7 +459,8 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
                                   int* __restrict__ labels,
                                   float* __restrict__ VROW, int ld, int aux_off, __nv_bfloat16* __restrict__ VROW_B,
                                   NoiseSource ns, size_t lo_plane = 0,     // lo_plane > 0: VROW_B is a hi plane with its lo plane that far on
-                                  const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr) {
+                                  const StepParams* __restrict__ sp_tab = nullptr, const int* __restrict__ sp_cur = nullptr,
+                                  int gumbel = 0) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     if (sp_tab) {
@@ -470,9 +471,20 @@ __global__ void step_begin_kernel(long long n_rows, float noise_scale, float2* X
     if (noisy_in) {
         a = noisy_in[2 * r]; b = noisy_in[2 * r + 1];
     } else {
-        const float u = uniforms_in ? uniforms_in[r]
-                                    : u32_to_unit_float(noise_draw(ns.seed, ns.element_offset + r, ns.step, 0, STREAM_UNIFORM).x);
-        a = floorf(X[r].x + u);
+        if (gumbel && !uniforms_in) {
+            // Gumbel-argmax over the two classes (the sampler the reference sketches in model/query_sat.py:15-28, hard instead
+            // of soft): class k wins with probability x_k / (x_0 + x_1) -- the same distribution as floor(x_0 + U), but not
+            // the same sample under the same uniform, so this mode is validated statistically only
+            const Philox4 p = noise_draw(ns.seed, ns.element_offset + r, ns.step, 0, STREAM_UNIFORM);
+            const float g0 = -logf(-logf(u32_to_unit_float(p.x) + 1e-20f) + 1e-20f);
+            const float g1 = -logf(-logf(u32_to_unit_float(p.y) + 1e-20f) + 1e-20f);
+            const float2 x = X[r];
+            a = (logf(fmaxf(x.x, 1e-20f)) + g0 >= logf(fmaxf(x.y, 1e-20f)) + g1) ? 1.0f : 0.0f;
+        } else {
+            const float u = uniforms_in ? uniforms_in[r]
+                                        : u32_to_unit_float(noise_draw(ns.seed, ns.element_offset + r, ns.step, 0, STREAM_UNIFORM).x);
+            a = floorf(X[r].x + u);
+        }
         b = 1.0f - a;
     }
     if (X) X[r] = make_float2(a, b);

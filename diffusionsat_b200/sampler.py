@@ -158,7 +158,8 @@ class DiffusionSampler:
 
     def __init__(self, model_path, dimacs_filename, *, device: int = 0, precision: str = "fp32",
                  chains_per_launch: int | None = None, seed: int = 0, chain_offset: int = 0,
-                 max_nodes_per_batch: int = MAX_NODES_PER_BATCH, verbose: bool = False, context=None):
+                 max_nodes_per_batch: int = MAX_NODES_PER_BATCH, verbose: bool = False, context=None,
+                 sampling: str = "inverse_cdf"):
         self.verbose = verbose
         print("model_path is ", model_path)
         weights = self._prepare_checkpoints(model_path)
@@ -171,6 +172,7 @@ class DiffusionSampler:
                               precision=precision, seed=seed, context=context,
                               feature_maps=weights.feature_maps, query_maps=weights.query_maps)
         self.ctx = self.model.ctx
+        self.ctx.set_sampling(sampling)         # "gumbel": Gumbel-argmax rounding (same distribution, other samples)
         self.unit = build_unit_graph(self.n_vars, self.clauses)
         self.batch_chains = chains_per_reference_batch(self.n_vars, len(self.clauses), max_nodes_per_batch)
         self.chains_per_launch = chains_per_launch

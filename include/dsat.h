@@ -69,6 +69,12 @@ long long dsat_launch_count(const dsat_ctx* ctx);
 int dsat_set_model(dsat_ctx* ctx, int n_layers, const float* const* kernels, const float* const* biases,
                    const int* in_dims, const int* out_dims);
 
+/* How the denoising step rounds x to a one-hot sample: DSAT_SAMPLE_INVERSE_CDF = floor(x0 + U), the reference's live code
+ * (model/query_sat.py:55-60) and the mode every bit-exact parity statement refers to; DSAT_SAMPLE_GUMBEL = Gumbel-argmax
+ * (the sampler sketched in model/query_sat.py:15-28), same distribution, validated statistically. */
+enum dsat_sampling { DSAT_SAMPLE_INVERSE_CDF = 0, DSAT_SAMPLE_GUMBEL = 1 };
+int dsat_set_sampling(dsat_ctx* ctx, int mode);
+
 /* dtype of the MLP path, see enum dsat_dtype */
 int dsat_set_precision(dsat_ctx* ctx, int dtype);
 /* The active dtype.  A new context starts in DSAT_F32_TC; dsat_set_model switches it to DSAT_F32 (CUDA cores, the same

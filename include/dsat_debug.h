@@ -51,6 +51,10 @@ int dsat_profile_rounds(dsat_ctx* ctx, int rounds, uint64_t seed, float* class_m
 int dsat_tc_linear_test(dsat_ctx* ctx, int rows, int K, int N, const float* a_host, const float* w_host,
                         const float* bias_host, int epi, int out_bf16, float* out_host);
 
+/* Randomized rounding alone: X (DSAT_BUF_X, written with dsat_debug_write) <- one-hot sample drawn with the context's
+ * sampling mode from the Philox stream (seed, step). */
+int dsat_debug_rounding(dsat_ctx* ctx, uint64_t seed, int step);
+
 /* Parity hooks: run the pieces of one model call separately and read/write activation buffers. */
 int dsat_debug_begin(dsat_ctx* ctx, float noise_scale, const float* noisy_num, const int32_t* labels);
 int dsat_debug_round(dsat_ctx* ctx, int round, const float* normals /* [N,4] host */);

@@ -141,16 +141,19 @@ def test_sample_matches_oracle_diffusion(ctx, n_vars, n_clauses, chains, steps, 
     # predictions to be clear of 0.5 and of the uniform thresholds, else skip the chain
     from diffusionsat_b200.sampler import unpack_assignments
     got = unpack_assignments(packed, n_vars)
+    checked = 0
     for c in range(chains):
         bits = final[c * n_vars:(c + 1) * n_vars]
         want = O.encode_assignment(bits)
         margins = [np.abs(t["predictions"].numpy()[c * n_vars:(c + 1) * n_vars] - 0.5).min() for t in trace]
-        if min(margins) < 1e-3:
+        if min(margins) < 1e-4:      # 100 x the fp32 paths' measured probability error; with 1e-3 only 2 of 6 chains were checked
             continue
+        checked += 1
         assert got[c] == want, "chain %d: %x != %x" % (c, got[c], want)
         assert latch_step[c] == latch[c * n_vars]
         assert bool(is_sat[c]) == O._satisfiable_py([bool(b) for b in bits], clauses)
         assert bool(sat_any[c]) == (latch[c * n_vars] >= 0)
+    assert checked >= (chains + 1) // 2, "only %d of %d chains were clear of rounding boundaries" % (checked, chains)
 
 
 def test_early_exit_is_per_group(ctx):
@@ -187,8 +190,10 @@ def test_edge_cases_empty_clause_duplicates_isolated_variable(ctx):
     graph, out, trace = H.oracle_trace(n_vars, clauses, chains, wts, 0.9, noisy, noise, rounds)
     pred, steps, _ = ctx.model_call(0.9, noisy, labels=noise["labels"], normals=noise["normals"], rounds=rounds)
     groups = ctx.debug_groups()
-    if np.array_equal(groups["graph_map"], trace[-1]["best_graph_map"].numpy()) and steps[0] == out[1]:
-        check("prediction", pred, out[0].numpy(), 1e-3)
+    assert steps[0] == out[1]
+    same = np.repeat(groups["graph_map"] == trace[-1]["best_graph_map"].numpy(), n_vars)
+    assert same.any(), "the logit-map choice differs from the oracle's for every graph"
+    check("prediction", pred[same], out[0].numpy()[same], 1e-3)
     # an empty clause can never be satisfied (reference VariableAssignment.satisfiable / is_batch_sat)
     clauses2 = [[1, 2], [], [-1]]
     bind(ctx, 2, clauses2, 3, wts)
