@@ -1781,24 +1781,26 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
     const int* colidx = direction == 0 ? c->cl_lit.p : c->lit_clause.p;
     const int rows_out = direction == 0 ? c->m : 2 * c->n;
     const int rows_in = direction == 0 ? 2 * c->n : c->m;
-    auto launch = [&](auto kernel, int row_bytes) {
-        const int rows_per_block = GATHER_WARPS * (row_bytes >= 512 ? 1 : 512 / row_bytes);
-        const int grid = gather_grid(kernel, (long long)chains * rows_out, rows_per_block, c->sm_count);
-        kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowdesc, colidx, rows_out, rows_in, chains, x_dev, y_dev);
-    };
     int rc = DSAT_OK;
     const int row_bytes = feat * (dtype == DSAT_BF16 ? 2 : 4);
     if (feat != 64 && feat != 128 && feat != 256) {
         c->err = "feature width must be 64, 128 or 256";
         rc = DSAT_ERR_UNSUPPORTED;
-    } else if (dtype == DSAT_BF16) {
-        if (row_bytes == 128) launch(spmm_rows_kernel<128, true>, 128);
-        else if (row_bytes == 256) launch(spmm_rows_kernel<256, true>, 256);
-        else launch(spmm_rows_kernel<512, true>, 512);
     } else {
-        if (row_bytes == 256) launch(spmm_rows_kernel<256, false>, 256);
-        else if (row_bytes == 512) launch(spmm_rows_kernel<512, false>, 512);
-        else launch(spmm_rows_kernel<1024, false>, 1024);
+        auto launch = [&](auto kernel) {
+            const int rows_per_block = GATHER_WARPS * (row_bytes >= 512 ? 1 : 512 / row_bytes);
+            const int grid = gather_grid(kernel, (long long)chains * rows_out, rows_per_block, c->sm_count);
+            kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowdesc, colidx, rows_out, rows_in, chains, x_dev, y_dev);
+        };
+        if (dtype == DSAT_BF16) {
+            if (row_bytes == 128) launch(spmm_rows_kernel<128, true>);
+            else if (row_bytes == 256) launch(spmm_rows_kernel<256, true>);
+            else launch(spmm_rows_kernel<512, true>);
+        } else {
+            if (row_bytes == 256) launch(spmm_rows_kernel<256, false>);
+            else if (row_bytes == 512) launch(spmm_rows_kernel<512, false>);
+            else launch(spmm_rows_kernel<1024, false>);
+        }
     }
     if (rc) return rc;
     LAUNCHED(c);

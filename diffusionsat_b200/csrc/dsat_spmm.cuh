@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, 8)
 spmm_rows_kernel(const int4* __restrict__ rowdesc, const int* __restrict__ colidx, int rows_out, int rows_in, int chains,
                  const void* __restrict__ Xv, void* __restrict__ Yv) {
     constexpr int CH = ROW_BYTES / 16;           // 16-byte chunks per feature row
-    constexpr int LPR = CH < 32 ? CH : 32;       // lanes per row
+    constexpr int LPR = CH < 32 ? CH : 32;       // lanes per row (fewer lanes per row with several strided chunks per lane were
+                                                 // tried in round 2: 12-35 % of the copy rate -- the 32-register budget spills)
     constexpr int RPW = 32 / LPR;                // output rows per warp pass
     constexpr int CPL = CH / LPR;                // chunks per lane
     constexpr int EPC = BF16 ? 8 : 4;            // features per chunk
@@ -97,10 +98,13 @@ spmm_rows_kernel(const int4* __restrict__ rowdesc, const int* __restrict__ colid
                     if (j < len)
                         x[j][k] = __ldg(reinterpret_cast<const uint4*>(xc + (size_t)col[j] * ROW_BYTES) + k * LPR);
                 }
+            const bool any4 = RPW == 1 ? len == 4 : __any_sync(__activemask(), len == 4);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
+                if (j < 3 || any4) {        // 3-SAT: the fourth (all-zero) chunk is not added
 #pragma unroll
-                for (int k = 0; k < CPL; ++k) spmm_add_chunk<BF16>(acc[k], x[j][k]);
+                    for (int k = 0; k < CPL; ++k) spmm_add_chunk<BF16>(acc[k], x[j][k]);
+                }
         } else {
             int e = d0.w;
             const int e1 = e + len;
