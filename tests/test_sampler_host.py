@@ -71,3 +71,26 @@ def test_missing_checkpoint_is_random_init_but_a_broken_one_raises(tmp_path, cap
     bad.write_bytes(b"not a zip archive")
     with pytest.raises(Exception):
         s._prepare_checkpoints(str(bad))
+
+
+def test_launch_sizing_rules():
+    """Launches hold whole reference batches; the first one assumes a 50 % SAT rate and at least four batches, later ones
+    follow the observed rate; a remainder smaller than a batch rides along; an explicit launch size is rounded down."""
+    class FakeCtx:
+        graph, chains = None, 0
+    s = DiffusionSampler.__new__(DiffusionSampler)
+    s.ctx, s.unit = FakeCtx(), object()
+    s.batch_chains, s.clauses, s.n_vars, s.chains_per_launch = 103, [[1]] * 133, 30, None
+    assert s._launch_chains(256) == 6 * 103                      # 256 / 0.5 * 1.15 -> 6 batches
+    assert s._launch_chains(10) == 4 * 103                       # never fewer than four batches
+    assert s._launch_chains(256, sat_rate=0.9) == 4 * 103
+    assert s._launch_chains(10 ** 9) % 103 == 0 and s._launch_chains(10 ** 9) * 133 <= 900_000     # memory cap
+    s.ctx.graph, s.ctx.chains = s.unit, 7 * 103
+    assert s._launch_chains(256) == 7 * 103                      # same shape as the previous launch is kept
+    s.ctx.graph = None
+    s.chains_per_launch = 4096
+    s.batch_chains = 31
+    assert s._launch_chains(10 ** 9) == 4092
+    assert s._launch_chains(10 ** 9, chains_left=4096) == 4096   # 4 chains left over ride along as a partial group
+    assert s._launch_chains(10 ** 9, chains_left=10000) == 4092
+    assert s._launch_chains(10 ** 9, chains_left=20) == 20
