@@ -390,6 +390,8 @@ def run_ours(args):
         sampler = DiffusionSampler(npz_path, cnf_path, context=ctx, precision=args.precision, seed=2000,
                                    chains_per_launch=chains, chain_offset=chain_offset)
     sampler.min_sat_rate = 0.0
+    if world > 1:       # untimed warm-up of the merge's collectives (NCCL sets up all-gather / reduce channels on first use)
+        D.merge_histograms(np.zeros((0, -(-n // 64)), dtype=np.uint64), np.zeros(0, dtype=np.int64), n)
     barrier()
     e2e_steps = args.steps
     hist_sizes = []
