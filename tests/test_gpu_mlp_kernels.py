@@ -142,6 +142,8 @@ PLANS = {
     "x3_all_pair": {"DSAT_X3_PAIR": "127"},
     "x3_shallow_rings": {"DSAT_X3_A_SLOTS": "2", "DSAT_X3_W_SLOTS": "2"},
     "x3_four_epilogue_warps": {"DSAT_X3_EPI4": "127"},
+    "x3_whole_clause_mlp": {"DSAT_X3_SPLIT": "0"},
+    "x3_layer_per_launch_update": {"DSAT_X3_SPLIT": "3"},
     "bf16_split_off": {"DSAT_SPLIT_MODE": "0"},
     "bf16_cta_pair": {"DSAT_PAIR_MODE": "31", "DSAT_SPLIT_MODE": "0"},
     "bf16_no_pair": {"DSAT_PAIR_MODE": "0"},
