@@ -910,9 +910,11 @@ bool launch_literal_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     const bool si = c->use_idx16 && idx_fits(bytes, g.lit_idx16_vecs);
     const size_t smem = bytes + (si ? (size_t)g.lit_idx16_vecs * 16 : 0);
     const size_t cplane = (size_t)c->Mt * c->ldc(), vplane = (size_t)c->Nt * c->ldv();
+    // DSAT_GATHER_F32_PLANES=0: widen 4*clauses_loss to an fp32 table while staging instead of keeping hi / lo bf16 tables
+    static const int planes_tables = getenv("DSAT_GATHER_F32_PLANES") ? atoi(getenv("DSAT_GATHER_F32_PLANES")) : 1;
     auto launch = [&](auto kernel) -> bool {
         kernel<<<grid, 512, smem, c->stream>>>(g, Q, c->CROWp.p, cplane, c->ldc(), F + Q, c->COUT.p, Q + F, c->QS.p, 3 * Q,
-                                                c->VROWp.p, vplane, c->ldv(), F + DSAT_AUX_PAD, skip_info(c));
+                                                c->VROWp.p, vplane, c->ldv(), F + DSAT_AUX_PAD, skip_info(c), planes_tables);
         return true;
     };
     if (w == 128) return si ? launch(literal_gather_smem_f32_kernel<128, true>) : launch(literal_gather_smem_f32_kernel<128, false>);

@@ -619,19 +619,110 @@ clause_gather_smem_f32_kernel(UnitGraphDev g, int Q,
     }
 }
 
+// Role 0 of the literal side with the hi / lo planes of 4*clauses_loss kept as TWO bf16 tables (the same bytes as one fp32
+// table): both are staged with cp.async -- converting to fp32 while staging went through registers in two dependent batches
+// and left the role-0 CTAs latency-bound -- and every edge adds hi and lo with the one-instruction widening add (acc += hi;
+// acc += lo).  A lane owns 8 features.
+template <int W, bool SI>
+__device__ __forceinline__ void literal_grad_from_planes(const UnitGraphDev& g, int Q, const __nv_bfloat16* __restrict__ CL4_HI,
+                                                         size_t cl_plane, int ld_cl, int cl_off, const float* __restrict__ QRY, int ld_q,
+                                                         __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off,
+                                                         uint8_t* gsm, int chain, int slice) {
+    using T = __nv_bfloat16;
+    constexpr int LPR = W / 8, RPW = 32 / LPR;
+    T* t_hi = reinterpret_cast<T*>(gsm);
+    T* t_lo = t_hi + (size_t)g.m * W;
+    const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(t_lo + (size_t)g.m * W);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int sub = lane / LPR, li = lane % LPR;
+    const size_t cbase = (size_t)chain * g.m;
+    const T* src = CL4_HI + cbase * ld_cl + cl_off + slice * W;
+    stage_rows_async<T>(t_hi, src, g.m, ld_cl, W, tid, blockDim.x);
+    stage_rows_async<T>(t_lo, src + cl_plane, g.m, ld_cl, W, tid, blockDim.x);
+    if constexpr (SI) {
+        uint4* d = reinterpret_cast<uint4*>(const_cast<unsigned short*>(s_idx));
+        for (int i = tid; i < g.lit_idx16_vecs; i += blockDim.x) d[i] = __ldg(reinterpret_cast<const uint4*>(g.lit_idx16) + i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int v0 = warp * RPW; v0 < g.n; v0 += nwarps * RPW) {
+        const bool live = v0 + sub < g.n;
+        int v = 0;
+        if (live) v = SI ? (int)s_idx[g.lit_ord_off + v0 + sub] : __ldg(g.var_order + v0 + sub);
+        const size_t row = (size_t)chain * g.n + v;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        float vw = 0.f;
+        if (live) {
+            const float4* qp = reinterpret_cast<const float4*>(QRY + row * ld_q + slice * W) + 2 * li;
+            q0 = __ldg(qp); q1 = __ldg(qp + 1);
+            vw = __ldg(g.vdeg_w + v);
+        }
+        Acc8 s4[2];
+#pragma unroll
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            acc8_zero(s4[sgn]);
+            const int code = 2 * v + sgn;
+            int e0 = 0, e1 = 0;
+            if (live) {
+                if constexpr (SI) { e0 = s_idx[code]; e1 = s_idx[code + 1]; }
+                else { e0 = __ldg(g.lit_rowptr + code); e1 = __ldg(g.lit_rowptr + code + 1); }
+            }
+            auto col = [&](int e) { return SI ? (int)s_idx[g.lit_col_off + e] : __ldg(g.lit_clause + e); };
+            int e = e0;
+            for (; e + 3 <= e1; e += 3) {
+                const int j0 = col(e), j1 = col(e + 1), j2 = col(e + 2);
+                DSAT_CHECK((unsigned)j0 < (unsigned)g.m && (unsigned)j1 < (unsigned)g.m && (unsigned)j2 < (unsigned)g.m);
+                const uint4 a0 = reinterpret_cast<const uint4*>(t_hi + (size_t)j0 * W)[li];
+                const uint4 b0 = reinterpret_cast<const uint4*>(t_lo + (size_t)j0 * W)[li];
+                const uint4 a1 = reinterpret_cast<const uint4*>(t_hi + (size_t)j1 * W)[li];
+                const uint4 b1 = reinterpret_cast<const uint4*>(t_lo + (size_t)j1 * W)[li];
+                const uint4 a2 = reinterpret_cast<const uint4*>(t_hi + (size_t)j2 * W)[li];
+                const uint4 b2 = reinterpret_cast<const uint4*>(t_lo + (size_t)j2 * W)[li];
+                acc8_add(s4[sgn], a0); acc8_add(s4[sgn], b0);
+                acc8_add(s4[sgn], a1); acc8_add(s4[sgn], b1);
+                acc8_add(s4[sgn], a2); acc8_add(s4[sgn], b2);
+            }
+            for (; e < e1; ++e) {
+                const int j = col(e);
+                acc8_add(s4[sgn], reinterpret_cast<const uint4*>(t_hi + (size_t)j * W)[li]);
+                acc8_add(s4[sgn], reinterpret_cast<const uint4*>(t_lo + (size_t)j * W)[li]);
+            }
+        }
+        if (!live) continue;
+        const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float grad[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float sg = sigmoid_f(qv[i]), sgn_ = sigmoid_f(-qv[i]);
+            grad[i] = (-sg * s4[0].v[i] + sgn_ * s4[1].v[i]) * vw;
+        }
+        __nv_bfloat16* dst = OUT_HI + row * ld_out + out_off + slice * W;
+        uint4 hi, lo;
+        split_bf16x2(grad[0], grad[1], hi.x, lo.x); split_bf16x2(grad[2], grad[3], hi.y, lo.y);
+        split_bf16x2(grad[4], grad[5], hi.z, lo.z); split_bf16x2(grad[6], grad[7], hi.w, lo.w);
+        reinterpret_cast<uint4*>(dst)[li] = hi;
+        reinterpret_cast<uint4*>(dst + out_plane)[li] = lo;
+    }
+}
+
 template <int W, bool SI>
 __global__ void __launch_bounds__(512, 2)
 literal_gather_smem_f32_kernel(UnitGraphDev g, int Q,
                                const __nv_bfloat16* __restrict__ CL4_HI, size_t cl_plane, int ld_cl, int cl_off,
                                const float* __restrict__ MSG, int ld_msg,
                                const float* __restrict__ QRY, int ld_q,
-                               __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1}) {
+                               __nv_bfloat16* __restrict__ OUT_HI, size_t out_plane, int ld_out, int out_off, SkipInfo skip = SkipInfo{nullptr, 1},
+                               int planes_as_tables = 1) {
     if (chain_done(skip, (int)blockIdx.x)) return;     // the whole CTA works on one chain
     constexpr int LPR = W / 4, RPW = 32 / LPR;
     extern __shared__ __align__(16) uint8_t gsm[];
     float* tab = reinterpret_cast<float*>(gsm);
     const unsigned short* s_idx = reinterpret_cast<const unsigned short*>(tab + (size_t)g.m * W);
     const int chain = blockIdx.x, slice = blockIdx.y >> 1, role = blockIdx.y & 1;
+    if (role == 0 && planes_as_tables) {
+        literal_grad_from_planes<W, SI>(g, Q, CL4_HI, cl_plane, ld_cl, cl_off, QRY, ld_q, OUT_HI, out_plane, ld_out, out_off, gsm, chain, slice);
+        return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int sub = lane / LPR, li = lane % LPR;
     const size_t cbase = (size_t)chain * g.m;
