@@ -879,7 +879,8 @@ bool launch_clause_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     size_t bytes = 0;
     static const int budget = getenv("DSAT_GATHER_F32_KB_CL") ? atoi(getenv("DSAT_GATHER_F32_KB_CL")) : 110;
     const int w = pick_slice_width((size_t)2 * c->n, c->Q, &bytes, budget, one_table ? 2 : 4);
-    if (!w) return false;
+    // one CTA per SM cannot overlap its staging with another CTA's gather: measured slower than the L2 gather (uf250)
+    if (!w || bytes > 112 * 1024) return false;
     dim3 grid((unsigned)c->chains, (unsigned)((one_table ? 2 : 1) * (c->Q / w)));
     const int Q = c->Q;
     const bool si = c->use_idx16 && idx_fits(bytes, g.cl_idx16_vecs);
@@ -904,7 +905,7 @@ bool launch_literal_gather_smem_f32(dsat_ctx* c, const UnitGraphDev& g) {
     size_t bytes = 0;
     static const int budget = getenv("DSAT_GATHER_F32_KB_LIT") ? atoi(getenv("DSAT_GATHER_F32_KB_LIT")) : 112;
     const int w = pick_slice_width((size_t)c->m, c->Q, &bytes, budget, 2);          // one fp32 table per CTA
-    if (!w) return false;
+    if (!w || bytes > 112 * 1024) return false;     // (as on the clause side: uf250's 1065 clause rows ran 1.39 ms against 1.09 ms)
     dim3 grid((unsigned)c->chains, (unsigned)(2 * (c->Q / w)));
     const int Q = c->Q, F = c->F;
     const bool si = c->use_idx16 && idx_fits(bytes, g.lit_idx16_vecs);
