@@ -32,6 +32,7 @@ _vp = C.c_void_p
 
 _SIGNATURES = {
     "dsat_version": (C.c_int, []),
+    "dsat_build_info": (C.c_int, []),
     "dsat_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "dsat_destroy": (None, [_vp]),
     "dsat_last_error": (C.c_char_p, [_vp]),

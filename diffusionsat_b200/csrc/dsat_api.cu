@@ -1265,7 +1265,18 @@ static void drop_step_graph(dsat_ctx* c) {
 
 extern "C" {
 
-int dsat_version(void) { return 1; }
+int dsat_version(void) { return 2; }
+
+int dsat_build_info(void) {
+    int flags = 0;
+#ifdef DSAT_WITH_TCGEN05
+    flags |= 1;
+#endif
+#ifdef DSAT_ASSERT
+    flags |= 2;
+#endif
+    return flags;
+}
 
 int dsat_create(int device, dsat_ctx** out) {
     if (!out) return DSAT_ERR_ARG;

@@ -51,6 +51,9 @@ int dsat_profile_rounds(dsat_ctx* ctx, int rounds, uint64_t seed, float* class_m
 int dsat_tc_linear_test(dsat_ctx* ctx, int rows, int K, int N, const float* a_host, const float* w_host,
                         const float* bias_host, int epi, int out_bf16, float* out_host);
 
+/* Build flags of the loaded library: bit 0 = tcgen05 paths compiled in, bit 1 = -DDSAT_ASSERT debug build (bounds checks). */
+int dsat_build_info(void);
+
 /* Randomized rounding alone: X (DSAT_BUF_X, written with dsat_debug_write) <- one-hot sample drawn with the context's
  * sampling mode from the Philox stream (seed, step). */
 int dsat_debug_rounding(dsat_ctx* ctx, uint64_t seed, int step);

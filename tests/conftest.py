@@ -25,3 +25,12 @@ def ctx(dsat_lib):
     c = _lib.Context(0)
     yield c
     c.close()
+
+
+def pytest_report_header(config):
+    try:
+        from diffusionsat_b200 import _lib
+        info = _lib.load_library().dsat_build_info()
+        return "libdsat build: tcgen05=%d assert=%d" % (info & 1, (info >> 1) & 1)
+    except Exception as exc:        # library not built yet
+        return "libdsat build: not loaded (%s)" % type(exc).__name__
