@@ -40,16 +40,23 @@ namespace {
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
-    size_t count = 0;
+    size_t count = 0;       // elements in use
+    size_t cap = 0;         // elements allocated
+    // (Re)size.  An allocation that is large enough is kept: cudaFree / cudaMalloc of multi-gigabyte buffers cost ~0.1 s per
+    // re-bound graph once the context had seen a few shapes (mixed-formula batches change shape with every batch).
     cudaError_t alloc(size_t n) {
+        if (p && n <= cap) { count = n; return cudaSuccess; }
         release();
-        count = n;
         if (n == 0) return cudaSuccess;
-        return cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T));
+        if (e == cudaSuccess) { count = n; cap = n; }
+        else p = nullptr;
+        return e;
     }
+    void drop() { count = 0; }      // contents invalid, memory kept for the next alloc
     void release() {
         if (p) cudaFree(p);
-        p = nullptr; count = 0;
+        p = nullptr; count = 0; cap = 0;
     }
     cudaError_t upload(const T* host, size_t n, cudaStream_t s) {
         return cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, s);
@@ -459,8 +466,33 @@ int tc_pack_weights(dsat_ctx* c) {
 }
 #endif
 
+// Invalidate every activation buffer (shape or model changed).  The memory stays with the context and is reused by the next
+// ensure_*_buffers when it is large enough; dsat_destroy frees it (free_buffers).
 void release_buffers(dsat_ctx* c) {
     c->generation++;        // every pointer a captured step holds may change
+    c->VROW.drop(); c->CROW.drop(); c->H1.drop(); c->H2.drop(); c->QS.drop(); c->LIT.drop();
+    c->CH.drop(); c->COUT.drop(); c->U1.drop(); c->U2.drop(); c->UOUT.drop(); c->SPRE.drop();
+    c->O1.drop(); c->LOGITS.drop(); c->OUT.drop(); c->X.drop(); c->labels.drop();
+    c->BITS.drop(); c->LAST.drop(); c->LATCH.drop(); c->FINAL.drop();
+    c->done.drop(); c->steps_taken.drop(); c->rounds_run.drop(); c->loss_sum.drop();
+    c->graph_sat.drop(); c->graph_map.drop(); c->graph_loss.drop(); c->latch_step.drop();
+    c->sat_now.drop(); c->is_sat.drop(); c->sat_any.drop(); c->packed.drop();
+    c->inj_normals.drop(); c->inj_uniforms.drop(); c->inj_noisy.drop(); c->inj_labels.drop();
+    c->hist_idx.drop(); c->hist_run.drop(); c->hist_totals.drop(); c->hist_keys.drop(); c->hist_counts.drop();
+#ifdef DSAT_WITH_TCGEN05
+    c->VROWb.drop(); c->CROWb.drop(); c->H1b.drop(); c->H2b.drop(); c->QSb.drop(); c->LITb.drop();
+    c->CHb.drop(); c->COUTb.drop(); c->UOUTb.drop(); c->U1b.drop(); c->U2b.drop(); c->SPREb.drop();
+    c->O1b.drop();
+    c->has_tc_buffers = false;
+    c->VROWp.drop(); c->CROWp.drop(); c->SPREp.drop(); c->H1p.drop(); c->H2p.drop();
+    c->CHp.drop(); c->U1p.drop(); c->U2p.drop();
+    c->has_x3_buffers = false;
+#endif
+    c->has_buffers = false;
+    c->has_simt_buffers = false;
+}
+
+void free_buffers(dsat_ctx* c) {
     c->VROW.release(); c->CROW.release(); c->H1.release(); c->H2.release(); c->QS.release(); c->LIT.release();
     c->CH.release(); c->COUT.release(); c->U1.release(); c->U2.release(); c->UOUT.release(); c->SPRE.release();
     c->O1.release(); c->LOGITS.release(); c->OUT.release(); c->X.release(); c->labels.release();
@@ -1324,7 +1356,7 @@ void dsat_destroy(dsat_ctx* c) {
     cudaStreamSynchronize(c->stream);
     drop_step_graph(c);
     c->step_tab.release(); c->step_cur.release();
-    release_buffers(c);
+    free_buffers(c);
     for (auto& op : c->ops) {
         op.w.release(); op.b.release();
 #ifdef DSAT_WITH_TCGEN05

@@ -26,6 +26,7 @@ reference's literal row of the same literal is ``sign*N_total + chain*n + var``.
 
 from __future__ import annotations
 
+import itertools
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -83,7 +84,18 @@ class UnitGraph:
     lit_clause: np.ndarray         # int32 [nnz]
     var_seg: np.ndarray            # int32 [G+1]   graph g owns variables [var_seg[g], var_seg[g+1])
     clause_seg: np.ndarray         # int32 [G+1]
-    clauses: list = field(default_factory=list, repr=False)
+    _clauses: list = field(default=None, repr=False)                # signed-literal lists, built on first use
+    _flat: np.ndarray = field(default=None, repr=False)             # the same literals laid end to end, clause by clause
+    _lens: np.ndarray = field(default=None, repr=False)
+
+    @property
+    def clauses(self) -> list:
+        """Clauses as lists of signed 1-based literals in their original order (only tests and ``reference_coo`` need them)."""
+        if self._clauses is None:
+            ptr = np.concatenate([[0], np.cumsum(self._lens)])
+            flat = self._flat.tolist()
+            self._clauses = [flat[ptr[j]:ptr[j + 1]] for j in range(len(self._lens))]
+        return self._clauses
 
     @property
     def nnz(self) -> int:
@@ -142,7 +154,7 @@ def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause
     sign = (flat < 0).astype(np.int64)
     clause_of_edge = np.repeat(np.arange(m, dtype=np.int64), lens)
     # inside a clause: reference literal-row order (positives by variable, then negatives), stable for repeated literals
-    order = np.lexsort((var, sign, clause_of_edge))
+    order = np.argsort((clause_of_edge * 2 + sign) * max(n, 1) + var, kind="stable")
     cl_lit = (2 * var + sign)[order]
     # literal -> clauses: stable counting sort by literal code keeps clause ids ascending
     order = np.argsort(cl_lit, kind="stable")
@@ -158,21 +170,21 @@ def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause
         cl_rowptr=cl_rowptr.astype(np.int32), cl_lit=cl_lit.astype(np.int32),
         lit_rowptr=lit_rowptr.astype(np.int32), lit_clause=lit_clause.astype(np.int32),
         var_seg=np.asarray(var_seg, dtype=np.int32), clause_seg=np.asarray(clause_seg, dtype=np.int32),
-        clauses=clauses,
+        _clauses=clauses, _flat=flat, _lens=lens,
     )
 
 
 def _flatten(clauses):
     m = len(clauses)
-    lens = np.fromiter((len(c) for c in clauses), dtype=np.int64, count=m)
-    flat = np.fromiter((lit for c in clauses for lit in c), dtype=np.int64, count=int(lens.sum()))
+    lens = np.fromiter(map(len, clauses), dtype=np.int64, count=m)
+    flat = np.fromiter(itertools.chain.from_iterable(clauses), dtype=np.int64, count=int(lens.sum()))
     return lens, flat
 
 
 def build_unit_graph(n_vars: int, clauses, var_seg=None, clause_seg=None) -> UnitGraph:
     """CSR/CSC arrays of one formula (or of a union, when the segments are given)."""
     lens, flat = _flatten(clauses)
-    return _graph_from_flat(int(n_vars), lens, flat, var_seg, clause_seg, [list(map(int, c)) for c in clauses])
+    return _graph_from_flat(int(n_vars), lens, flat, var_seg, clause_seg, None)
 
 
 def build_union_graph(formulas) -> UnitGraph:
@@ -191,9 +203,7 @@ def build_union_graph(formulas) -> UnitGraph:
         clause_seg.append(clause_seg[-1] + len(clauses))
     lens = np.concatenate(lens_all) if lens_all else np.zeros(0, dtype=np.int64)
     flat = np.concatenate(flat_all) if flat_all else np.zeros(0, dtype=np.int64)
-    ptr = np.concatenate([[0], np.cumsum(lens)])
-    shifted = [flat[ptr[j]:ptr[j + 1]].tolist() for j in range(len(lens))]
-    return _graph_from_flat(off, lens, flat, var_seg, clause_seg, shifted)
+    return _graph_from_flat(off, lens, flat, var_seg, clause_seg, None)
 
 
 def unit_graph_from_reference_coo(indices, dense_shape, variables_graph=None, clauses_graph=None):
