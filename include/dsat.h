@@ -86,7 +86,11 @@ int dsat_get_precision(const dsat_ctx* ctx);
  * disjoint union.  group_graphs = graphs per early-exit batch (reference: all graphs of one TF batch,
  * model/query_sat.py:330-338); 0 means "all graphs of this context".
  * Replaces data/dimac.py:14-18,213-260 + data/SatSpecifics.py:21-69 (adjacency construction) and the
- * degree weights of model/query_sat.py:193-197. */
+ * degree weights of model/query_sat.py:193-197.
+ * Every argument is validated before the context is touched (sizes, monotone row pointers, index ranges, CSR and CSC
+ * describing the same edges): a rejected call leaves the previously bound graph in place.  Binding a graph of another
+ * shape re-plans the kernels but re-uses the context's device allocations when they are large enough; a context keeps
+ * its largest allocations until dsat_destroy. */
 int dsat_set_graph(dsat_ctx* ctx, int n_vars, int n_clauses, int nnz,
                    const int32_t* cl_rowptr, const int32_t* cl_lit,
                    const int32_t* lit_rowptr, const int32_t* lit_clause,
