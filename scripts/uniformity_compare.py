@@ -47,11 +47,12 @@ def main():
         cnf = "/tmp/uniformity_compare.cnf"
         with open(cnf, "w") as fh:
             fh.write(synth.dimacs_text(n_vars, clauses))
-        for precision in ("fp32", "bf16"):
-            sampler = DiffusionSampler(FIXTURE, cnf, precision=precision, seed=17)
+        for precision, sampling in (("fp32", "inverse_cdf"), ("fp32_simt", "inverse_cdf"), ("bf16", "inverse_cdf"), ("fp32", "gumbel")):
+            sampler = DiffusionSampler(FIXTURE, cnf, precision=precision, seed=17, sampling=sampling)
             t0 = time.time()
             hist = sampler.samples(want)
-            report("cuda " + precision, hist, models, time.time() - t0, "sat rate %.2f" % (sampler.last_stats["sat"] / sampler.last_stats["total"]))
+            report("cuda %s%s" % (precision, " gumbel" if sampling == "gumbel" else ""), hist, models, time.time() - t0,
+                   "sat rate %.2f" % (sampler.last_stats["sat"] / sampler.last_stats["total"]))
     else:
         import torch
         from oracle import querysat_oracle as O
