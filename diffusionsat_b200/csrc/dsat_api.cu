@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/dsat.h"
@@ -75,6 +76,7 @@ enum OpId { OP_V1 = 0, OP_Q2, OP_L2, OP_L3, OP_C1, OP_C2, OP_U1, OP_U2, OP_U3, O
 
 }  // namespace
 
+constexpr int SPMM_DW_CLAUSE = 2;        // int4 per clause-side row descriptor: four entries cover every clause of k<=4-SAT
 struct dsat_ctx {
     int device = 0;
     int sm_count = 148;
@@ -109,8 +111,12 @@ struct dsat_ctx {
     DevBuf<int> var_order;               // variables by descending degree (literal-side gather)
     DevBuf<unsigned short> cl_idx16, lit_idx16;   // 16-bit adjacency blocks for the shared-memory gathers (dsat_message.cuh)
     int cl_idx16_vecs = 0, lit_idx16_vecs = 0, cl_col_off = 0, lit_col_off = 0, lit_ord_off = 0;
-    DevBuf<int> cl_desc, lit_desc;       // standalone segment sums: two int4 per output row in processing order (dsat_spmm.cuh)
+    DevBuf<int> cl_desc, lit_desc, lit_desc4;   // standalone segment sums: row descriptors in processing order (dsat_spmm.cuh);
+                                                // the literal side keeps a 2-int4 and a 4-int4 form (chosen per shape)
     bool use_spmm_order = true;
+    int spmm_minb = 0, spmm_pf = -1;     // DSAT_SPMM_MINB / DSAT_SPMM_PF: 0 / -1 = per-shape default (spmm_plan)
+    int spmm_half = -1;                  // DSAT_SPMM_HALF=0|1: half the lanes per row (two chunks per lane), -1 = per-shape default
+    int spmm_lit_dw = 0;                 // DSAT_SPMM_LIT_DW=2|4: int4 per literal-side row descriptor, 0 = per-shape default
     bool use_idx16 = true;               // stage the 16-bit adjacency in the shared-memory gathers (DSAT_IDX16=0 disables)
 
     // activations
@@ -1338,6 +1344,14 @@ int dsat_create(int device, dsat_ctx** out) {
         if (e && e[0] == '0') c->use_fused = false;
         e = getenv("DSAT_SPMM_ORDER");
         if (e) c->use_spmm_order = e[0] != '0';
+        e = getenv("DSAT_SPMM_MINB");
+        if (e) c->spmm_minb = atoi(e);
+        e = getenv("DSAT_SPMM_PF");
+        if (e) c->spmm_pf = atoi(e);
+        e = getenv("DSAT_SPMM_LIT_DW");
+        if (e) c->spmm_lit_dw = atoi(e);
+        e = getenv("DSAT_SPMM_HALF");
+        if (e) c->spmm_half = atoi(e);
         e = getenv("DSAT_IDX16");
         if (e) c->use_idx16 = e[0] != '0';
         e = getenv("DSAT_SMEM_GATHER");
@@ -1369,7 +1383,7 @@ void dsat_destroy(dsat_ctx* c) {
     c->cl_rowptr.release(); c->cl_lit.release(); c->lit_rowptr.release(); c->lit_clause.release();
     c->var_seg.release(); c->clause_seg.release(); c->deg_w.release(); c->vdeg_w.release(); c->rev_w.release(); c->var_order.release();
     c->cl_idx16.release(); c->lit_idx16.release(); c->cl_idx16_vecs = c->lit_idx16_vecs = 0;
-    c->cl_desc.release(); c->lit_desc.release();
+    c->cl_desc.release(); c->lit_desc.release(); c->lit_desc4.release();
     for (auto& pm : c->prof) cudaEventDestroy(pm.ev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1604,10 +1618,12 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
         }
     }
     CK_CUDA(c, up_f(c->rev_w, rev_w));
-    {   // processing order of the standalone segment sums: rows that share their first gathered row become
-        // neighbours, so the warps of one CTA hit L1; each row's {index, entry range, scale} is packed into one int4
+    {   // processing order of the standalone segment sums: rows of equal length are grouped (the rows sharing a warp pass
+        // then run the same number of steps), and inside a length rows that share their first gathered row become
+        // neighbours, so the warps of one CTA hit L1; a row's {index, length, scale, first entry} and its first
+        // 4 * (dw - 1) gathered rows are packed into dw int4 (dsat_spmm.cuh)
         auto pack = [&](int rows, const int* rowptr, const int* col, const std::vector<float>& scale, int none,
-                        DevBuf<int>& dst) -> cudaError_t {
+                        int dw, DevBuf<int>& dst) -> cudaError_t {
             std::vector<int> ord(rows > 0 ? rows : 1, 0), key(rows > 0 ? rows : 1, 0);
             for (int j = 0; j < rows; ++j) {
                 ord[j] = j;
@@ -1616,20 +1632,25 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
                 key[j] = mn;
             }
             if (c->use_spmm_order)
-                std::stable_sort(ord.begin(), ord.begin() + rows, [&](int a, int b) { return key[a] < key[b]; });
-            std::vector<int> desc(8 * (size_t)(rows > 0 ? rows : 1), 0);
+                std::stable_sort(ord.begin(), ord.begin() + rows, [&](int a, int b) {
+                    const int la = rowptr[a + 1] - rowptr[a], lb = rowptr[b + 1] - rowptr[b];
+                    return la != lb ? la > lb : key[a] < key[b];
+                });
+            const size_t w = 4 * (size_t)dw;
+            std::vector<int> desc(w * (size_t)(rows > 0 ? rows : 1), 0);
             for (int p = 0; p < rows; ++p) {
                 const int j = ord[p], len = rowptr[j + 1] - rowptr[j];
                 int bits;
                 memcpy(&bits, &scale[j], sizeof(int));
-                int* d = &desc[8 * (size_t)p];
+                int* d = &desc[w * (size_t)p];
                 d[0] = j; d[1] = len; d[2] = bits; d[3] = rowptr[j];
-                for (int k = 0; k < 4; ++k) d[4 + k] = k < len ? col[rowptr[j] + k] : -1;
+                for (int k = 0; k < 4 * (dw - 1); ++k) d[4 + k] = k < len ? col[rowptr[j] + k] : -1;
             }
             return up_i(dst, desc.data(), desc.size());
         };
-        CK_CUDA(c, pack(n_clauses, cl_rowptr, cl_lit, rev_w, 2 * n_vars, c->cl_desc));
-        CK_CUDA(c, pack(2 * n_vars, lit_rowptr, lit_clause, deg_w, n_clauses, c->lit_desc));
+        CK_CUDA(c, pack(n_clauses, cl_rowptr, cl_lit, rev_w, 2 * n_vars, SPMM_DW_CLAUSE, c->cl_desc));
+        CK_CUDA(c, pack(2 * n_vars, lit_rowptr, lit_clause, deg_w, n_clauses, 2, c->lit_desc));
+        CK_CUDA(c, pack(2 * n_vars, lit_rowptr, lit_clause, deg_w, n_clauses, 4, c->lit_desc4));
     }
     c->has_graph = true;
     return DSAT_OK;
@@ -1873,13 +1894,53 @@ int dsat_hist_reduce(dsat_ctx* c, int chain_limit, uint64_t* keys_out, int64_t* 
 }
 
 // ------------------------------------------------------------------------------------------ SpMM
+// Instantiation of spmm_rows_kernel per shape: resident CTAs per SM (= register budget) and descriptor prefetch.
+// DSAT_SPMM_MINB=4|5|6|8 and DSAT_SPMM_PF=0|1 override the table for A/B runs.
+struct SpmmPlan { int min_blocks; bool prefetch; int desc_words; bool half_lanes; };
+static SpmmPlan spmm_plan(int forced_minb, int forced_pf, int forced_lit_dw, int forced_half, int row_bytes, bool bf16,
+                          int direction) {
+    // measured on the n = 10000 sweep (profiles/r2_spmm_variants.txt).  Clause side: registers for the gathers (no spills)
+    // and, for rows of >= 512 bytes, the prefetched descriptor; bf16 rows of >= 256 bytes run with half the lanes per row
+    // (twice the gathers in flight per warp).  Literal side: the twelve-entry descriptor for rows of <= 256 bytes, the plain
+    // 32-register kernel for 512-byte fp32 rows.
+    SpmmPlan p{8, false, direction == 0 ? SPMM_DW_CLAUSE : 2, false};
+    if (direction == 0) {
+        if (bf16) {
+            if (row_bytes == 128) p = {6, false, 2, false};
+            else p = {4, false, 2, true};
+        } else {
+            if (row_bytes == 256) p = {8, false, 2, false};
+            else if (row_bytes == 512) p = {5, true, 2, false};
+            else p = {4, true, 2, false};
+        }
+    } else {
+        if (bf16) {
+            if (row_bytes <= 256) p = {5, false, 4, false};
+            else p = {4, false, 2, true};
+        } else {
+            if (row_bytes == 256) p = {6, false, 4, false};
+            else if (row_bytes == 512) p = {8, false, 2, false};
+            else p = {5, false, 2, false};
+        }
+    }
+    const bool forced_any = forced_minb == 4 || forced_minb == 5 || forced_minb == 6 || forced_minb == 8 || forced_pf == 0 ||
+                            forced_pf == 1 || forced_lit_dw == 2 || forced_lit_dw == 4;
+    if (forced_any) p.half_lanes = false;       // an A/B run names the full-lane instantiation unless DSAT_SPMM_HALF=1
+    if (forced_minb == 4 || forced_minb == 5 || forced_minb == 6 || forced_minb == 8) p.min_blocks = forced_minb;
+    if (forced_pf == 0 || forced_pf == 1) p.prefetch = forced_pf == 1;
+    if (direction == 1 && (forced_lit_dw == 2 || forced_lit_dw == 4)) p.desc_words = forced_lit_dw;
+    if (p.desc_words == 4) p.prefetch = false;
+    if (forced_half == 0 || forced_half == 1) p.half_lanes = forced_half == 1;
+    if (p.half_lanes && row_bytes <= 512) p.desc_words = 2;
+    return p;
+}
+
 int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int feat, int dtype, int chains) {
     if (!c) return DSAT_ERR_ARG;
     CK_ARG(c, c->has_graph, "dsat_spmm: graph not set");
     CK_ARG(c, x_dev && y_dev && chains > 0 && (direction == 0 || direction == 1), "dsat_spmm: bad argument");
     CK_ARG(c, dtype == DSAT_F32 || dtype == DSAT_BF16, "dsat_spmm: dtype must be f32 or bf16");
     CK_CUDA(c, cudaSetDevice(c->device));
-    const int4* rowdesc = reinterpret_cast<const int4*>(direction == 0 ? c->cl_desc.p : c->lit_desc.p);
     const int* colidx = direction == 0 ? c->cl_lit.p : c->lit_clause.p;
     const int rows_out = direction == 0 ? c->m : 2 * c->n;
     const int rows_in = direction == 0 ? 2 * c->n : c->m;
@@ -1889,19 +1950,52 @@ int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int fe
         c->err = "feature width must be 64, 128 or 256";
         rc = DSAT_ERR_UNSUPPORTED;
     } else {
+        const SpmmPlan plan = spmm_plan(c->spmm_minb, c->spmm_pf, c->spmm_lit_dw, c->spmm_half, row_bytes, dtype == DSAT_BF16,
+                                        direction);
+        const int4* rowdesc = reinterpret_cast<const int4*>(direction == 0 ? c->cl_desc.p
+                                                            : plan.desc_words == 4 ? c->lit_desc4.p : c->lit_desc.p);
         auto launch = [&](auto kernel) {
-            const int rows_per_block = GATHER_WARPS * (row_bytes >= 512 ? 1 : 512 / row_bytes);
+            const int rows_per_block = GATHER_WARPS * (row_bytes >= 512 ? 1 : 512 / row_bytes) * (plan.half_lanes ? 2 : 1);
             const int grid = gather_grid(kernel, (long long)chains * rows_out, rows_per_block, c->sm_count);
             kernel<<<grid, GATHER_WARPS * 32, 0, c->stream>>>(rowdesc, colidx, rows_out, rows_in, chains, x_dev, y_dev);
         };
-        if (dtype == DSAT_BF16) {
-            if (row_bytes == 128) launch(spmm_rows_kernel<128, true>);
-            else if (row_bytes == 256) launch(spmm_rows_kernel<256, true>);
-            else launch(spmm_rows_kernel<512, true>);
-        } else {
-            if (row_bytes == 256) launch(spmm_rows_kernel<256, false>);
-            else if (row_bytes == 512) launch(spmm_rows_kernel<512, false>);
-            else launch(spmm_rows_kernel<1024, false>);
+        auto by_shape = [&](auto minb, auto pf, auto dwc) {
+            constexpr int MB = decltype(minb)::value;
+            constexpr bool PF = decltype(pf)::value;
+            constexpr int DW = decltype(dwc)::value;
+            if (dtype == DSAT_BF16) {
+                if (row_bytes == 128) launch(spmm_rows_kernel<128, true, MB, PF, DW>);
+                else if (row_bytes == 256) launch(spmm_rows_kernel<256, true, MB, PF, DW>);
+                else launch(spmm_rows_kernel<512, true, MB, PF, DW>);
+            } else {
+                if (row_bytes == 256) launch(spmm_rows_kernel<256, false, MB, PF, DW>);
+                else if (row_bytes == 512) launch(spmm_rows_kernel<512, false, MB, PF, DW>);
+                else launch(spmm_rows_kernel<1024, false, MB, PF, DW>);
+            }
+        };
+        const int dw = plan.desc_words;
+        if (plan.half_lanes && row_bytes <= 512) {      // half the lanes per row, two chunks per lane, 64 registers
+            if (dtype == DSAT_BF16) {
+                if (row_bytes == 128) launch(spmm_rows_kernel<128, true, 4, false, 2, 4>);
+                else if (row_bytes == 256) launch(spmm_rows_kernel<256, true, 4, false, 2, 8>);
+                else launch(spmm_rows_kernel<512, true, 4, false, 2, 16>);
+            } else {
+                if (row_bytes == 256) launch(spmm_rows_kernel<256, false, 4, false, 2, 8>);
+                else launch(spmm_rows_kernel<512, false, 4, false, 2, 16>);
+            }
+            LAUNCHED(c);
+            return DSAT_OK;
+        }
+        auto by_pf = [&](auto minb) {
+            if (dw == 4) by_shape(minb, std::false_type{}, std::integral_constant<int, 4>{});
+            else if (plan.prefetch) by_shape(minb, std::true_type{}, std::integral_constant<int, 2>{});
+            else by_shape(minb, std::false_type{}, std::integral_constant<int, 2>{});
+        };
+        switch (plan.min_blocks) {
+            case 4: by_pf(std::integral_constant<int, 4>{}); break;
+            case 5: by_pf(std::integral_constant<int, 5>{}); break;
+            case 6: by_pf(std::integral_constant<int, 6>{}); break;
+            default: by_pf(std::integral_constant<int, 8>{}); break;
         }
     }
     if (rc) return rc;
