@@ -597,6 +597,10 @@ def run_mixed(args):
     for i in range(args.formulas):          # n ~ U[3,100], k = {1 w.p. .3 | 2} + Geom(.4) (data/k_sat.py:45-46), ratio ~ 4.3
         nv = int(rng.integers(3, 101))
         formulas.append(synth.random_ksat_mixed(nv, max(1, int(4.3 * nv)), seed=1000 + i))
+    # what a loader keeps per formula: its clauses laid end to end, once (the reference trains from pre-tensorised TFRecords,
+    # data/dimac.py:129-211); batches are then cut, joined and indexed (dsat_graph_build) per step inside the timed region
+    from diffusionsat_b200 import graph as G
+    formulas = [G.flatten_formula(*f) for f in formulas]
     ctx = _lib.Context(local_rank)
     ctx.set_model(weights.init_weights(seed=1234))
     ctx.set_precision(_lib.PRECISIONS[args.precision])
@@ -622,7 +626,9 @@ def run_mixed(args):
                 "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": secs * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": PRECISION_DTYPE[args.precision], "data": "synthetic",
                 "config": {"workload": "BASELINE configs[3]: %d mixed k-SAT formulas (n ~ U[3,100]) = %d nodes in %d reference batches "
-                                       "of <= 20000 nodes, one model call (32 rounds) per batch, batches dealt to %d GPUs"
+                                       "of <= 20000 nodes, one model call (32 rounds) per batch, batches dealt to %d GPUs; "
+                                       "formulas pre-flattened once, union graph of every batch built inside the timed region "
+                                       "(native dsat_graph_build, on a helper thread under the previous batch's model call)"
                                        % (len(formulas), nodes, len(batches), world), "precision": args.precision},
                 "nodes_per_s": nodes / secs, "batches": len(batches)}
         _RESTORE_STDOUT()

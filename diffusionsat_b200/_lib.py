@@ -48,6 +48,7 @@ _SIGNATURES = {
     "dsat_get_precision": (C.c_int, [_vp]),
     "dsat_set_graph": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, C.c_int, _i32p, _i32p,
                                  C.c_int, C.c_int]),
+    "dsat_graph_build": (C.c_int, [C.c_int, C.c_int, C.c_longlong, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "dsat_model_call": (C.c_int, [_vp, C.c_float, _f32p, _i32p, _f32p, C.c_int, C.c_uint64, C.c_uint64, _f32p, _i32p,
                                   _f32p]),
     "dsat_sample": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _f32p, _i32p, _f32p, _u64p, _u8p, _i32p,

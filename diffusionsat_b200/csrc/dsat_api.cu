@@ -17,6 +17,7 @@
 #include "dsat_gemm_simt.cuh"
 #include "dsat_message.cuh"
 #include "dsat_spmm.cuh"
+#include "dsat_graph_host.cuh"
 #include "dsat_norm_head.cuh"
 #include "dsat_hist.cuh"
 #ifdef DSAT_WITH_TCGEN05
@@ -114,6 +115,9 @@ struct dsat_ctx {
     DevBuf<int> cl_desc, lit_desc, lit_desc4;   // standalone segment sums: row descriptors in processing order (dsat_spmm.cuh);
                                                 // the literal side keeps a 2-int4 and a 4-int4 form (chosen per shape)
     bool use_spmm_order = true;
+    std::vector<int32_t> h_cl_rowptr, h_cl_lit, h_lit_rowptr, h_lit_clause;     // host copy of the bound graph (ensure_spmm_desc)
+    std::vector<float> h_deg_w, h_rev_w;
+    bool spmm_desc_ready = false;
     int spmm_minb = 0, spmm_pf = -1;     // DSAT_SPMM_MINB / DSAT_SPMM_PF: 0 / -1 = per-shape default (spmm_plan)
     int spmm_half = -1;                  // DSAT_SPMM_HALF=0|1: half the lanes per row (two chunks per lane), -1 = per-shape default
     int spmm_lit_dw = 0;                 // DSAT_SPMM_LIT_DW=2|4: int4 per literal-side row descriptor, 0 = per-shape default
@@ -1618,45 +1622,41 @@ int dsat_set_graph(dsat_ctx* c, int n_vars, int n_clauses, int nnz, const int32_
         }
     }
     CK_CUDA(c, up_f(c->rev_w, rev_w));
-    {   // processing order of the standalone segment sums: rows of equal length are grouped (the rows sharing a warp pass
-        // then run the same number of steps), and inside a length rows that share their first gathered row become
-        // neighbours, so the warps of one CTA hit L1; a row's {index, length, scale, first entry} and its first
-        // 4 * (dw - 1) gathered rows are packed into dw int4 (dsat_spmm.cuh)
-        auto pack = [&](int rows, const int* rowptr, const int* col, const std::vector<float>& scale, int none,
-                        int dw, DevBuf<int>& dst) -> cudaError_t {
-            std::vector<int> ord(rows > 0 ? rows : 1, 0), key(rows > 0 ? rows : 1, 0);
-            for (int j = 0; j < rows; ++j) {
-                ord[j] = j;
-                int mn = none;
-                for (int e = rowptr[j]; e < rowptr[j + 1]; ++e) mn = col[e] < mn ? col[e] : mn;
-                key[j] = mn;
-            }
-            if (c->use_spmm_order)
-                std::stable_sort(ord.begin(), ord.begin() + rows, [&](int a, int b) {
-                    const int la = rowptr[a + 1] - rowptr[a], lb = rowptr[b + 1] - rowptr[b];
-                    return la != lb ? la > lb : key[a] < key[b];
-                });
-            const size_t w = 4 * (size_t)dw;
-            std::vector<int> desc(w * (size_t)(rows > 0 ? rows : 1), 0);
-            for (int p = 0; p < rows; ++p) {
-                const int j = ord[p], len = rowptr[j + 1] - rowptr[j];
-                int bits;
-                memcpy(&bits, &scale[j], sizeof(int));
-                int* d = &desc[w * (size_t)p];
-                d[0] = j; d[1] = len; d[2] = bits; d[3] = rowptr[j];
-                for (int k = 0; k < 4 * (dw - 1); ++k) d[4 + k] = k < len ? col[rowptr[j] + k] : -1;
-            }
-            return up_i(dst, desc.data(), desc.size());
-        };
-        CK_CUDA(c, pack(n_clauses, cl_rowptr, cl_lit, rev_w, 2 * n_vars, SPMM_DW_CLAUSE, c->cl_desc));
-        CK_CUDA(c, pack(2 * n_vars, lit_rowptr, lit_clause, deg_w, n_clauses, 2, c->lit_desc));
-        CK_CUDA(c, pack(2 * n_vars, lit_rowptr, lit_clause, deg_w, n_clauses, 4, c->lit_desc4));
-    }
+    // host copy for the row descriptors of the standalone segment sums, which are built by the first dsat_spmm call on this
+    // graph (ensure_spmm_desc): the model path never pays for them
+    c->h_cl_rowptr.assign(cl_rowptr, cl_rowptr + n_clauses + 1);
+    c->h_cl_lit.assign(cl_lit, cl_lit + nnz);
+    c->h_lit_rowptr.assign(lit_rowptr, lit_rowptr + 2 * n_vars + 1);
+    c->h_lit_clause.assign(lit_clause, lit_clause + nnz);
+    c->h_deg_w = deg_w;
+    c->h_rev_w = rev_w;
+    c->spmm_desc_ready = false;
     c->has_graph = true;
     return DSAT_OK;
 }
 
 int dsat_words_per_graph(const dsat_ctx* c) { return c ? c->words : 0; }
+
+// ---------------------------------------------------------------------------------- graph build (host)
+int dsat_graph_build(int n_vars, int n_clauses, long long nnz, const int32_t* lens, const int32_t* flat, int32_t* cl_rowptr,
+                     int32_t* cl_lit, int32_t* lit_rowptr, int32_t* lit_clause, int32_t* bad_clause) {
+    if (bad_clause) *bad_clause = -1;
+    if (n_vars < 0 || n_clauses < 0 || nnz < 0 || nnz >= (1ll << 31) || !cl_rowptr || !lit_rowptr ||
+        (n_clauses > 0 && !lens) || (nnz > 0 && (!flat || !cl_lit || !lit_clause)))
+        return DSAT_ERR_ARG;
+    long long total = 0;
+    for (int j = 0; j < n_clauses; ++j) {
+        if (lens[j] < 0) return DSAT_ERR_ARG;
+        total += lens[j];
+    }
+    if (total != nnz) return DSAT_ERR_ARG;
+    const long long rc = dsat::graph_build_host(n_vars, n_clauses, lens, flat, cl_rowptr, cl_lit, lit_rowptr, lit_clause);
+    if (rc < 0) {
+        if (bad_clause) *bad_clause = (int32_t)(-rc - 1);
+        return DSAT_ERR_ARG;
+    }
+    return DSAT_OK;
+}
 
 // ----------------------------------------------------------------------------------- model call
 int dsat_model_call(dsat_ctx* c, float noise_scale, const float* noisy_num, const int32_t* labels,
@@ -1935,12 +1935,57 @@ static SpmmPlan spmm_plan(int forced_minb, int forced_pf, int forced_lit_dw, int
     return p;
 }
 
+// Row descriptors of the standalone segment sums (dsat_spmm.cuh), built on first use after dsat_set_graph.
+// Processing order: rows of equal length are grouped (the rows sharing a warp pass then run the same number of steps), and
+// inside a length rows that share their first gathered row become neighbours, so the warps of one CTA hit L1; a row's
+// {index, length, scale, first entry} and its first 4 * (dw - 1) gathered rows are packed into dw int4.
+static int ensure_spmm_desc(dsat_ctx* c) {
+    if (c->spmm_desc_ready) return DSAT_OK;
+    auto pack = [&](int rows, const int* rowptr, const int* col, const std::vector<float>& scale, int none, int dw,
+                    DevBuf<int>& dst) -> cudaError_t {
+        std::vector<int> ord(rows > 0 ? rows : 1, 0), key(rows > 0 ? rows : 1, 0);
+        for (int j = 0; j < rows; ++j) {
+            ord[j] = j;
+            int mn = none;
+            for (int e = rowptr[j]; e < rowptr[j + 1]; ++e) mn = col[e] < mn ? col[e] : mn;
+            key[j] = mn;
+        }
+        if (c->use_spmm_order)
+            std::stable_sort(ord.begin(), ord.begin() + rows, [&](int a, int b) {
+                const int la = rowptr[a + 1] - rowptr[a], lb = rowptr[b + 1] - rowptr[b];
+                return la != lb ? la > lb : key[a] < key[b];
+            });
+        const size_t w = 4 * (size_t)dw;
+        std::vector<int> desc(w * (size_t)(rows > 0 ? rows : 1), 0);
+        for (int p = 0; p < rows; ++p) {
+            const int j = ord[p], len = rowptr[j + 1] - rowptr[j];
+            int bits;
+            memcpy(&bits, &scale[j], sizeof(int));
+            int* d = &desc[w * (size_t)p];
+            d[0] = j; d[1] = len; d[2] = bits; d[3] = rowptr[j];
+            for (int k = 0; k < 4 * (dw - 1); ++k) d[4 + k] = k < len ? col[rowptr[j] + k] : -1;
+        }
+        cudaError_t e = dst.alloc(desc.size());
+        if (e != cudaSuccess) return e;
+        return dsat_memcpy_sync(dst.p, desc.data(), desc.size() * sizeof(int), cudaMemcpyHostToDevice);
+    };
+    const int* no_col = nullptr;
+    const int* cl_col = c->h_cl_lit.empty() ? no_col : c->h_cl_lit.data();
+    const int* lit_col = c->h_lit_clause.empty() ? no_col : c->h_lit_clause.data();
+    CK_CUDA(c, pack(c->m, c->h_cl_rowptr.data(), cl_col, c->h_rev_w, 2 * c->n, SPMM_DW_CLAUSE, c->cl_desc));
+    CK_CUDA(c, pack(2 * c->n, c->h_lit_rowptr.data(), lit_col, c->h_deg_w, c->m, 2, c->lit_desc));
+    CK_CUDA(c, pack(2 * c->n, c->h_lit_rowptr.data(), lit_col, c->h_deg_w, c->m, 4, c->lit_desc4));
+    c->spmm_desc_ready = true;
+    return DSAT_OK;
+}
+
 int dsat_spmm(dsat_ctx* c, int direction, const void* x_dev, void* y_dev, int feat, int dtype, int chains) {
     if (!c) return DSAT_ERR_ARG;
     CK_ARG(c, c->has_graph, "dsat_spmm: graph not set");
     CK_ARG(c, x_dev && y_dev && chains > 0 && (direction == 0 || direction == 1), "dsat_spmm: bad argument");
     CK_ARG(c, dtype == DSAT_F32 || dtype == DSAT_BF16, "dsat_spmm: dtype must be f32 or bf16");
     CK_CUDA(c, cudaSetDevice(c->device));
+    if (int rc_desc = ensure_spmm_desc(c)) return rc_desc;
     const int* colidx = direction == 0 ? c->cl_lit.p : c->lit_clause.p;
     const int rows_out = direction == 0 ? c->m : 2 * c->n;
     const int rows_in = direction == 0 ? 2 * c->n : c->m;

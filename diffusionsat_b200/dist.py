@@ -165,7 +165,7 @@ def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_cha
 
 # --------------------------------------------------------------------------- formulas sharded over ranks
 def pack_batches(formulas, max_nodes: int = 20000):
-    """Reference batches of a list of ``(n_vars, clauses)`` formulas: greedy packing in the given order while the node
+    """Reference batches of a list of ``(n_vars, clauses)`` formulas (or ``graph.FlatFormula`` items): greedy packing in the given order while the node
     total ``sum(2n + m)`` stays <= ``max_nodes`` (reference ``data/dimac.py:172-174,267-293``; the first formula of a
     batch always fits).  The reference drops the formula that overflows a batch (``:281-287``, SURVEY Appendix A.16);
     here it opens the next batch, so no formula is lost.  Returns a list of lists of formula indices."""
@@ -190,6 +190,7 @@ def forward_formulas_sharded(make_context, formulas, noise_scale: float, rounds:
     logits are gathered on rank ``dst`` (outputs are disjoint: no reduction).  Noise and the noisy inputs are keyed by
     ``(seed, batch index)``, so the result does not depend on the number of ranks.
     Returns on ``dst`` ``(logits per formula [list of float32 arrays], steps_taken per batch [int array])``."""
+    from concurrent.futures import ThreadPoolExecutor
     from .graph import build_union_graph
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -197,13 +198,24 @@ def forward_formulas_sharded(make_context, formulas, noise_scale: float, rounds:
     sizes = [sum(int(formulas[i][0]) for i in b) for b in batches]
     ctx = make_context(rank)
     mine = {}
-    for b in range(rank, len(batches), world):
+
+    def prepare(b):
+        """Host side of batch b: the union graph and the noisy input (no device work)."""
         unit = build_union_graph([formulas[i] for i in batches[b]])
-        ctx.set_graph(unit, chains=1, group_graphs=0)            # the whole batch is one early-exit group
         bits = np.random.default_rng([seed, b]).integers(0, 2, unit.n_vars).astype(np.float32)
-        noisy = np.stack([bits, 1.0 - bits], axis=1)
-        pred, steps, _ = ctx.model_call(noise_scale, noisy, rounds=rounds, seed=seed + 7919 * (b + 1))
-        mine[b] = (pred, int(steps[0]))
+        return unit, np.stack([bits, 1.0 - bits], axis=1)
+
+    # the next batch's graph is built on a helper thread while this batch's model call runs (the call blocks in libdsat
+    # with the GIL released), so the host-side build leaves the critical path
+    my_batches = list(range(rank, len(batches), world))
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        ahead = pool.submit(prepare, my_batches[0]) if my_batches else None
+        for k, b in enumerate(my_batches):
+            unit, noisy = ahead.result()
+            ahead = pool.submit(prepare, my_batches[k + 1]) if k + 1 < len(my_batches) else None
+            ctx.set_graph(unit, chains=1, group_graphs=0)            # the whole batch is one early-exit group
+            pred, steps, _ = ctx.model_call(noise_scale, noisy, rounds=rounds, seed=seed + 7919 * (b + 1))
+            mine[b] = (pred, int(steps[0]))
     if world == 1:
         flat = {b: mine[b] for b in mine}
     else:

@@ -141,15 +141,22 @@ class UnitGraph:
         return np.concatenate([pos, neg], axis=0), (2 * n_total, chains * m)
 
 
-def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause_seg, clauses) -> UnitGraph:
-    """CSR/CSC arrays from the literals of all clauses laid end to end (``lens[j]`` literals for clause j)."""
+def _native_library():
+    """libdsat.so if it has been built (its host-side ``dsat_graph_build`` needs no GPU), else None."""
+    try:
+        from . import _lib
+        return _lib.load_library()
+    except (RuntimeError, OSError):
+        return None
+
+
+def _graph_arrays_numpy(n: int, lens: np.ndarray, flat: np.ndarray):
+    """The four index arrays by two stable argsorts over all edges (the specification ``dsat_graph_build`` is tested against)."""
     m = int(lens.shape[0])
+    lens = lens.astype(np.int64)
+    flat = flat.astype(np.int64)
     cl_rowptr = np.zeros(m + 1, dtype=np.int64)
     np.cumsum(lens, out=cl_rowptr[1:])
-    if flat.size and (np.any(flat == 0) or np.any(np.abs(flat) > n)):
-        bad = int(np.flatnonzero((flat == 0) | (np.abs(flat) > n))[0])
-        j = int(np.searchsorted(cl_rowptr, bad, side="right") - 1)
-        raise ValueError("literal out of range in clause %d: %r" % (j, flat[cl_rowptr[j]:cl_rowptr[j + 1]].tolist()))
     var = np.abs(flat) - 1
     sign = (flat < 0).astype(np.int64)
     clause_of_edge = np.repeat(np.arange(m, dtype=np.int64), lens)
@@ -161,14 +168,51 @@ def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause
     lit_clause = clause_of_edge[order]
     lit_rowptr = np.zeros(2 * n + 1, dtype=np.int64)
     np.cumsum(np.bincount(cl_lit, minlength=2 * n), out=lit_rowptr[1:])
+    return (cl_rowptr.astype(np.int32), cl_lit.astype(np.int32), lit_rowptr.astype(np.int32), lit_clause.astype(np.int32))
+
+
+def _graph_arrays_native(lib, n: int, lens: np.ndarray, flat: np.ndarray):
+    """The same arrays from ``dsat_graph_build`` (include/dsat.h): linear in the number of edges."""
+    import ctypes as C
+    m, nnz = int(lens.shape[0]), int(flat.shape[0])
+    lens32 = np.ascontiguousarray(lens, dtype=np.int32)
+    flat32 = np.ascontiguousarray(flat, dtype=np.int32)
+    cl_rowptr = np.empty(m + 1, dtype=np.int32)
+    cl_lit = np.empty(nnz, dtype=np.int32)
+    lit_rowptr = np.empty(2 * n + 1, dtype=np.int32)
+    lit_clause = np.empty(nnz, dtype=np.int32)
+    bad = C.c_int32(-1)
+    ip = C.POINTER(C.c_int32)
+    rc = lib.dsat_graph_build(n, m, nnz, *[a.ctypes.data_as(ip) for a in (lens32, flat32, cl_rowptr, cl_lit, lit_rowptr,
+                                                                           lit_clause)], C.byref(bad))
+    if rc != 0:
+        raise ValueError("dsat_graph_build failed (%d), clause %d" % (rc, bad.value))
+    return cl_rowptr, cl_lit, lit_rowptr, lit_clause
+
+
+def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause_seg, clauses, native=None) -> UnitGraph:
+    """CSR/CSC arrays from the literals of all clauses laid end to end (``lens[j]`` literals for clause j).
+
+    ``native``: None = the library's ``dsat_graph_build`` when libdsat.so is built, numpy otherwise; True / False force one."""
+    m = int(lens.shape[0])
+    if flat.size and (np.any(flat == 0) or np.any(np.abs(flat) > n)):
+        rowptr = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
+        bad = int(np.flatnonzero((flat == 0) | (np.abs(flat) > n))[0])
+        j = int(np.searchsorted(rowptr, bad, side="right") - 1)
+        raise ValueError("literal out of range in clause %d: %r" % (j, flat[rowptr[j]:rowptr[j + 1]].tolist()))
+    lib = _native_library() if native is None or native else None
+    if native and lib is None:
+        raise RuntimeError("libdsat.so is not built: no native graph build")
+    if lib is not None:
+        cl_rowptr, cl_lit, lit_rowptr, lit_clause = _graph_arrays_native(lib, n, lens, flat)
+    else:
+        cl_rowptr, cl_lit, lit_rowptr, lit_clause = _graph_arrays_numpy(n, lens, flat)
     if var_seg is None:
         var_seg = [0, n]
     if clause_seg is None:
         clause_seg = [0, m]
     return UnitGraph(
-        n_vars=n, n_clauses=m,
-        cl_rowptr=cl_rowptr.astype(np.int32), cl_lit=cl_lit.astype(np.int32),
-        lit_rowptr=lit_rowptr.astype(np.int32), lit_clause=lit_clause.astype(np.int32),
+        n_vars=n, n_clauses=m, cl_rowptr=cl_rowptr, cl_lit=cl_lit, lit_rowptr=lit_rowptr, lit_clause=lit_clause,
         var_seg=np.asarray(var_seg, dtype=np.int32), clause_seg=np.asarray(clause_seg, dtype=np.int32),
         _clauses=clauses, _flat=flat, _lens=lens,
     )
@@ -181,29 +225,59 @@ def _flatten(clauses):
     return lens, flat
 
 
-def build_unit_graph(n_vars: int, clauses, var_seg=None, clause_seg=None) -> UnitGraph:
+@dataclass
+class FlatFormula:
+    """A formula with its clauses already laid end to end (what a data loader keeps per formula, so that packing it into
+    many batches never walks Python lists again; the reference keeps pre-tensorised TFRecords, ``data/dimac.py:129-211``)."""
+
+    n_vars: int
+    lens: np.ndarray      # int32 [m]    literals per clause
+    flat: np.ndarray      # int32 [nnz]  signed 1-based literals, clause by clause
+
+    @property
+    def n_clauses(self) -> int:
+        return int(self.lens.shape[0])
+
+    def __iter__(self):                     # unpacks like the (n_vars, clauses) pair it stands for
+        yield self.n_vars
+        yield self
+
+    def __len__(self):                      # len(clauses)
+        return self.n_clauses
+
+    def __getitem__(self, i):               # formula[0] = n_vars, formula[1] = the clauses
+        return (self.n_vars, self)[i]
+
+
+def flatten_formula(n_vars: int, clauses) -> FlatFormula:
+    lens, flat = _flatten(clauses)
+    if flat.size and (np.any(flat == 0) or np.any(np.abs(flat) > int(n_vars))):
+        raise ValueError("literal out of range in a formula with %d variables" % int(n_vars))
+    return FlatFormula(int(n_vars), lens.astype(np.int32), flat.astype(np.int32))
+
+
+def build_unit_graph(n_vars: int, clauses, var_seg=None, clause_seg=None, native=None) -> UnitGraph:
     """CSR/CSC arrays of one formula (or of a union, when the segments are given)."""
     lens, flat = _flatten(clauses)
-    return _graph_from_flat(int(n_vars), lens, flat, var_seg, clause_seg, None)
+    return _graph_from_flat(int(n_vars), lens, flat, var_seg, clause_seg, None, native)
 
 
-def build_union_graph(formulas) -> UnitGraph:
-    """Disjoint union of ``[(n_vars, clauses), ...]`` with the reference's variable shift
+def build_union_graph(formulas, native=None) -> UnitGraph:
+    """Disjoint union of ``[(n_vars, clauses), ...]`` (or ``FlatFormula`` items) with the reference's variable shift
     (``data/dimac.py:165-170,239-241``): one unit whose graphs are the formulas."""
-    lens_all, flat_all, var_seg, clause_seg = [], [], [0], [0]
-    off = 0
-    for n_vars, clauses in formulas:
-        lens, flat = _flatten(clauses)
-        if flat.size and np.any(np.abs(flat) > int(n_vars)):
-            raise ValueError("literal out of range in a formula with %d variables" % int(n_vars))
-        lens_all.append(lens)
-        flat_all.append(flat + np.sign(flat) * off)
-        off += int(n_vars)
-        var_seg.append(off)
-        clause_seg.append(clause_seg[-1] + len(clauses))
-    lens = np.concatenate(lens_all) if lens_all else np.zeros(0, dtype=np.int64)
-    flat = np.concatenate(flat_all) if flat_all else np.zeros(0, dtype=np.int64)
-    return _graph_from_flat(off, lens, flat, var_seg, clause_seg, None)
+    flats = [f if isinstance(f, FlatFormula) else flatten_formula(*f) for f in formulas]
+    if not flats:
+        return _graph_from_flat(0, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), [0], [0], None, native)
+    n_per = np.fromiter((f.n_vars for f in flats), dtype=np.int64, count=len(flats))
+    m_per = np.fromiter((f.lens.shape[0] for f in flats), dtype=np.int64, count=len(flats))
+    e_per = np.fromiter((f.flat.shape[0] for f in flats), dtype=np.int64, count=len(flats))
+    var_seg = np.concatenate([[0], np.cumsum(n_per)])
+    clause_seg = np.concatenate([[0], np.cumsum(m_per)])
+    lens = np.concatenate([f.lens for f in flats])
+    flat = np.concatenate([f.flat for f in flats]).astype(np.int64)
+    shift = np.repeat(var_seg[:-1], e_per)                  # every literal moves by its formula's variable offset
+    flat = np.where(flat < 0, flat - shift, flat + shift)
+    return _graph_from_flat(int(var_seg[-1]), lens, flat, var_seg, clause_seg, None, native)
 
 
 def unit_graph_from_reference_coo(indices, dense_shape, variables_graph=None, clauses_graph=None):

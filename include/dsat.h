@@ -97,6 +97,17 @@ int dsat_set_graph(dsat_ctx* ctx, int n_vars, int n_clauses, int nnz,
                    int n_graphs, const int32_t* var_seg, const int32_t* clause_seg,
                    int n_chains, int group_graphs);
 
+/* Host-only helper (no context, no device): the index arrays dsat_set_graph takes, from the signed 1-based literals of all
+ * clauses laid end to end (lens[j] literals for clause j, sum = nnz; a disjoint union passes its formulas already shifted by
+ * their variable offsets, data/dimac.py:165-170,239-241).  cl_rowptr [n_clauses+1], cl_lit [nnz] (codes 2*var+sign, inside a
+ * clause in the order of the reference's literal rows: positives by variable, then negatives; repeated literals kept),
+ * lit_rowptr [2*n_vars+1], lit_clause [nnz] (ascending, repeats kept).  Replaces data/dimac.py:14-18 (compute_adj_indices)
+ * + data/SatSpecifics.py:21-69 (create_adj_matrices) for callers that build many graphs per second (mixed-formula batches);
+ * diffusionsat_b200/graph.py holds the same construction in numpy and the tests compare the two.
+ * A literal of magnitude 0 or > n_vars returns DSAT_ERR_ARG with *bad_clause = its clause (else -1; may be NULL). */
+int dsat_graph_build(int n_vars, int n_clauses, long long nnz, const int32_t* lens, const int32_t* flat,
+                     int32_t* cl_rowptr, int32_t* cl_lit, int32_t* lit_rowptr, int32_t* lit_clause, int32_t* bad_clause);
+
 /* One model call = QuerySAT.diffusion_step / call(training=False)  (model/query_sat.py:133-184,
  * 186-373, 467-481).  Host buffers: noisy_num [N,2]; labels [N] int32 or NULL (drawn from Philox,
  * the reference draws them with tf.random at :145); normals [rounds,N,4] or NULL (Philox; reference
