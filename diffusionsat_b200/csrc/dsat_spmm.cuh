@@ -135,6 +135,7 @@ spmm_rows_kernel(const int4* __restrict__ rowdesc, const int* __restrict__ colid
             for (int w = 0; w < DW; ++w) d[w] = spmm_ld_desc(rowdesc + DW * pos + w);
         }
         const int len = d[0].y;
+        DSAT_CHECK(c >= 0 && c < chains && d[0].x >= 0 && d[0].x < rows_out && len >= 0);
         const char* xc = reinterpret_cast<const char*>(Xv) + (size_t)c * x_chain + l * 16;
         asm("" : "+l"(xc));      // one full pointer: a gather address is then a single IMAD.WIDE (column x ROW_BYTES + xc)
         float acc[CPL][EPC];
@@ -160,8 +161,10 @@ spmm_rows_kernel(const int4* __restrict__ rowdesc, const int* __restrict__ colid
 #pragma unroll
                         for (int j = 0; j < N; ++j)
 #pragma unroll
-                            for (int k = 0; k < CPL; ++k)
+                            for (int k = 0; k < CPL; ++k) {
+                                DSAT_CHECK(col[j] >= 0 && col[j] < rows_in);
                                 x[j][k] = __ldg(reinterpret_cast<const uint4*>(xc + (size_t)col[j] * ROW_BYTES) + k * LPR);
+                            }
 #pragma unroll
                         for (int j = 0; j < N; ++j)
 #pragma unroll
@@ -200,6 +203,7 @@ spmm_rows_kernel(const int4* __restrict__ rowdesc, const int* __restrict__ colid
             const int e1 = e + len;
             for (; e + 4 <= e1; e += 4) {
                 const int c0 = __ldg(colidx + e), c1 = __ldg(colidx + e + 1), c2 = __ldg(colidx + e + 2), c3 = __ldg(colidx + e + 3);
+                DSAT_CHECK(c0 >= 0 && c0 < rows_in && c1 >= 0 && c1 < rows_in && c2 >= 0 && c2 < rows_in && c3 >= 0 && c3 < rows_in);
                 uint4 x0[CPL], x1[CPL], x2[CPL], x3[CPL];
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
