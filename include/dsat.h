@@ -135,7 +135,9 @@ int dsat_words_per_graph(const dsat_ctx* ctx);
 /* Stand-alone segment-sum SpMM on device buffers (message-passing roofline sweeps):
  * direction 0: clause <- literal   Y[c,j,:] = rev_w[j]  * sum_{lit in j} X[c,lit,:]   X [chains,2n,feat]
  * direction 1: literal <- clause   Y[c,l,:] = deg_w[l] * sum_{j contains l} X[c,j,:]  X [chains,m,feat]
- * (tf.sparse.sparse_dense_matmul call sites model/query_sat.py:255,269).  feat in {64,128,256}. */
+ * (tf.sparse.sparse_dense_matmul call sites model/query_sat.py:255,269).  feat in {64,128,256}.
+ * The first call after dsat_set_graph builds the row descriptors of the bound graph on the host and uploads them
+ * (a few ms at n = 10000); the model path never pays for them.  Sums run in entry order with fp32 accumulation. */
 int dsat_spmm(dsat_ctx* ctx, int direction, const void* x_dev, void* y_dev, int feat, int dtype, int chains);
 
 /* Histogram of the last dsat_sample / dsat_sample_enqueue run, reduced on the device: sort, unique and count of the
