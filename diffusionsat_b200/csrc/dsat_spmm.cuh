@@ -11,8 +11,8 @@
 //
 // Locality: the grid is exactly one resident wave and each warp strides over the flattened (chain, row) space,
 // so at any moment all SMs work on the same one or two chains and a chain's gathered table (<= 22 MB at
-// n = 10000) is fetched from HBM once and re-read from L2; `order` additionally makes rows that share their first
-// gathered row neighbours.  The position is advanced with a decomposed stride (RowCursor): a 64-bit division per
+// n = 10000) is fetched from HBM once and re-read from L2; the processing order additionally groups rows by length and, inside
+// a length, makes rows that share their first gathered row neighbours.  The position is advanced with a decomposed stride (RowCursor): a 64-bit division per
 // row had made the kernel issue-bound.  Sums run in entry order, fp32 accumulation.
 #pragma once
 #include "dsat_message.cuh"
@@ -68,7 +68,7 @@ __device__ __forceinline__ int4 spmm_ld_desc(const int4* p) {
 // chain, and all its gathers are issued together.  DW = 2 (four entries: every clause of k<=4-SAT) on the clause side,
 // DW = 4 (twelve entries: 98.5 % of the literals of a ratio-4.3 3-SAT formula) on the literal side, where walking colidx
 // (descriptor -> colidx -> gathers, once per four entries) had left the narrow-row shapes latency-bound.  Longer rows
-// walk colidx from the first entry.  The processing order groups rows of equal length (dsat_set_graph), so the rows that
+// walk colidx from the first entry.  The processing order groups rows of equal length (ensure_spmm_desc), so the rows that
 // share a warp pass (RPW > 1) run the same number of steps.
 //
 // MINB = resident CTAs per SM the register allocation is held to (8 -> 32 registers, 6 -> 40, 5 -> 48, 4 -> 64): the
