@@ -114,6 +114,60 @@ def mlp_flops_per_round(n_rows, m_rows, f=128, q=128):
     return 2.0 * (var_side * n_rows + clause_side * m_rows)
 
 
+def per_kernel_roofline(class_ms, n_rows, m_rows, precision, peak_tflops, peak_gbs, f=128, q=128):
+    """Both roofs for every launch class of one round: executed tensor-core FLOPs (3 bf16 MMAs per product on the
+    fp32-accurate path) against the measured bf16 rate, and ALGORITHMIC bytes (every operand row read once, every result row
+    written once; weights stay in L2) against the measured copy rate.  Which Dense layers a class covers follows
+    run_round (dsat_api.cu): fp32-accurate = whole query MLP (`query_out`), literal layers 1 / 2 / 3 (`v1_hidden`, `lit_2`,
+    `lit_3`), clause layers 1 / 2, whole update (`update_3`) and output (`output_2`) MLPs; bf16 = one launch per MLP.
+    Operands are hi/lo bf16 planes or fp32 (4 bytes per element) on the fp32-accurate path, bf16 on the bf16 path
+    (logits fp32).  Returns {class: {ms, tensor_pipe_frac, hbm_frac, bound}} for the classes that ran."""
+    from diffusionsat_b200.weights import mlp_layer_dims
+    dims = mlp_layer_dims(f, q)
+    pad = lambda x: (x + 15) // 16 * 16
+    es = 4 if precision == "fp32" else 2
+    v1, vrow = pad(f + 9), pad(f + 9) + 3 * q             # [variables | aux] and the whole variable row (update MLP input)
+    macs = lambda layers: sum(i * o for i, o in layers)
+    lq, cu = dims["lit_query"], dims["clause_update"]
+    if precision == "fp32":
+        launches = {      # class: (rows, MACs per row, input columns, output columns)
+            "query_out": (n_rows, macs(dims["variables_query"]), v1, 3 * q),
+            "v1_hidden": (n_rows, macs(lq[:1]), v1, pad(lq[0][1])),
+            "lit_2": (n_rows, macs(lq[1:2]), pad(lq[1][0]), pad(lq[1][1])),
+            "lit_3": (n_rows, macs(lq[2:]), pad(lq[2][0]), pad(lq[2][1])),
+            "clause_1": (m_rows, macs(cu[:1]), pad(cu[0][0]), pad(cu[0][1])),
+            "clause_2": (m_rows, macs(cu[1:]), pad(cu[1][0]), pad(cu[1][1])),
+            "update_3": (n_rows, macs(dims["update_gate"]), vrow, f),
+            "output_2": (n_rows, macs(dims["variables_output"]), f, 16),
+        }
+    else:
+        launches = {
+            "query_out": (n_rows, macs(dims["variables_query"]), v1, 3 * q),
+            "lit_3": (n_rows, macs(lq), v1, pad(lq[2][1])),
+            "clause_2": (m_rows, macs(cu), pad(cu[0][0]), pad(cu[1][1])),
+            "update_3": (n_rows, macs(dims["update_gate"]), vrow, f),
+            "output_2": (n_rows, macs(dims["variables_output"]), f, 16 * 4 // es),       # logits are fp32
+        }
+    mma = 3 if precision == "fp32" else 1
+    out = {}
+    for name, (rows, mac, cin, cout) in launches.items():
+        ms = class_ms.get(name)
+        if not ms:
+            continue
+        tf = mma * 2.0 * rows * mac / (ms / 1e3) / 1e12
+        gbs = rows * (cin + cout) * es / (ms / 1e3) / 1e9
+        out[name] = {"ms": ms, "tensor_pipe_frac": tf / peak_tflops, "hbm_frac": gbs / peak_gbs,
+                     "bound": "tensor" if tf / peak_tflops >= gbs / peak_gbs else "hbm"}
+    # PairNorm: read the MLP result, read the old state, write the new state (the variable side also writes the output
+    # MLP's input)
+    for name, rows, arrays in (("pairnorm_clause", m_rows, 3), ("pairnorm_var", n_rows, 4)):
+        ms = class_ms.get(name)
+        if ms:
+            out[name] = {"ms": ms, "tensor_pipe_frac": 0.0, "hbm_frac": rows * f * es * arrays / (ms / 1e3) / 1e9 / peak_gbs,
+                         "bound": "hbm"}
+    return out
+
+
 # ------------------------------------------------------------------------------------ reference arm
 def cpu_oracle_rate(batch_chains, dsteps, rounds, threads, repeats=1, warmup=0):
     """samples/s of the CPU oracle port: one reference batch, `dsteps` of 32 denoising steps, scaled."""
@@ -318,6 +372,11 @@ def measure_precision(ctx, precision, args, world, rank, local_rank, unit, batch
         "bf16_mma_per_algorithmic_product": mma_per_product,
         "tensor_pipe_frac": mma_per_product * achieved_tf / peak_tf,
         "class_ms_per_round": {k: v[0] / 4 for k, v in prof.items() if v[1]}}
+    try:        # reporting only: never let it cost the line
+        res["roofline"]["per_kernel"] = per_kernel_roofline(res["roofline"]["class_ms_per_round"], ctx.n_rows, ctx.n_clause_rows,
+                                                            precision, peak_tf, pk["hbm_gbs"])
+    except Exception as exc:
+        res["roofline"]["per_kernel_error"] = repr(exc)
     es = 4 if precision == "fp32" else 2
     q = 128
     nnz = unit.nnz
