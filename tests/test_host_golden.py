@@ -172,3 +172,31 @@ def test_is_graph_sat_matches_clause_by_clause_check():
             ok = all(any((bits[abs(l) - 1] if l > 0 else not bits[abs(l) - 1]) for l in c) for c in clauses)
             assert got[gi] == float(ok), (trial, gi)
             off += n
+
+
+def test_sat_checks_match_the_reference_functions_run_over_the_shim():
+    """``is_graph_sat`` (host, predict_step) and the oracle's ``is_batch_sat`` (early exit) against flags computed by the
+    reference's own ``utils/sat.py:118-124,165-180`` (tests/golden/make_sat_check_golden.py): unsatisfiable formula, empty
+    clause, repeated literals, logits of exactly 0 (half-to-even rounding)."""
+    import ast
+    import os
+    import torch
+    from diffusionsat_b200 import graph as G
+    from diffusionsat_b200.query_sat import is_graph_sat
+    from oracle import querysat_oracle as O
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sat_check_golden.npz"))
+    formulas = ast.literal_eval(str(gold["formulas"][0]))
+    union = G.build_union_graph(formulas)
+    coo, shape = union.reference_coo(1)
+    cg = np.repeat(np.arange(len(formulas)), [len(c) for _, c in formulas])
+    assert gold["graph_sat"].shape == (len(gold["logits"]), len(formulas))
+    assert 0 < gold["graph_sat"].sum() < gold["graph_sat"].size               # both outcomes occur
+    for z, want in zip(gold["logits"], gold["graph_sat"]):
+        np.testing.assert_array_equal(is_graph_sat(z, coo, shape, cg, len(formulas)), want)
+    off = 0
+    for g, (n_vars, clauses) in enumerate(formulas):
+        og = O.OracleGraph.from_formulas([(n_vars, clauses)])
+        for t, z in enumerate(gold["logits"]):
+            got = float(O.is_batch_sat(torch.from_numpy(z[off:off + n_vars].copy()).reshape(-1, 1), og))
+            assert got == float(gold["batch_sat_per_formula"][t, g]), (g, t)
+        off += n_vars
