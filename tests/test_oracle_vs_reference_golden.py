@@ -63,3 +63,24 @@ def test_diffusion_loop_matches_reference_source(tag):
                                 torch.from_numpy(c["labels"].astype(np.int64)), torch.from_numpy(c["normals"]), c["rounds"])
     np.testing.assert_array_equal(final, c["predictions"])
     assert acc == pytest.approx(c["accuracy"])
+
+
+UNION = np.load(os.path.join(os.path.dirname(__file__), "golden", "union_golden.npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("tag", ["u", "v"])
+def test_union_batch_model_call_matches_reference_source(tag):
+    """Disjoint unions of DIFFERENT formulas (tests/golden/make_union_golden.py): graphs of unequal size in one batch, as in
+    training batches and predict_step -- per-graph PairNorm statistics, per-graph logit-map choice, whole-batch early exit."""
+    g = lambda k: UNION["%s_%s" % (tag, k)]
+    formulas = ast.literal_eval(str(g("formulas")[0]))
+    graph = O.OracleGraph.from_formulas(formulas)
+    assert graph.n_vars == sum(n for n, _ in formulas)
+    w = O.weights_to_torch(W.init_weights(seed=int(g("wseed")), bias_scale=0.1))
+    noisy = O.randomized_rounding(torch.full((graph.n_vars, 2), 0.5), torch.from_numpy(g("uniform")))
+    np.testing.assert_array_equal(noisy.numpy(), g("noisy"))
+    out = O.model_call(graph, w, float(g("noise_scale")), noisy, torch.from_numpy(g("labels").astype(np.int64)),
+                       torch.from_numpy(g("normals")), int(g("rounds")))
+    assert out["steps_taken"] == int(g("steps_taken"))
+    np.testing.assert_allclose(out["prediction"].numpy(), g("prediction"), rtol=2e-4, atol=2e-5)
+    assert float(out["loss"]) == pytest.approx(float(g("loss")), rel=1e-4)
