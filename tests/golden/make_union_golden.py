@@ -62,8 +62,30 @@ def main():
             f"{tag}_steps_taken": int(res["steps_taken"]), f"{tag}_loss": np.float32(float(res["loss"])),
         })
         print("union", tag, "graphs", len(formulas), "variables", n, "steps_taken", int(res["steps_taken"]), "loss", float(res["loss"]))
+    out.update(predict_tries_golden())
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
+
+
+def predict_tries_golden():
+    """``predict_step`` with ``prediction_tries = 3`` (reference model/query_sat.py:424-451) on the REFERENCE's class with its
+    ``call`` replaced by a stub that returns three given logit vectors: pins the bookkeeping around the calls (is_graph_sat per
+    try, "newly solved" clipping, per-variable masks, zeros for graphs never solved).  Stored next to the union cases."""
+    rng = np.random.default_rng(4242)
+    formulas = [synth.random_ksat_mixed(n, m, seed=70 + i) for i, (n, m) in enumerate([(4, 5), (6, 9), (3, 3), (5, 14), (4, 4)])]
+    formulas.append((2, [[1], [-1]]))                       # never satisfiable: its variables must end as zeros
+    union, adj, cg, vg = union_inputs(formulas)
+    tries = 3
+    logits = (rng.standard_normal((tries, union.n_vars, 1)) * 2).astype(np.float32)
+    model = M.build_model(W.init_weights(seed=1, bias_scale=0.1), 2)
+    model.prediction_tries = tries
+    feed = iter(logits)
+    model.call = lambda *a, **k: (torch.from_numpy(next(feed)), torch.tensor(0.25), 7)
+    res = model.predict_step(adj, cg, vg, None)
+    pred = res["prediction"].detach().numpy()
+    print("predict_step tries: solved variables", int((pred != 0).sum()), "of", union.n_vars)
+    return {"p_formulas": np.array([str(formulas)]), "p_logits": logits, "p_prediction": pred.astype(np.float32),
+            "p_steps_taken": int(res["steps_taken"]), "p_loss": np.float32(float(res["loss"]))}
 
 
 if __name__ == "__main__":

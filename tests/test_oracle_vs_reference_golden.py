@@ -84,3 +84,25 @@ def test_union_batch_model_call_matches_reference_source(tag):
     assert out["steps_taken"] == int(g("steps_taken"))
     np.testing.assert_allclose(out["prediction"].numpy(), g("prediction"), rtol=2e-4, atol=2e-5)
     assert float(out["loss"]) == pytest.approx(float(g("loss")), rel=1e-4)
+
+
+def test_predict_step_tries_bookkeeping_matches_reference_source():
+    """``QuerySAT.predict_step`` with ``prediction_tries = 3`` (reference model/query_sat.py:424-451): the host bookkeeping
+    around the model calls -- per-try ``is_graph_sat``, "newly solved" clipping, per-variable masks, zeros for graphs never
+    solved -- against the reference's own method run with the same three stubbed logit vectors."""
+    from diffusionsat_b200 import graph as G
+    from diffusionsat_b200.query_sat import QuerySAT
+    formulas = ast.literal_eval(str(UNION["p_formulas"][0]))
+    union = G.build_union_graph(formulas)
+    coo, shape = union.reference_coo(1)
+    vg = np.repeat(np.arange(len(formulas)), [n for n, _ in formulas])
+    cg = np.repeat(np.arange(len(formulas)), [len(c) for _, c in formulas])
+    model = QuerySAT.__new__(QuerySAT)                      # no GPU context: only the bookkeeping is under test
+    model.prediction_tries = int(UNION["p_logits"].shape[0])
+    feed = iter(UNION["p_logits"])
+    model.call = lambda *a, **k: (next(feed).copy(), np.float32(0.25), 7)
+    res = model.predict_step((coo, shape), cg, vg)
+    np.testing.assert_array_equal(res["prediction"], UNION["p_prediction"])
+    assert res["steps_taken"] == int(UNION["p_steps_taken"]) and float(res["loss"]) == float(UNION["p_loss"])
+    never = slice(union.n_vars - 2, union.n_vars)           # the unsatisfiable last formula keeps zeros
+    assert not res["prediction"][never].any() and res["prediction"].any()
