@@ -200,3 +200,25 @@ def test_sat_checks_match_the_reference_functions_run_over_the_shim():
             got = float(O.is_batch_sat(torch.from_numpy(z[off:off + n_vars].copy()).reshape(-1, 1), og))
             assert got == float(gold["batch_sat_per_formula"][t, g]), (g, t)
         off += n_vars
+
+
+def test_input_helpers_match_the_reference_functions_run_over_the_shim():
+    """numpy restatements in diffusionsat_b200/query_sat.py against the reference's module-level helpers
+    (model/query_sat.py:55-82, tests/golden/make_helper_golden.py) with the same injected uniform draws."""
+    import os
+    from diffusionsat_b200 import query_sat as Q
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "helper_golden.npz"))
+    assert Q.t_power == float(gold["t_power"])
+    np.testing.assert_array_equal(Q.randomized_rounding_tf(gold["rr_x"], noise=gold["rr_u"]), gold["rr_out"])
+    assert gold["rr_out"][:4, 0].tolist() == [0.0, 1.0, 1.0, 1.0]           # floor(x0 + u) on the boundaries
+    for i in range(3):
+        np.testing.assert_allclose(Q.distribution_at_time(gold["rr_x"], np.float32(gold["dat_%d_t" % i])),
+                                   gold["dat_%d_out" % i], rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(Q.add_t_emb(gold["rr_x"], 0.625), gold["emb_out"])
+
+    class Feed:                                     # the generator fed the same uniforms to every call
+        def random(self, shape, dtype=np.float32):
+            return gold["rr_u"].reshape(shape).astype(dtype)
+    for i in range(3):
+        got = Q.construct_training_input(gold["cti_bits"], float(gold["cti_%d_t" % i]), rng=Feed())
+        np.testing.assert_array_equal(got, gold["cti_%d_out" % i])
