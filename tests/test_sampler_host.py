@@ -94,3 +94,41 @@ def test_launch_sizing_rules():
     assert s._launch_chains(10 ** 9, chains_left=4096) == 4096   # 4 chains left over ride along as a partial group
     assert s._launch_chains(10 ** 9, chains_left=10000) == 4092
     assert s._launch_chains(10 ** 9, chains_left=20) == 20
+
+
+def test_stop_rules_and_histogram_match_the_reference_samples_loop():
+    """The sampler's host logic -- reference batches consumed in order with ``consume_batches``, histogram of the consumed
+    satisfying chains -- replayed on the assignments that the REFERENCE's own ``samples()`` loop was fed
+    (tests/golden/make_samples_golden.py: satuniformity/DiffusionSampler.py:229-311 over the TF stand-in, ``diffusion()``
+    stubbed).  The histogram must not depend on how many reference batches a launch holds."""
+    import ast
+    import os
+    from diffusionsat_b200.variable_assignment import VariableAssignment
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "samples_golden.npz"))
+    n_vars, graphs = int(gold["n_vars"]), int(gold["graphs"])
+    clauses = ast.literal_eval(str(gold["clauses"][0]))
+
+    def encode(bits):
+        asgn = VariableAssignment(clauses=clauses)
+        asgn.assign_all_from_bit_list([float(b) for b in bits])
+        return int(asgn), asgn.satisfiable()
+
+    for name in ("mixed", "unsat_first"):
+        batches = gold[name + "_batches"]
+        chains = batches.reshape(len(batches) * graphs, n_vars)
+        coded = [encode(row) for row in chains]
+        for n_samples in (1, 5, 17, 1000):
+            want = dict(zip(gold["%s_%d_keys" % (name, n_samples)].tolist(), gold["%s_%d_counts" % (name, n_samples)].tolist()))
+            for per_launch in (1, 2, 5, len(batches)):
+                hist, total, sat_total, need, pos, stop = {}, 0, 0, n_samples, 0, False
+                while need > 0 and not stop and pos < len(coded):
+                    launch = coded[pos:pos + per_launch * graphs]
+                    flags = np.array([s for _, s in launch], dtype=np.uint8)
+                    used, sat_used, stop = consume_batches(flags, graphs, need, total, sat_total)
+                    for key, sat in launch[:used]:
+                        if sat:
+                            hist[key] = hist.get(key, 0) + 1
+                    total, sat_total, need, pos = total + used, sat_total + sat_used, need - sat_used, pos + per_launch * graphs
+                assert hist == want, (name, n_samples, per_launch)
+                assert stop == bool(gold["%s_%d_aborted" % (name, n_samples)]), (name, n_samples, per_launch)
+    assert sum(gold["mixed_5_counts"]) == 5 and not len(gold["unsat_first_1000_keys"])
