@@ -164,17 +164,21 @@ def sample_chains_sharded(make_context, unit_graph, total_chains: int, batch_cha
 
 
 # --------------------------------------------------------------------------- formulas sharded over ranks
-def pack_batches(formulas, max_nodes: int = 20000):
-    """Reference batches of a list of ``(n_vars, clauses)`` formulas (or ``graph.FlatFormula`` items): greedy packing in the given order while the node
-    total ``sum(2n + m)`` stays <= ``max_nodes`` (reference ``data/dimac.py:172-174,267-293``; the first formula of a
-    batch always fits).  The reference drops the formula that overflows a batch (``:281-287``, SURVEY Appendix A.16);
-    here it opens the next batch, so no formula is lost.  Returns a list of lists of formula indices."""
+def pack_batches(formulas, max_nodes: int = 20000, drop_overflow: bool = False):
+    """Reference batches of a list of ``(n_vars, clauses)`` formulas (or ``graph.FlatFormula`` items): greedy packing in the
+    given order while the node total ``sum(2n + m)`` stays <= ``max_nodes`` (reference ``data/dimac.py:172-174,267-293``; the
+    first formula of a batch always fits).  The reference drops the formula that overflows a batch (``:281-287``, SURVEY
+    Appendix A.16); here it opens the next batch, so no formula is lost.  ``drop_overflow=True`` reproduces the reference's
+    batches exactly (pinned against its own code in tests/golden/batching_golden.json).  Returns a list of lists of formula
+    indices."""
     batches, cur, nodes = [], [], 0
     for i, (n_vars, clauses) in enumerate(formulas):
         cost = 2 * int(n_vars) + len(clauses)
         if cur and nodes + cost > max_nodes:
             batches.append(cur)
             cur, nodes = [], 0
+            if drop_overflow:
+                continue
         cur.append(i)
         nodes += cost
     if cur:

@@ -222,3 +222,35 @@ def test_input_helpers_match_the_reference_functions_run_over_the_shim():
     for i in range(3):
         got = Q.construct_training_input(gold["cti_bits"], float(gold["cti_%d_t" % i]), rng=Feed())
         np.testing.assert_array_equal(got, gold["cti_%d_out" % i])
+
+
+def test_batching_rules_match_the_reference_code():
+    """``chains_per_reference_batch``, ``pack_batches`` and the variable shift of ``build_union_graph`` against the
+    reference's own ``BatchedDimacsDataset`` methods (data/dimac.py:165-174,267-293; tests/golden/make_batching_golden.py)."""
+    import json
+    import os
+    from diffusionsat_b200 import dist as D, graph as G
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batching_golden.json")))
+    for c in gold["copies"]:
+        assert G.sat_node_count(c["n_vars"], c["n_clauses"]) == c["nodes"]
+        got = G.chains_per_reference_batch(c["n_vars"], c["n_clauses"], c["max_nodes"])
+        assert got == c["first_batch"] and all(b == got for b in c["batch_sizes"]), c
+    assert [c["first_batch"] for c in gold["copies"] if c["max_nodes"] == 20000][:3] == [103, 31, 12]     # n = 30, 100, 250
+
+    class Sized:                                    # only len() of the clause list matters to the packing rule
+        def __init__(self, m):
+            self.m = m
+
+        def __len__(self):
+            return self.m
+    for m in gold["mixed"]:
+        formulas = [(n, Sized(k)) for n, k in m["sizes"]]
+        assert D.pack_batches(formulas, m["max_nodes"], drop_overflow=True) == m["batches"]
+        ours = D.pack_batches(formulas, m["max_nodes"])
+        assert [i for b in ours for i in b] == list(range(len(formulas)))                  # the default loses nothing
+        assert ours[0] == m["batches"][0]                                                  # identical up to the first drop
+        assert m["dropped"] and m["dropped"][0] == ours[1][0]                               # ... which opens our second batch
+    for s in gold["shift"]:
+        union = G.build_union_graph([(s["offset"], [[1]] if s["offset"] else []), (3, s["clauses"])]) if s["offset"] \
+            else G.build_union_graph([(3, s["clauses"])])
+        assert union.clauses[-len(s["clauses"]):] == s["shifted"]
