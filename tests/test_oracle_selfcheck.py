@@ -56,7 +56,7 @@ def test_batch_of_copies_equals_independent_runs():
         rows = slice(c * n_vars, (c + 1) * n_vars)
         part = O.model_loop(one, w, 0.3, torch.from_numpy(noisy[rows]), labels[rows],
                             torch.from_numpy(noise["normals"][:, rows]), 2, dtype=torch.float64)
-        assert torch.allclose(full[3][rows], part[3], rtol=1e-10, atol=1e-12)     # per-graph ops only
+        assert torch.allclose(full[3][rows], part[3], rtol=1e-8, atol=1e-10)     # per-graph ops only
 
 
 def test_clause_loss_is_unsat_probability_and_negation_flips_it():
