@@ -55,6 +55,8 @@ def _t(x, dtype=None):
 def _dims(shape):
     if isinstance(shape, torch.Tensor):
         return [int(v) for v in shape.reshape(-1)]
+    if isinstance(shape, (int, np.integer)):           # tf.ones(n): a scalar shape is a vector length
+        return [int(shape)]
     return [int(v) for v in shape]
 
 
@@ -376,6 +378,7 @@ def install():
     tf.reduce_sum, tf.reduce_mean, tf.reduce_min, tf.argmin = reduce_sum, reduce_mean, reduce_min, argmin
     tf.gather, tf.stop_gradient, tf.one_hot, tf.clip_by_value, tf.stack = gather, stop_gradient, one_hot, clip_by_value, stack
     tf.range = tf_range
+    tf.repeat = lambda x, repeats, axis=None: torch.repeat_interleave(_t(x), _t(repeats, int64), dim=axis)
     tf.round = lambda x: torch.round(_t(x))                      # half-to-even, like tf.round
     tf.floor = lambda x: torch.floor(_t(x))
     tf.sigmoid = lambda x: torch.sigmoid(_t(x))

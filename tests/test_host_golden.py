@@ -254,3 +254,31 @@ def test_batching_rules_match_the_reference_code():
         union = G.build_union_graph([(s["offset"], [[1]] if s["offset"] else []), (3, s["clauses"])]) if s["offset"] \
             else G.build_union_graph([(3, s["clauses"])])
         assert union.clauses[-len(s["clauses"]):] == s["shifted"]
+
+
+@pytest.mark.parametrize("tag", ["mixed", "edge", "copies"])
+def test_batch_tensors_match_the_reference_create_adj_matrices(tag):
+    """The reference-layout COO of a union (``UnitGraph.reference_coo``), its way back (``unit_graph_from_reference_coo``) and
+    the membership adapters against ``SatSpecifics.create_adj_matrices`` run on ``shift_clause`` + ``compute_adj_indices``
+    output (data/SatSpecifics.py:21-69, data/dimac.py:165-170,239-241; tests/golden/make_adjacency_golden.py)."""
+    import ast
+    import os
+    from diffusionsat_b200 import graph as G
+    from diffusionsat_b200.query_sat import _coo, _graph_ids
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adjacency_golden.npz"))
+    formulas = ast.literal_eval(str(gold[tag + "_formulas"][0]))
+    union = G.build_union_graph(formulas)
+    coo, shape = union.reference_coo(1)
+    np.testing.assert_array_equal(coo, gold[tag + "_adj_indices"])             # same pairs in the same storage order
+    assert tuple(shape) == tuple(gold[tag + "_adj_shape"].tolist())
+    # membership matrices -> per-node graph ids
+    vg, n_graphs = _graph_ids((gold[tag + "_vg_indices"], gold[tag + "_vg_shape"]), union.n_vars)
+    cg, n_graphs_c = _graph_ids((gold[tag + "_cg_indices"], gold[tag + "_cg_shape"]), union.n_clauses)
+    assert n_graphs == n_graphs_c == len(formulas)
+    np.testing.assert_array_equal(vg, np.repeat(np.arange(len(formulas)), [n for n, _ in formulas]))
+    np.testing.assert_array_equal(cg, np.repeat(np.arange(len(formulas)), [len(c) for _, c in formulas]))
+    # and back: the graph rebuilt from the reference's tensors is the graph built from the formulas
+    idx, shp = _coo((gold[tag + "_adj_indices"], gold[tag + "_adj_shape"]))
+    back = G.unit_graph_from_reference_coo(idx, shp, vg, cg)
+    for name in ("cl_rowptr", "cl_lit", "lit_rowptr", "lit_clause", "var_seg", "clause_seg"):
+        np.testing.assert_array_equal(getattr(back, name), getattr(union, name), err_msg=name)
