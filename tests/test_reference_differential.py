@@ -64,3 +64,28 @@ def test_variable_assignment_agrees_with_the_reference_class(case):
         b.assign_all_from_int(int(a))
         out.append((int(a), bool(a.satisfiable()), str(a), list(a.as_int_list()), b.values() == a.values()))
     assert out[0] == out[1]
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.dictionaries(st.integers(0, 12), st.integers(1, 40), min_size=1, max_size=8),
+       st.dictionaries(st.integers(0, 12), st.integers(1, 40), min_size=1, max_size=8))
+def test_chi_square_agrees_with_the_reference_function(observed, expected):
+    import math
+    import warnings
+    from diffusionsat_b200.uniformity import chi_square_likelihood
+    _ref()
+    from utils.chi_square import chi_square_likelihood as ref_chi
+
+    def run(fn):
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                return ("ok", float(fn(dict(observed), dict(expected))))
+        except Exception as exc:        # noqa: BLE001 - scipy rejects sums that differ; both sides must do the same
+            return ("error", type(exc).__name__)
+    a, b = run(chi_square_likelihood), run(ref_chi)
+    assert a[0] == b[0]
+    if a[0] == "ok":
+        assert (math.isnan(a[1]) and math.isnan(b[1])) or a[1] == pytest.approx(b[1], rel=1e-12, abs=1e-300)
+    else:
+        assert a[1] == b[1]
