@@ -51,3 +51,27 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle", text, flags=re.M), f
+
+
+def test_ctypes_prototypes_have_the_arity_of_the_header_declarations():
+    """Every prototype in include/*.h against the ctypes declaration that binds it: same number of parameters, pointer
+    parameters bound as pointers (a drifted binding would pass garbage across the C ABI without any error)."""
+    import ctypes as C
+    from diffusionsat_b200 import _lib
+    text = ""
+    for h in ("dsat.h", "dsat_debug.h"):
+        text += re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", h)).read(), flags=re.S)
+    protos = re.findall(r"\b(dsat_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 20
+    seen = set()
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        res, argtypes = _lib._SIGNATURES[name]
+        assert len(argtypes) == len(plist), "%s: header has %d parameters, ctypes binding %d" % (name, len(plist), len(argtypes))
+        for decl, ctype in zip(plist, argtypes):
+            is_ptr = "*" in decl
+            bound_ptr = ctype in (C.c_void_p, C.c_char_p) or hasattr(ctype, "contents") or issubclass(ctype, C._Pointer)
+            assert is_ptr == bound_ptr, "%s: parameter %r bound as %r" % (name, decl, ctype)
+        seen.add(name)
+    assert seen == set(_lib.EXPORTED_SYMBOLS)
