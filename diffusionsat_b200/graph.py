@@ -195,6 +195,8 @@ def _graph_from_flat(n: int, lens: np.ndarray, flat: np.ndarray, var_seg, clause
 
     ``native``: None = the library's ``dsat_graph_build`` when libdsat.so is built, numpy otherwise; True / False force one."""
     m = int(lens.shape[0])
+    if 2 * n + 1 >= 2 ** 31 or int(flat.shape[0]) >= 2 ** 31 or m + 1 >= 2 ** 31:
+        raise ValueError("graph too large for 32-bit index arrays (%d variables, %d clauses, %d literals)" % (n, m, flat.shape[0]))
     if flat.size and (np.any(flat == 0) or np.any(np.abs(flat) > n)):
         rowptr = np.concatenate([[0], np.cumsum(lens, dtype=np.int64)])
         bad = int(np.flatnonzero((flat == 0) | (np.abs(flat) > n))[0])
